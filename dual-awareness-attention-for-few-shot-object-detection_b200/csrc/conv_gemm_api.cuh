@@ -1,0 +1,177 @@
+// Host launcher of the tcgen05 implicit-GEMM kernel: validates the request, picks the
+// output tile, encodes the TMA tensor maps and launches one persistent CTA per SM.
+#pragma once
+#include <stdlib.h>
+
+#include "api_common.cuh"
+#include "conv_gemm.cuh"
+
+namespace dana {
+
+struct TileChoice {
+  int bw, bh, bn;
+};
+
+// Pick (bw, bh, bn) with bw*bh*bn == 128 (powers of two) minimising padded work.
+inline TileChoice choose_tile(int w, int h, int n, bool batched_b) {
+  TileChoice best{128, 1, 1};
+  long long best_cost = -1;
+  for (int bw = 1; bw <= 128; bw <<= 1) {
+    for (int bh = 1; bw * bh <= 128; bh <<= 1) {
+      const int bn = 128 / (bw * bh);
+      if (batched_b && bn != 1) continue;
+      const long long tx = (w + bw - 1) / bw, ty = (h + bh - 1) / bh, tn = (n + bn - 1) / bn;
+      const long long cost = tx * ty * tn;
+      // prefer wider rows on ties (longer contiguous TMA runs)
+      if (best_cost < 0 || cost < best_cost || (cost == best_cost && bw > best.bw)) {
+        best_cost = cost;
+        best = TileChoice{bw, bh, bn};
+      }
+    }
+  }
+  return best;
+}
+
+template <int BLOCK_N, int NSPLIT>
+inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  conv_gemm_kernel<BLOCK_N, NSPLIT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
+inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream) {
+  if (a == nullptr || a->a_hi == nullptr || a->b_hi == nullptr) return DANA_EINVAL;
+  if ((a->a_lo == nullptr) != (a->b_lo == nullptr)) return DANA_EINVAL;
+  if (a->out_hi == nullptr && a->out_f32 == nullptr) return DANA_EINVAL;
+  if (a->n_out <= 0 || a->a_c <= 0 || a->out_w <= 0 || a->out_h <= 0 || a->out_n <= 0) return DANA_EINVAL;
+  const int taps = a->taps_r * a->taps_s;
+  if (taps != 1 && taps != 9) return DANA_ENOTSUP;
+  if (taps > 1 && (a->a_c % 64) != 0) return DANA_EINVAL;
+  // TMA alignment rules: 16-byte base and strides
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(a->a_hi) || !al16(a->b_hi) || (a->a_lo && !al16(a->a_lo)) || (a->b_lo && !al16(a->b_lo)))
+    return DANA_EINVAL;
+  if ((a->a_sx % 8) || (a->a_sy % 8) || (a->a_sn % 8) || (a->b_pitch % 8) || (a->b_batch_stride % 8))
+    return DANA_EINVAL;
+  const bool batched = a->b_batch_stride != 0;
+
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  TileChoice tc{a->tile_w, a->tile_h, a->tile_n};
+  if (tc.bw <= 0 || tc.bh <= 0 || tc.bn <= 0)
+    tc = choose_tile(a->out_w, a->out_h, a->out_n, batched || a->bias_sn != 0);
+  if (tc.bw * tc.bh * tc.bn != 128 || (batched && tc.bn != 1)) return DANA_EINVAL;
+  p.bw = tc.bw;
+  p.bh = tc.bh;
+  p.bn = tc.bn;
+  p.tiles_x = (a->out_w + tc.bw - 1) / tc.bw;
+  p.tiles_y = (a->out_h + tc.bh - 1) / tc.bh;
+  p.tiles_n = (a->out_n + tc.bn - 1) / tc.bn;
+  p.taps_r = a->taps_r;
+  p.taps_s = a->taps_s;
+  p.pad = a->pad;
+  p.c_in = static_cast<int>(a->a_c);
+  p.c_blocks = static_cast<int>((a->a_c + 63) / 64);
+  p.n_out = a->n_out;
+  p.out_w = a->out_w;
+  p.out_h = a->out_h;
+  p.out_n = a->out_n;
+  p.so_x = a->o_sx;
+  p.so_y = a->o_sy;
+  p.so_n = a->o_sn;
+  p.sr_x = a->r_sx;
+  p.sr_y = a->r_sy;
+  p.sr_n = a->r_sn;
+  p.b_batched = batched ? 1 : 0;
+  p.bias_sn = a->bias_sn;
+  if (a->bias_sn != 0 && tc.bn != 1) return DANA_EINVAL;
+  p.relu = a->relu;
+  p.alpha = a->alpha;
+  p.scale = a->scale;
+  p.bias = a->bias;
+  p.res_hi = static_cast<const __nv_bfloat16*>(a->res_hi);
+  p.res_lo = static_cast<const __nv_bfloat16*>(a->res_lo);
+  p.res_f32 = a->res_f32;
+  p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
+  p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);
+  p.out_f32 = a->out_f32;
+
+  // BLOCK_N heuristic: waves(tiles) * columns * per-column cost (narrow tiles are smem-read bound)
+  const long long sp_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
+  const int sms = sm_count();
+  int block_n = 64;
+  {
+    double best = -1.0;
+    const int cand[3] = {256, 128, 64};
+    const double percol[3] = {0.5, 0.64, 0.80};
+    for (int i = 0; i < 3; ++i) {
+      const int bn_ = cand[i];
+      if (bn_ > 64 && a->n_out <= bn_ / 2) continue;
+      const long long tiles = sp_tiles * ((a->n_out + bn_ - 1) / bn_);
+      const long long waves = (tiles + sms - 1) / sms;
+      const double cost = static_cast<double>(waves) * (bn_ * percol[i] + 24.0);
+      if (best < 0 || cost < best) {
+        best = cost;
+        block_n = bn_;
+      }
+    }
+    const char* env = getenv("DANA_BLOCK_N");
+    if (env != nullptr) {
+      const int v = atoi(env);
+      if (v == 64 || v == 128 || v == 256) block_n = v;
+    }
+  }
+  p.tiles_co = (a->n_out + block_n - 1) / block_n;
+
+  // tensor maps
+  const int nsplit = (a->a_lo != nullptr) ? 2 : 1;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(a->a_c), static_cast<uint64_t>(a->a_w),
+                              static_cast<uint64_t>(a->a_h), static_cast<uint64_t>(a->a_n)};
+    const uint64_t str[3] = {static_cast<uint64_t>(a->a_sx) * 2, static_cast<uint64_t>(a->a_sy) * 2,
+                             static_cast<uint64_t>(a->a_sn) * 2};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(tc.bw), static_cast<uint32_t>(tc.bh),
+                             static_cast<uint32_t>(tc.bn)};
+    int rc = encode_bf16_map(&p.tm_a_hi, a->a_hi, 4, dims, str, box);
+    if (rc != DANA_OK) return rc;
+    if (nsplit == 2) {
+      rc = encode_bf16_map(&p.tm_a_lo, a->a_lo, 4, dims, str, box);
+      if (rc != DANA_OK) return rc;
+    }
+  }
+  {
+    const uint64_t k_total = static_cast<uint64_t>(taps) * static_cast<uint64_t>(a->a_c);
+    const uint64_t nb = batched ? static_cast<uint64_t>(a->out_n) : 1;
+    const uint64_t dims[3] = {k_total, static_cast<uint64_t>(a->n_out), nb};
+    const uint64_t bs = batched ? static_cast<uint64_t>(a->b_batch_stride)
+                                : static_cast<uint64_t>(a->b_pitch) * static_cast<uint64_t>(a->n_out);
+    const uint64_t str[2] = {static_cast<uint64_t>(a->b_pitch) * 2, ((bs * 2 + 15) / 16) * 16};
+    const uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+    int rc = encode_bf16_map(&p.tm_b_hi, a->b_hi, 3, dims, str, box);
+    if (rc != DANA_OK) return rc;
+    if (nsplit == 2) {
+      rc = encode_bf16_map(&p.tm_b_lo, a->b_lo, 3, dims, str, box);
+      if (rc != DANA_OK) return rc;
+    }
+  }
+
+  const long long num_tiles = sp_tiles * p.tiles_co;
+  const int grid = static_cast<int>(num_tiles < sms ? num_tiles : sms);
+  if (nsplit == 1) {
+    if (block_n == 256) return launch_conv_gemm<256, 1>(p, grid, stream);
+    if (block_n == 128) return launch_conv_gemm<128, 1>(p, grid, stream);
+    return launch_conv_gemm<64, 1>(p, grid, stream);
+  }
+  if (block_n == 256) return launch_conv_gemm<256, 2>(p, grid, stream);
+  if (block_n == 128) return launch_conv_gemm<128, 2>(p, grid, stream);
+  return launch_conv_gemm<64, 2>(p, grid, stream);
+}
+
+}  // namespace dana

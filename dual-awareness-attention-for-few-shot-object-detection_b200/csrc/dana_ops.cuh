@@ -1,0 +1,449 @@
+// CUDA-core kernels around the tensor-core GEMMs of the DAnA forward path: the 7x7 stem with
+// fused BN+ReLU+max-pool, support-side BA block and unary term, positional encoding,
+// mean-centering, the attention softmax, RPN pair softmax, small pooling / conversion kernels.
+// Every kernel cites the reference lines it restates.
+#pragma once
+#include "api_common.cuh"
+#include "tc_common.cuh"
+
+namespace dana {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float ld_pair(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long i) {
+  float v = __bfloat162float(hi[i]);
+  if (lo != nullptr) v += __bfloat162float(lo[i]);
+  return v;
+}
+__device__ __forceinline__ void st_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, long long i, float v) {
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  hi[i] = h;
+  if (lo != nullptr) lo[i] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem: conv1 7x7/2 pad 3 (3->64, no bias) + frozen BN + ReLU + MaxPool 3x3/2 pad 0 ceil_mode
+// (lib/model/framework/resnet.py:109-113, dana.py:344).  Input NCHW fp32, output NHWC bf16 hi/lo.
+// One CTA = 8x8 pooled pixels = 17x17 conv pixels (halo recomputed), fp32 CUDA-core math.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStemPT = 8;                      // pooled tile edge
+constexpr int kStemCT = 2 * kStemPT + 1;        // conv tile edge (17)
+constexpr int kStemIT = 2 * kStemCT + 5;        // input tile edge (39)
+constexpr int kStemInFloats = (3 * kStemIT * kStemIT + 3) / 4 * 4;  // keep the weight table 16-byte aligned
+constexpr int kStemSmem = (kStemInFloats + 147 * 64 + kStemCT * kStemCT * 65) * 4;
+
+__global__ void __launch_bounds__(256, 1)
+stem_kernel(const float* __restrict__ in, const float* __restrict__ w /*[64][3][7][7]*/,
+            const float* __restrict__ scale, const float* __restrict__ bias, int height, int width, int conv_h,
+            int conv_w, int pool_h, int pool_w, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  extern __shared__ __align__(16) float s_stem[];
+  float* s_in = s_stem;                               // [3][39][39]
+  float* s_w = s_in + kStemInFloats;                  // [147][64]
+  float* s_c = s_w + 147 * 64;                        // [289][65]
+  const int b = blockIdx.z;
+  const int py0 = blockIdx.y * kStemPT, px0 = blockIdx.x * kStemPT;
+  const int cy0 = 2 * py0, cx0 = 2 * px0;             // first conv pixel of the tile
+  const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;     // first input pixel
+  const int tid = threadIdx.x;
+  const float* img = in + static_cast<long long>(b) * 3 * height * width;
+  for (int i = tid; i < 3 * kStemIT * kStemIT; i += 256) {
+    const int c = i / (kStemIT * kStemIT);
+    const int rem = i - c * kStemIT * kStemIT;
+    const int yy = rem / kStemIT, xx = rem - yy * kStemIT;
+    const int gy = iy0 + yy, gx = ix0 + xx;
+    s_in[i] = (gy >= 0 && gy < height && gx >= 0 && gx < width)
+                  ? __ldg(img + (static_cast<long long>(c) * height + gy) * width + gx)
+                  : 0.0f;
+  }
+  for (int i = tid; i < 147 * 64; i += 256) {
+    const int tap = i >> 6, co = i & 63;
+    s_w[i] = __ldg(w + co * 147 + tap);
+  }
+  __syncthreads();
+  const int cgp = tid & 3;   // 16-channel group
+  const int ps = tid >> 2;   // pixel slot 0..63
+  for (int p = ps; p < kStemCT * kStemCT; p += 64) {
+    const int cy = p / kStemCT, cx = p - cy * kStemCT;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+    for (int c = 0; c < 3; ++c) {
+      for (int ky = 0; ky < 7; ++ky) {
+        const float* irow = s_in + (c * kStemIT + 2 * cy + ky) * kStemIT + 2 * cx;
+        const float* wrow = s_w + ((c * 7 + ky) * 7) * 64 + cgp * 16;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const float v = irow[kx];
+          const float4* w4 = reinterpret_cast<const float4*>(wrow + kx * 64);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 ww = w4[j4];
+            acc[j4 * 4 + 0] += v * ww.x;
+            acc[j4 * 4 + 1] += v * ww.y;
+            acc[j4 * 4 + 2] += v * ww.z;
+            acc[j4 * 4 + 3] += v * ww.w;
+          }
+        }
+      }
+    }
+    const bool in_img = (cy0 + cy < conv_h) && (cx0 + cx < conv_w);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = cgp * 16 + j;
+      const float v = fmaxf(acc[j] * __ldg(scale + co) + __ldg(bias + co), 0.0f);
+      s_c[p * 65 + co] = in_img ? v : -INFINITY;  // ceil_mode windows ignore out-of-range pixels
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kStemPT * kStemPT * 64; i += 256) {
+    const int co = i & 63;
+    const int pp = i >> 6;
+    const int py = pp / kStemPT, px = pp - py * kStemPT;
+    if (py0 + py >= pool_h || px0 + px >= pool_w) continue;
+    float m = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, s_c[((2 * py + dy) * kStemCT + 2 * px + dx) * 65 + co]);
+    const long long o = ((static_cast<long long>(b) * pool_h + py0 + py) * pool_w + px0 + px) * 64 + co;
+    st_pair(out_hi, out_lo, o, m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AvgPool2d(k, stride 1) on NHWC bf16 pairs -> fp32 NHWC (dana.py:42,114: 20x20 -> 7x7, k = 14)
+// ---------------------------------------------------------------------------------------------
+__global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                    int maps, int h, int w, int c, int k, float* __restrict__ out) {
+  const int oh = h - k + 1, ow = w - k + 1;
+  const long long total = static_cast<long long>(maps) * oh * ow * c;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const int ox = static_cast<int>((i / c) % ow);
+    const int oy = static_cast<int>((i / c / ow) % oh);
+    const int m = static_cast<int>(i / c / ow / oh);
+    float s = 0.0f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx)
+        s += ld_pair(hi, lo, ((static_cast<long long>(m) * h + oy + dy) * w + ox + dx) * c + ch);
+    out[i] = s / static_cast<float>(k * k);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Support side of BA + CISA (dana.py:126-147 per shot; rcnn_head dana.py:255-276 with enhance off).
+//   V  = S + PE                                              (:128)
+//   w  = softmax_n(V c + c0);  g = w^T V;  V' = V + gamma * leaky_relu(g)      (:133-137)
+//   u  = softmax_n(V' a + a0); r = unary_gamma * u^T V'       (:144-146 folded: adds r to every output row)
+//   Vc = V' - mean_n V'  -> A operand of the k projection (the Linear bias cancels, :140-141)
+//   V'^T -> B operand of the P.V contraction (:147)
+// ---------------------------------------------------------------------------------------------
+// rows = maps*ns, warp per row.  v_out = in + pe[row % ns]; logit[row] = v . wvec + wb (if wvec)
+__global__ void support_pe_logit_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                        const float* __restrict__ in_f32, const float* __restrict__ pe, int rows, int ns,
+                                        int c, const float* __restrict__ wvec, const float* __restrict__ wb,
+                                        float* __restrict__ v_out, float* __restrict__ logit) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long base = static_cast<long long>(row) * c;
+  const float* per = pe ? pe + static_cast<long long>(row % ns) * c : nullptr;
+  float dot = 0.0f;
+  for (int ch = lane; ch < c; ch += 32) {
+    float v = in_f32 ? in_f32[base + ch] : ld_pair(in_hi, in_lo, base + ch);
+    if (per) v += per[ch];
+    v_out[base + ch] = v;
+    if (wvec) dot += v * __ldg(wvec + ch);
+  }
+  if (wvec) {
+    dot = warp_sum(dot);
+    if (lane == 0) logit[row] = dot + __ldg(wb);
+  }
+}
+
+// block per map: p = softmax_n(logit); wsum[c] = sum_n p_n v[n][c]; colmean[c] = mean_n v[n][c]
+__global__ void __launch_bounds__(256)
+support_softmax_wsum_kernel(const float* __restrict__ v, const float* __restrict__ logit, int ns, int c,
+                            float* __restrict__ wsum, float* __restrict__ colmean) {
+  extern __shared__ float s_p[];  // ns
+  __shared__ float s_red[32];
+  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* lg = logit + static_cast<long long>(m) * ns;
+  float mx = -INFINITY;
+  for (int i = tid; i < ns; i += blockDim.x) mx = fmaxf(mx, lg[i]);
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float sum = 0.0f;
+  for (int i = tid; i < ns; i += blockDim.x) {
+    const float e = expf(lg[i] - mx);
+    s_p[i] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = 0.0f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += s_red[i];
+  const float inv = 1.0f / sum;
+  const float* vm = v + static_cast<long long>(m) * ns * c;
+  for (int ch = tid; ch < c; ch += blockDim.x) {
+    float a = 0.0f, mean = 0.0f;
+    for (int n = 0; n < ns; ++n) {
+      const float x = vm[static_cast<long long>(n) * c + ch];
+      a += (s_p[n] * inv) * x;
+      mean += x;
+    }
+    if (wsum) wsum[static_cast<long long>(m) * c + ch] = a;
+    if (colmean) colmean[static_cast<long long>(m) * c + ch] = mean / static_cast<float>(ns);
+  }
+}
+
+// warp per row: v[row] += gamma * leaky_relu(g[map]) (in place); logit[row] = v . wvec + wb
+__global__ void support_enhance_logit_kernel(float* __restrict__ v, const float* __restrict__ g, float gamma, int rows,
+                                             int ns, int c, const float* __restrict__ wvec,
+                                             const float* __restrict__ wb, float* __restrict__ logit) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long base = static_cast<long long>(row) * c;
+  const float* gm = g ? g + static_cast<long long>(row / ns) * c : nullptr;
+  float dot = 0.0f;
+  for (int ch = lane; ch < c; ch += 32) {
+    float x = v[base + ch];
+    if (gm) {
+      const float gg = gm[ch];
+      x += gamma * (gg > 0.0f ? gg : 0.01f * gg);
+      v[base + ch] = x;
+    }
+    dot += x * __ldg(wvec + ch);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) logit[row] = dot + __ldg(wb);
+}
+
+// Vc = v - colmean -> bf16 pair [rows][c];  v^T -> bf16 pair vt[set][c][slot*ns_pitch... + n]
+// vt layout: vt[(map / shots)][ch][ (map % shots) * ns + n ] with row pitch vt_pitch
+// grid: (ceil(ns/32), ceil(c/32), maps), block (32, 8)
+__global__ void support_finalize_kernel(const float* __restrict__ v, const float* __restrict__ colmean, int ns, int c,
+                                        int shots, long long vt_pitch, __nv_bfloat16* __restrict__ vc_hi,
+                                        __nv_bfloat16* __restrict__ vc_lo, __nv_bfloat16* __restrict__ vt_hi,
+                                        __nv_bfloat16* __restrict__ vt_lo) {
+  __shared__ float tile[32][33];
+  const int m = blockIdx.z;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* vm = v + static_cast<long long>(m) * ns * c;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, ch = c0 + threadIdx.x;
+    float x = 0.0f;
+    if (n < ns && ch < c) {
+      x = vm[static_cast<long long>(n) * c + ch];
+      const long long o = (static_cast<long long>(m) * ns + n) * c + ch;
+      st_pair(vc_hi, vc_lo, o, x - colmean[static_cast<long long>(m) * c + ch]);
+    }
+    tile[i][threadIdx.x] = x;
+  }
+  __syncthreads();
+  const int set = m / shots, slot = m % shots;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ch = c0 + i, n = n0 + threadIdx.x;
+    if (ch < c && n < ns) {
+      const long long o = (static_cast<long long>(set) * c + ch) * vt_pitch + static_cast<long long>(slot) * ns + n;
+      st_pair(vt_hi, vt_lo, o, tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// rbar[set][c] = (unary_gamma / shots) * sum_k r[set*shots + k][c]     (:146 + shot mean :150)
+__global__ void support_rbar_kernel(const float* __restrict__ r, int sets, int shots, int c, float unary_gamma,
+                                    float* __restrict__ rbar) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sets * c) return;
+  const int set = i / c, ch = i - set * c;
+  float s = 0.0f;
+  for (int k = 0; k < shots; ++k) s += r[(static_cast<long long>(set) * shots + k) * c + ch];
+  rbar[i] = s * unary_gamma / static_cast<float>(shots);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mean-centering over groups of rows (q/k projections, dana.py:125,141,267,272) -> bf16 pair.
+// grid (groups, ceil(c/128)), block 128: thread per column, two passes over the group's rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void center_rows_kernel(const float* __restrict__ in, int group_rows, int c, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo) {
+  const int g = blockIdx.x;
+  const int ch = blockIdx.y * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const long long base = static_cast<long long>(g) * group_rows * c + ch;
+  float s = 0.0f;
+  for (int r = 0; r < group_rows; ++r) s += in[base + static_cast<long long>(r) * c];
+  const float mean = s / static_cast<float>(group_rows);
+  for (int r = 0; r < group_rows; ++r) {
+    const long long o = base + static_cast<long long>(r) * c;
+    st_pair(hi, lo, o, in[o] - mean);
+  }
+}
+// large groups (RPN level, thousands of rows): partial column sums with atomics, then subtract
+__global__ void colsum_partial_kernel(const float* __restrict__ in, int group_rows, int c, int rows_per_block,
+                                      float* __restrict__ sums) {
+  const int g = blockIdx.z;
+  const int ch = blockIdx.y * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(group_rows, r0 + rows_per_block);
+  const long long base = static_cast<long long>(g) * group_rows * c + ch;
+  float s = 0.0f;
+  for (int r = r0; r < r1; ++r) s += in[base + static_cast<long long>(r) * c];
+  atomicAdd(sums + static_cast<long long>(g) * c + ch, s);
+}
+__global__ void center_apply_kernel(const float* __restrict__ in, const float* __restrict__ sums, int group_rows, int c,
+                                    long long total, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const long long row = i / c;
+    const long long g = row / group_rows;
+    st_pair(hi, lo, i, in[i] - sums[g * c + ch] / static_cast<float>(group_rows));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention softmax (dana.py:142-143,273-274): logits [rows][pitch] fp32 (already scaled by
+// 1/sqrt(d) in the GEMM epilogue), `segs` segments of `ns` columns per row -> P bf16 pair, pad = 0.
+// warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_softmax_kernel(const float* __restrict__ s, long long rows, int segs, int ns, int pitch,
+                                    __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + row * pitch;
+  for (int k = 0; k < segs; ++k) {
+    const float* sk = sr + k * ns;
+    float mx = -INFINITY;
+    for (int j = lane; j < ns; j += 32) mx = fmaxf(mx, sk[j]);
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < ns; j += 32) sum += expf(sk[j] - mx);
+    sum = warp_sum(sum);
+    for (int j = lane; j < ns; j += 32) st_pair(p_hi, p_lo, row * pitch + k * ns + j, expf(sk[j] - mx) / sum);
+  }
+  for (int j = segs * ns + lane; j < pitch; j += 32) st_pair(p_hi, p_lo, row * pitch + j, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RPN pair softmax + delta repack (rpn.py:47-72, proposal_layer.py:67,97-103).
+// in: [pixels][2A + 4A] fp32 NHWC (cls scores first, channel a = bg, A + a = fg).
+// out: fg [pixels*A], deltas [pixels*A][4]
+// ---------------------------------------------------------------------------------------------
+__global__ void rpn_fg_prob_kernel(const float* __restrict__ in, long long pixels, int num_a, int pitch,
+                                   float* __restrict__ fg, float4* __restrict__ deltas) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= pixels * num_a) return;
+  const long long px = i / num_a;
+  const int a = static_cast<int>(i - px * num_a);
+  const float* row = in + px * pitch;
+  const float s0 = row[a], s1 = row[num_a + a];
+  const float m = fmaxf(s0, s1);
+  const float e0 = expf(s0 - m), e1 = expf(s1 - m);
+  fg[i] = e1 / (e0 + e1);
+  const float* d = row + 2 * num_a + a * 4;
+  deltas[i] = make_float4(d[0], d[1], d[2], d[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+// out pair [rows][c_pitch] (+col offset) = in fp32 [rows][c] + pe[row % period][c]
+__global__ void add_pe_split_kernel(const float* __restrict__ in, const float* __restrict__ pe, long long rows, int c,
+                                    int period, long long out_pitch, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo) {
+  const long long total = rows * c;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / c;
+    const int ch = static_cast<int>(i - row * c);
+    float v = in[i];
+    if (pe) v += pe[static_cast<long long>(row % period) * c + ch];
+    st_pair(hi, lo, row * out_pitch + ch, v);
+  }
+}
+// fp32 -> bf16 pair, same shape
+__global__ void split_f32_kernel(const float* __restrict__ in, long long n, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    st_pair(hi, lo, i, in[i]);
+}
+// bf16 pair -> fp32
+__global__ void merge_pair_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                  long long n, float* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = ld_pair(hi, lo, i);
+}
+// mean over `sp` spatial positions: in pair [items][sp][c] -> fp32 [items][c] and pair
+__global__ void spatial_mean_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                    long long items, int sp, int c, float* __restrict__ out,
+                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  const long long total = items * c;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long it = i / c;
+    const int ch = static_cast<int>(i - it * c);
+    // reference: .mean(3).mean(2) -- mean over w first, then over h (sp = h*w, square)
+    float s = 0.0f;
+    for (int p = 0; p < sp; ++p) s += ld_pair(hi, lo, (it * sp + p) * c + ch);
+    const float m = s / static_cast<float>(sp);
+    if (out) out[i] = m;
+    if (out_hi) st_pair(out_hi, out_lo, i, m);
+  }
+}
+// 2-class softmax over rows of [rows][2]
+__global__ void softmax2_kernel(const float* __restrict__ in, long long rows, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float a = in[2 * i], b = in[2 * i + 1];
+  const float m = fmaxf(a, b);
+  const float ea = expf(a - m), eb = expf(b - m);
+  out[2 * i] = ea / (ea + eb);
+  out[2 * i + 1] = eb / (ea + eb);
+}
+// NHWC pair -> NCHW fp32 (boundary export of feature maps)
+__global__ void nhwc_pair_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                         int c, int hw, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const long long base = static_cast<long long>(b) * c * hw;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, ch = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < hw && ch < c) ? ld_pair(hi, lo, base + static_cast<long long>(p) * c + ch) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ch = c0 + i, p = p0 + threadIdx.x;
+    if (ch < c && p < hw) out[base + static_cast<long long>(ch) * hw + p] = tile[threadIdx.x][i];
+  }
+}
+
+inline int grid_for(long long n, int tb) {
+  long long g = (n + tb - 1) / tb;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace dana

@@ -1,0 +1,323 @@
+// RoIAlign forward / backward (lib/model/csrc/cpu/ROIAlign_cpu.cpp:18-219 sampling rules:
+// no coordinate rounding, no half-pixel shift, malformed RoIs forced to 1x1, adaptive
+// ceil(roi/pooled) sampling grid when sampling_ratio <= 0, samples outside [-1, H] x [-1, W] are zero).
+//
+// Forward design.  Bilinear sampling on a regular grid followed by an average is separable:
+//     out[ph][pw] = (1/count) * sum_y sum_x  wy[ph][y] * wx[pw][x] * F[y][x]
+// with wy[ph][y] the summed row weights of the bin's samples (wx likewise).  One CTA per RoI
+// (x channel group) builds the two small weight tables in shared memory once, then every thread
+// owns a few consecutive channels of the NHWC map: all loads of a warp are one contiguous
+// 128..512-byte run, each feature value is read O(1) times instead of 4 x grid^2 times, and the
+// loop bounds are warp-uniform.  Sample coordinates are evaluated with explicit round-to-nearest
+// intrinsics in the reference's expression order so floor()/validity decisions agree bit for bit.
+#pragma once
+#include "api_common.cuh"
+#include "tc_common.cuh"
+
+namespace dana {
+
+struct RoiGeom {
+  int batch_ind;
+  float start_w, start_h, bin_w, bin_h;
+  int grid_w, grid_h;
+};
+
+__device__ __forceinline__ RoiGeom roi_geometry(const float* roi, float spatial_scale, int pooled_h, int pooled_w,
+                                                int sampling_ratio) {
+  RoiGeom g;
+  g.batch_ind = static_cast<int>(roi[0]);
+  g.start_w = __fmul_rn(roi[1], spatial_scale);
+  g.start_h = __fmul_rn(roi[2], spatial_scale);
+  const float end_w = __fmul_rn(roi[3], spatial_scale);
+  const float end_h = __fmul_rn(roi[4], spatial_scale);
+  const float roi_w = fmaxf(__fsub_rn(end_w, g.start_w), 1.0f);
+  const float roi_h = fmaxf(__fsub_rn(end_h, g.start_h), 1.0f);
+  g.bin_h = __fdiv_rn(roi_h, static_cast<float>(pooled_h));
+  g.bin_w = __fdiv_rn(roi_w, static_cast<float>(pooled_w));
+  g.grid_h = (sampling_ratio > 0) ? sampling_ratio : static_cast<int>(ceilf(__fdiv_rn(roi_h, static_cast<float>(pooled_h))));
+  g.grid_w = (sampling_ratio > 0) ? sampling_ratio : static_cast<int>(ceilf(__fdiv_rn(roi_w, static_cast<float>(pooled_w))));
+  return g;
+}
+
+// sample coordinate of (bin p, sub-sample i): start + p*bin + (i + .5)*bin/grid, reference order
+__device__ __forceinline__ float sample_coord(float start, float bin, int p, int i, int grid) {
+  const float a = __fadd_rn(start, __fmul_rn(static_cast<float>(p), bin));
+  const float b = __fdiv_rn(__fmul_rn(static_cast<float>(i) + 0.5f, bin), static_cast<float>(grid));
+  return __fadd_rn(a, b);
+}
+
+// 1-D half of bilinear_interpolate: returns false when the sample is outside [-1, size]
+__device__ __forceinline__ bool axis_taps(float v, int size, int& low, int& high, float& wl, float& wh) {
+  if (v < -1.0f || v > static_cast<float>(size)) return false;
+  if (v <= 0.0f) v = 0.0f;
+  low = static_cast<int>(v);
+  if (low >= size - 1) {
+    high = low = size - 1;
+    v = static_cast<float>(low);
+  } else {
+    high = low + 1;
+  }
+  wh = v - static_cast<float>(low);  // weight of `high`
+  wl = 1.0f - wh;                    // weight of `low`
+  return true;
+}
+
+// Builds w[p][0..size) and the non-zero range [lo[p], hi[p]] for one axis; called by `pooled` threads.
+__device__ __forceinline__ void build_axis_table(float* w, int* lo, int* hi, int p, int size, float start, float bin,
+                                                 int grid) {
+  float* row = w + p * size;
+  for (int i = 0; i < size; ++i) row[i] = 0.0f;
+  int mn = size, mx = -1;
+  for (int i = 0; i < grid; ++i) {
+    const float v = sample_coord(start, bin, p, i, grid);
+    int l, h;
+    float wl, wh;
+    if (!axis_taps(v, size, l, h, wl, wh)) continue;
+    row[l] += wl;
+    row[h] += wh;
+    mn = min(mn, l);
+    mx = max(mx, h);
+  }
+  lo[p] = mn;
+  hi[p] = mx;
+}
+
+constexpr int kRoiMaxPooled = 16;
+
+// VEC channels per thread.  NCHW_OUT: output [R][C][ph][pw] staged through shared memory so the
+// global write is one contiguous run; otherwise output [R][ph][pw][C] (fp32 and/or bf16 hi/lo).
+// grid: (num_rois, channel_groups), block: cg_channels / VEC threads
+template <int VEC, bool NCHW_OUT>
+__global__ void __launch_bounds__(256)
+roi_align_fwd_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restrict__ rois, int channels, int height,
+                     int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio,
+                     float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  extern __shared__ float s_dyn[];
+  float* s_wy = s_dyn;                          // [pooled_h][height]
+  float* s_wx = s_wy + pooled_h * height;       // [pooled_w][width]
+  float* s_stage = s_wx + pooled_w * width;     // NCHW_OUT: [blockDim.x*VEC][pooled_h*pooled_w]
+  __shared__ int s_ylo[kRoiMaxPooled], s_yhi[kRoiMaxPooled], s_xlo[kRoiMaxPooled], s_xhi[kRoiMaxPooled];
+  __shared__ RoiGeom s_g;
+
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_g = roi_geometry(rois + static_cast<long long>(r) * 5, spatial_scale, pooled_h, pooled_w, sampling_ratio);
+  __syncthreads();
+  const RoiGeom g = s_g;
+  if (tid < pooled_h) build_axis_table(s_wy, s_ylo, s_yhi, tid, height, g.start_h, g.bin_h, g.grid_h);
+  if (tid >= 32 && tid < 32 + pooled_w)
+    build_axis_table(s_wx, s_xlo, s_xhi, tid - 32, width, g.start_w, g.bin_w, g.grid_w);
+  __syncthreads();
+
+  const int cg_channels = blockDim.x * VEC;
+  const int c0 = blockIdx.y * cg_channels + tid * VEC;
+  const bool c_ok = c0 < channels;
+  const float inv_count_den = static_cast<float>(g.grid_h * g.grid_w);
+  const float* fbase = feat + static_cast<long long>(g.batch_ind) * height * width * channels + c0;
+  const int bins = pooled_h * pooled_w;
+
+  for (int ph = 0; ph < pooled_h; ++ph) {
+    float acc[kRoiMaxPooled > 8 ? 8 : kRoiMaxPooled][VEC];
+#pragma unroll
+    for (int pw = 0; pw < 8; ++pw)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[pw][v] = 0.0f;
+    const int ylo = s_ylo[ph], yhi = s_yhi[ph];
+    for (int y = ylo; y <= yhi; ++y) {
+      const float wy = s_wy[ph * height + y];
+      if (wy == 0.0f) continue;
+      const float* frow = fbase + static_cast<long long>(y) * width * channels;
+#pragma unroll
+      for (int pw = 0; pw < 8; ++pw) {
+        if (pw < pooled_w) {
+          float rs[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) rs[v] = 0.0f;
+          const int xlo = s_xlo[pw], xhi = s_xhi[pw];
+          for (int x = xlo; x <= xhi; ++x) {
+            const float wx = s_wx[pw * width + x];
+            if (c_ok) {
+              if (VEC == 4) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(frow + static_cast<long long>(x) * channels));
+                rs[0] += wx * f.x;
+                rs[1 % VEC] += wx * f.y;
+                rs[2 % VEC] += wx * f.z;
+                rs[3 % VEC] += wx * f.w;
+              } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) rs[v] += wx * __ldg(frow + static_cast<long long>(x) * channels + v);
+              }
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[pw][v] += wy * rs[v];
+        }
+      }
+    }
+    // write this row of bins
+#pragma unroll
+    for (int pw = 0; pw < 8; ++pw) {
+      if (pw < pooled_w) {
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o[v] = acc[pw][v] / inv_count_den;
+        if (NCHW_OUT) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) s_stage[(tid * VEC + v) * bins + ph * pooled_w + pw] = o[v];
+        } else if (c_ok) {
+          const long long off = (static_cast<long long>(r) * bins + ph * pooled_w + pw) * channels + c0;
+          if (out != nullptr) {
+            if (VEC == 4) {
+              *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) out[off + v] = o[v];
+            }
+          }
+          if (out_hi != nullptr) {
+            __nv_bfloat16 h[VEC], l[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) split_bf16(o[v], h[v], l[v]);
+            if (VEC == 4) {
+              *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(pack_bf16x2(h[0], h[1 % VEC]), pack_bf16x2(h[2 % VEC], h[3 % VEC]));
+              if (out_lo != nullptr)
+                *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pack_bf16x2(l[0], l[1 % VEC]), pack_bf16x2(l[2 % VEC], l[3 % VEC]));
+            } else {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) {
+                out_hi[off + v] = h[v];
+                if (out_lo != nullptr) out_lo[off + v] = l[v];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (NCHW_OUT) {
+    __syncthreads();
+    // [R][C][bins]: this CTA's channels are one contiguous run of cg_channels*bins floats
+    const int cbase = blockIdx.y * cg_channels;
+    const int nch = min(cg_channels, channels - cbase);
+    float* dst = out + (static_cast<long long>(r) * channels + cbase) * bins;
+    const int total = nch * bins;
+    for (int i = tid; i < total; i += blockDim.x) dst[i] = s_stage[i];
+  }
+}
+
+// NCHW -> NHWC transpose of one feature map batch: [B][C][HW] -> [B][HW][C], 32x32 tiles
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int channels, int hw) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* src = in + static_cast<long long>(b) * channels * hw;
+  float* dst = out + static_cast<long long>(b) * channels * hw;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < channels && p < hw) ? src[static_cast<long long>(c) * hw + p] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < hw && c < channels) dst[static_cast<long long>(p) * channels + c] = tile[threadIdx.x][i];
+  }
+}
+
+// Backward: scatter with atomics into NCHW grad (lib/model/csrc/cuda/ROIAlign_cuda.cu:178-254 semantics).
+__global__ void roi_align_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
+                                     long long nthreads, int channels, int height, int width, int pooled_h,
+                                     int pooled_w, float spatial_scale, int sampling_ratio,
+                                     float* __restrict__ grad_in) {
+  for (long long index = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; index < nthreads;
+       index += static_cast<long long>(blockDim.x) * gridDim.x) {
+    const int pw = static_cast<int>(index % pooled_w);
+    const int ph = static_cast<int>((index / pooled_w) % pooled_h);
+    const int c = static_cast<int>((index / pooled_w / pooled_h) % channels);
+    const int n = static_cast<int>(index / pooled_w / pooled_h / channels);
+    const RoiGeom g = roi_geometry(rois + static_cast<long long>(n) * 5, spatial_scale, pooled_h, pooled_w, sampling_ratio);
+    float* gin = grad_in + (static_cast<long long>(g.batch_ind) * channels + c) * height * width;
+    const float go = grad_out[index];
+    const float count = static_cast<float>(g.grid_h * g.grid_w);
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const float y = sample_coord(g.start_h, g.bin_h, ph, iy, g.grid_h);
+      int yl, yh;
+      float wyl, wyh;
+      if (!axis_taps(y, height, yl, yh, wyl, wyh)) continue;
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const float x = sample_coord(g.start_w, g.bin_w, pw, ix, g.grid_w);
+        int xl, xh;
+        float wxl, wxh;
+        if (!axis_taps(x, width, xl, xh, wxl, wxh)) continue;
+        atomicAdd(gin + yl * width + xl, go * (wyl * wxl) / count);
+        atomicAdd(gin + yl * width + xh, go * (wyl * wxh) / count);
+        atomicAdd(gin + yh * width + xl, go * (wyh * wxl) / count);
+        atomicAdd(gin + yh * width + xh, go * (wyh * wxh) / count);
+      }
+    }
+  }
+}
+
+inline int roi_align_forward_run(const float* input, const float* rois, int num_rois, int batch, int channels,
+                                 int height, int width, int pooled_h, int pooled_w, float spatial_scale,
+                                 int sampling_ratio, int layout, float* out, void* out_hi, void* out_lo,
+                                 void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  if (num_rois == 0) return DANA_OK;
+  if (!input || !rois || num_rois < 0 || batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return DANA_EINVAL;
+  if (pooled_h <= 0 || pooled_w <= 0 || pooled_h > 8 || pooled_w > 8) return DANA_ENOTSUP;
+  const size_t table_bytes = sizeof(float) * (static_cast<size_t>(pooled_h) * height + static_cast<size_t>(pooled_w) * width);
+  if (layout == 0) {
+    if (!out || !workspace) return DANA_EINVAL;
+    const int64_t need = 4LL * batch * channels * height * width;
+    if (workspace_bytes < need) return DANA_EINVAL;
+    float* nhwc = static_cast<float*>(workspace);
+    const int hw = height * width;
+    nchw_to_nhwc_kernel<<<dim3((hw + 31) / 32, (channels + 31) / 32, batch), dim3(32, 8), 0, stream>>>(input, nhwc,
+                                                                                                      channels, hw);
+    const int threads = 128;
+    const size_t smem = table_bytes + sizeof(float) * threads * pooled_h * pooled_w;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      DANA_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+      configured = smem;
+    }
+    roi_align_fwd_kernel<1, true><<<dim3(num_rois, (channels + threads - 1) / threads), threads, smem, stream>>>(
+        nhwc, rois, channels, height, width, pooled_h, pooled_w, spatial_scale, sampling_ratio, out, nullptr, nullptr);
+  } else if (layout == 1) {
+    if (!out && !out_hi) return DANA_EINVAL;
+    if (channels % 4 != 0) return DANA_ENOTSUP;
+    const int threads = (channels / 4 >= 256) ? 256 : ((channels / 4 + 31) / 32) * 32;
+    const int cg = threads * 4;
+    static size_t configured = 0;
+    if (table_bytes > 48 * 1024 && table_bytes > configured) {
+      DANA_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(table_bytes)));
+      configured = table_bytes;
+    }
+    roi_align_fwd_kernel<4, false><<<dim3(num_rois, (channels + cg - 1) / cg), threads, table_bytes, stream>>>(
+        input, rois, channels, height, width, pooled_h, pooled_w, spatial_scale, sampling_ratio, out,
+        static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo));
+  } else {
+    return DANA_EINVAL;
+  }
+  DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
+inline int roi_align_backward_run(const float* grad_out, const float* rois, int num_rois, int batch, int channels,
+                                  int height, int width, int pooled_h, int pooled_w, float spatial_scale,
+                                  int sampling_ratio, float* grad_input, cudaStream_t stream) {
+  if (!grad_input || batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return DANA_EINVAL;
+  DANA_CUDA_CHECK(cudaMemsetAsync(grad_input, 0, 4LL * batch * channels * height * width, stream));
+  if (num_rois == 0) return DANA_OK;
+  if (!grad_out || !rois) return DANA_EINVAL;
+  const long long nthreads = static_cast<long long>(num_rois) * channels * pooled_h * pooled_w;
+  const int tb = 256;
+  const long long blocks = (nthreads + tb - 1) / tb;
+  roi_align_bwd_kernel<<<static_cast<int>(blocks > 148 * 32 ? 148 * 32 : blocks), tb, 0, stream>>>(
+      grad_out, rois, nthreads, channels, height, width, pooled_h, pooled_w, spatial_scale, sampling_ratio, grad_input);
+  DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
+}  // namespace dana

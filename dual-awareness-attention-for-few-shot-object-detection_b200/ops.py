@@ -1,0 +1,379 @@
+"""torch-tensor front end of the C ABI: every function here only validates shapes, allocates
+outputs / workspaces with torch (device memory + current stream are torch's job) and hands raw
+pointers to libdana_b200.so.  No math happens in Python."""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvGemmArgs, check
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.DanaError("dana_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+class Pair:
+    """bf16 (hi, lo) planes of an activation / weight: x ~= hi + lo.  lo is None in plain-bf16 mode."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(shape, device, split=True):
+        hi = torch.empty(shape, dtype=torch.bfloat16, device=device)
+        lo = torch.empty(shape, dtype=torch.bfloat16, device=device) if split else None
+        return Pair(hi, lo)
+
+    @staticmethod
+    def zeros(shape, device, split=True):
+        hi = torch.zeros(shape, dtype=torch.bfloat16, device=device)
+        lo = torch.zeros(shape, dtype=torch.bfloat16, device=device) if split else None
+        return Pair(hi, lo)
+
+    @staticmethod
+    def from_float(x, split=True):
+        """Host-side (torch) split, used for weights at load time and in tests."""
+        hi = x.to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16) if split else None
+        return Pair(hi.contiguous(), None if lo is None else lo.contiguous())
+
+    def float(self):
+        return self.hi.float() if self.lo is None else self.hi.float() + self.lo.float()
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def view(self, *shape):
+        return Pair(self.hi.view(*shape), None if self.lo is None else self.lo.view(*shape))
+
+    def __getitem__(self, idx):
+        return Pair(self.hi[idx], None if self.lo is None else self.lo[idx])
+
+
+# --------------------------------------------------------------------------- tensor-core GEMM / conv
+def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strides, *, out: Optional[Pair] = None,
+              out_f32=None, taps=(1, 1, 0), scale=None, bias=None, bias_sn=0, res: Optional[Pair] = None,
+              res_f32=None, r_strides=(0, 0, 0), relu=False, alpha=1.0, b_pitch=None, b_batch_stride=0,
+              tile=(0, 0, 0)):
+    """Raw call of dana_conv_gemm; see include/dana_b200.h for the argument meaning."""
+    _need_cuda(a.hi, w.hi)
+    args = ConvGemmArgs()
+    args.a_hi, args.a_lo = _p(a.hi), _p(a.lo)
+    args.a_c, args.a_w, args.a_h, args.a_n = [int(v) for v in a_dims]
+    args.a_sx, args.a_sy, args.a_sn = [int(v) for v in a_strides]
+    args.taps_r, args.taps_s, args.pad = taps
+    args.b_hi, args.b_lo = _p(w.hi), _p(w.lo)
+    args.b_pitch = int(b_pitch if b_pitch is not None else w.hi.stride(-2))
+    args.b_batch_stride = int(b_batch_stride)
+    args.n_out = int(n_out)
+    args.tile_w, args.tile_h, args.tile_n = tile
+    args.out_w, args.out_h, args.out_n = [int(v) for v in out_dims]
+    args.o_sx, args.o_sy, args.o_sn = [int(v) for v in o_strides]
+    args.out_hi = _p(out.hi) if out is not None else None
+    args.out_lo = _p(out.lo) if out is not None else None
+    args.out_f32 = _p(out_f32)
+    args.scale, args.bias, args.bias_sn = _p(scale), _p(bias), int(bias_sn)
+    args.res_hi = _p(res.hi) if res is not None else None
+    args.res_lo = _p(res.lo) if res is not None else None
+    args.res_f32 = _p(res_f32)
+    args.r_sx, args.r_sy, args.r_sn = [int(v) for v in r_strides]
+    args.alpha = float(alpha)
+    args.relu = 1 if relu else 0
+    check(_lib.load().dana_conv_gemm(ctypes.byref(args), _stream()), "dana_conv_gemm")
+
+
+def conv_nhwc(x: Pair, w: Pair, n_out: int, *, ksize=1, stride=1, scale=None, bias=None, res: Optional[Pair] = None,
+              relu=False, out: Optional[Pair] = None, out_f32=None, out_channel_offset=0, split=True):
+    """Conv2d (1x1 any stride, or 3x3 stride 1 pad 1) + per-channel scale/bias (+residual) (+ReLU) on an NHWC
+    activation pair [N,H,W,C] (resnet.py:71-76 Bottleneck convs + frozen BN).  Returns the output pair."""
+    n, h, wd, c = x.hi.shape
+    sn, sy, sx, sc = x.hi.stride()
+    assert sc == 1
+    if ksize == 1:
+        oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
+        a_dims = (c, ow, oh, n)
+        a_strides = (sx * stride, sy * stride, sn)
+        taps = (1, 1, 0)
+    else:
+        assert ksize == 3 and stride == 1
+        oh, ow = h, wd
+        a_dims = (c, wd, h, n)
+        a_strides = (sx, sy, sn)
+        taps = (3, 3, 1)
+    if out is None and out_f32 is None:
+        out = Pair.empty((n, oh, ow, n_out), x.hi.device, split=split)
+    ref = out.hi if out is not None else out_f32
+    osn, osy, osx, osc = ref.stride()
+    assert osc == 1
+    o_strides = (osx, osy, osn)
+    r_strides = (0, 0, 0)
+    if res is not None:
+        rsn, rsy, rsx, _ = res.hi.stride()
+        r_strides = (rsx, rsy, rsn)
+    if out_channel_offset:
+        out_v = Pair(out.hi[..., out_channel_offset:], None if out.lo is None else out.lo[..., out_channel_offset:])
+    else:
+        out_v = out
+    conv_gemm(x, a_dims, a_strides, w, n_out, (ow, oh, n), o_strides, out=out_v, out_f32=out_f32, taps=taps,
+              scale=scale, bias=bias, res=res, r_strides=r_strides, relu=relu)
+    return out
+
+
+def linear(x: Pair, w: Pair, n_out: int, *, bias=None, scale=None, relu=False, alpha=1.0, out: Optional[Pair] = None,
+           out_f32=None, split=True, batch=1, b_batch_stride=0, bias_sn=0):
+    """y = alpha * x @ w.T (* scale) + bias on a row-major pair x [batch*rows, K] (nn.Linear / torch.bmm,
+    dana.py:124,140,142,147).  With batch > 1 the rows are split evenly and w / bias may differ per batch."""
+    rows_total, k = x.hi.shape
+    pitch = x.hi.stride(0)
+    assert rows_total % batch == 0
+    rows = rows_total // batch
+    if out is None and out_f32 is None:
+        out = Pair.empty((rows_total, n_out), x.hi.device, split=split)
+    ref = out.hi if out is not None else out_f32
+    opitch = ref.stride(0)
+    conv_gemm(x, (k, rows, 1, batch), (pitch, pitch * rows, pitch * rows), w, n_out, (rows, 1, batch),
+              (opitch, opitch * rows, opitch * rows), out=out, out_f32=out_f32, scale=scale, bias=bias,
+              bias_sn=bias_sn, relu=relu, alpha=alpha, b_batch_stride=b_batch_stride)
+    return out if out is not None else out_f32
+
+
+# --------------------------------------------------------------------------- NMS / proposals / RoIAlign
+def nms(boxes, scores, thresh: float):
+    """Greedy NMS, kept input indices ascending (int64).  Mirrors model._C.nms (csrc/nms.h:10-28)."""
+    _need_cuda(boxes, scores)
+    n = boxes.shape[0]
+    dev = boxes.device
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device="cpu")  # reference: empty CPU long (nms.h:17-18)
+    boxes = boxes.contiguous().float()
+    scores = scores.contiguous().float()
+    lib = _lib.load()
+    wsb = lib.dana_nms_workspace_bytes(n)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    keep = torch.empty((n,), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    check(lib.dana_nms(_p(boxes), _p(scores), n, float(thresh), _p(keep), _p(count), _p(ws), wsb, _stream()),
+          "dana_nms")
+    return keep[: int(count.item())]
+
+
+class ProposalWorkspace:
+    """Reusable device scratch of the proposal layer for one (batch, H*W*A, pre_nms_top_n)."""
+
+    def __init__(self, batch, hwa, pre_nms_top_n, device):
+        self.key = (batch, hwa, pre_nms_top_n)
+        self.bytes = _lib.load().dana_proposals_workspace_bytes(batch, hwa, pre_nms_top_n)
+        self.buf = torch.empty((self.bytes,), dtype=torch.uint8, device=device)
+
+
+def proposals(fg_scores, deltas, base_anchors, im_info, feat_h, feat_w, feat_stride, pre_nms_top_n, post_nms_top_n,
+              nms_thresh, workspace: Optional[ProposalWorkspace] = None, want_scores=False):
+    """_ProposalLayer.forward (proposal_layer.py:49-190) -> rois [B, post, 5] (zero padded)."""
+    _need_cuda(fg_scores, deltas, base_anchors, im_info)
+    b = fg_scores.shape[0]
+    num_a = base_anchors.shape[0]
+    hwa = feat_h * feat_w * num_a
+    assert fg_scores.shape == (b, hwa) and deltas.shape == (b, hwa, 4)
+    dev = fg_scores.device
+    if workspace is None or workspace.key != (b, hwa, pre_nms_top_n):
+        workspace = ProposalWorkspace(b, hwa, pre_nms_top_n, dev)
+    rois = torch.empty((b, post_nms_top_n, 5), dtype=torch.float32, device=dev)
+    sc = torch.empty((b, post_nms_top_n), dtype=torch.float32, device=dev) if want_scores else None
+    cnt = torch.empty((b,), dtype=torch.int32, device=dev)
+    check(_lib.load().dana_proposals(_p(fg_scores.contiguous()), _p(deltas.contiguous()),
+                                     _p(base_anchors.contiguous().float()), _p(im_info.contiguous().float()), b,
+                                     feat_h, feat_w, num_a, feat_stride, pre_nms_top_n, post_nms_top_n,
+                                     float(nms_thresh), _p(rois), _p(sc), _p(cnt), _p(workspace.buf), workspace.bytes,
+                                     _stream()), "dana_proposals")
+    if want_scores:
+        return rois, sc, cnt
+    return rois
+
+
+def roi_align_forward(inp, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
+    """model._C.roi_align_forward (csrc/ROIAlign.h:11-27): NCHW fp32 in -> [R,C,ph,pw] fp32."""
+    _need_cuda(inp, rois)
+    inp = inp.contiguous().float()
+    rois = rois.contiguous().float()
+    b, c, h, w = inp.shape
+    r = rois.shape[0]
+    out = torch.empty((r, c, pooled_h, pooled_w), dtype=torch.float32, device=inp.device)
+    if r == 0:
+        return out
+    lib = _lib.load()
+    wsb = lib.dana_roi_align_workspace_bytes(b, c, h, w, 0)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=inp.device)
+    check(lib.dana_roi_align_forward(_p(inp), _p(rois), r, b, c, h, w, pooled_h, pooled_w, float(spatial_scale),
+                                     int(sampling_ratio), 0, _p(out), None, None, _p(ws), wsb, _stream()),
+          "dana_roi_align_forward")
+    return out
+
+
+def roi_align_nhwc(feat_nhwc, rois, spatial_scale, pooled, sampling_ratio, *, want_f32=True, want_pair=True,
+                   split=True):
+    """Pipeline variant: NHWC fp32 map [B,H,W,C] -> [R,ph,pw,C] as fp32 and/or bf16 pair."""
+    _need_cuda(feat_nhwc, rois)
+    b, h, w, c = feat_nhwc.shape
+    r = rois.shape[0]
+    dev = feat_nhwc.device
+    out = torch.empty((r, pooled, pooled, c), dtype=torch.float32, device=dev) if want_f32 else None
+    pair = Pair.empty((r, pooled, pooled, c), dev, split=split) if want_pair else None
+    check(_lib.load().dana_roi_align_forward(_p(feat_nhwc), _p(rois), r, b, c, h, w, pooled, pooled,
+                                             float(spatial_scale), int(sampling_ratio), 1, _p(out),
+                                             _p(pair.hi) if pair else None,
+                                             _p(pair.lo) if (pair and pair.lo is not None) else None, None, 0,
+                                             _stream()), "dana_roi_align_forward")
+    return out, pair
+
+
+def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch, channels, height, width,
+                       sampling_ratio):
+    """model._C.roi_align_backward (csrc/ROIAlign.h:29-45)."""
+    _need_cuda(grad, rois)
+    grad = grad.contiguous().float()
+    rois = rois.contiguous().float()
+    gin = torch.empty((batch, channels, height, width), dtype=torch.float32, device=grad.device)
+    check(_lib.load().dana_roi_align_backward(_p(grad), _p(rois), rois.shape[0], batch, channels, height, width,
+                                              pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _p(gin),
+                                              _stream()), "dana_roi_align_backward")
+    return gin
+
+
+# --------------------------------------------------------------------------- CUDA-core stages
+def stem(im_nchw, weight, scale, bias, split=True):
+    b, c, h, w = im_nchw.shape
+    assert c == 3
+    conv_h, conv_w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    ph, pw = (conv_h - 2) // 2 + 1, (conv_w - 2) // 2 + 1
+    out = Pair.empty((b, ph, pw, 64), im_nchw.device, split=split)
+    check(_lib.load().dana_stem(_p(im_nchw.contiguous()), _p(weight), _p(scale), _p(bias), b, h, w, _p(out.hi),
+                                _p(out.lo), _stream()), "dana_stem")
+    return out
+
+
+def avgpool(x: Pair, k: int):
+    n, h, w, c = x.hi.shape
+    out = torch.empty((n, h - k + 1, w - k + 1, c), dtype=torch.float32, device=x.hi.device)
+    check(_lib.load().dana_avgpool(_p(x.hi), _p(x.lo), n, h, w, c, k, _p(out), _stream()), "dana_avgpool")
+    return out
+
+
+def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b, unary_gamma=0.1, vt_pitch,
+                    split=True):
+    """Support side of BA+CISA.  x: Pair or fp32 tensor [maps, ns, c].  Returns (vc pair [maps*ns, c],
+    vt pair [sets, c, vt_pitch], rbar fp32 [sets, c])."""
+    if isinstance(x, Pair):
+        maps, ns, c = x.hi.shape
+        dev = x.hi.device
+        in_hi, in_lo, in_f32 = _p(x.hi), _p(x.lo), None
+    else:
+        maps, ns, c = x.shape
+        dev = x.device
+        in_hi, in_lo, in_f32 = None, None, _p(x)
+    sets = maps // shots
+    f = dict(dtype=torch.float32, device=dev)
+    v = torch.empty((maps, ns, c), **f)
+    logit = torch.empty((maps, ns), **f)
+    g = torch.empty((maps, c), **f)
+    r = torch.empty((maps, c), **f)
+    colmean = torch.empty((maps, c), **f)
+    vc = Pair.empty((maps * ns, c), dev, split=split)
+    vt = Pair.zeros((sets, c, vt_pitch), dev, split=split)
+    rbar = torch.empty((sets, c), **f)
+    check(_lib.load().dana_support_prepare(in_hi, in_lo, in_f32, _p(pe), maps, shots, ns, c, _p(ba_w), _p(ba_b),
+                                           float(gamma), _p(un_w), _p(un_b), float(unary_gamma), _p(v), _p(logit),
+                                           _p(g), _p(r), _p(colmean), _p(vc.hi), _p(vc.lo), _p(vt.hi), _p(vt.lo),
+                                           int(vt_pitch), _p(rbar), _stream()), "dana_support_prepare")
+    return vc, vt, rbar
+
+
+def center_rows(x_f32, groups, group_rows, split=True):
+    c = x_f32.shape[-1]
+    dev = x_f32.device
+    out = Pair.empty((groups * group_rows, c), dev, split=split)
+    sums = torch.empty((groups, c), dtype=torch.float32, device=dev) if group_rows > 256 else None
+    check(_lib.load().dana_center_rows(_p(x_f32), groups, group_rows, c, _p(out.hi), _p(out.lo), _p(sums), _stream()),
+          "dana_center_rows")
+    return out
+
+
+def attn_softmax(logits_f32, segs, ns, split=True):
+    rows, pitch = logits_f32.shape
+    out = Pair.empty((rows, pitch), logits_f32.device, split=split)
+    check(_lib.load().dana_attn_softmax(_p(logits_f32), rows, segs, ns, pitch, _p(out.hi), _p(out.lo), _stream()),
+          "dana_attn_softmax")
+    return out
+
+
+def rpn_fg_prob(rpn_out_f32, num_a):
+    """rpn_out_f32 [B,H,W,6A] fp32 -> fg [B, H*W*A], deltas [B, H*W*A, 4]."""
+    b, h, w, pitch = rpn_out_f32.shape
+    dev = rpn_out_f32.device
+    fg = torch.empty((b, h * w * num_a), dtype=torch.float32, device=dev)
+    deltas = torch.empty((b, h * w * num_a, 4), dtype=torch.float32, device=dev)
+    check(_lib.load().dana_rpn_fg_prob(_p(rpn_out_f32), b * h * w, num_a, pitch, _p(fg), _p(deltas), _stream()),
+          "dana_rpn_fg_prob")
+    return fg, deltas
+
+
+def add_pe_split(x_f32, pe, period, out: Pair, out_pitch):
+    rows = x_f32.numel() // x_f32.shape[-1]
+    c = x_f32.shape[-1]
+    check(_lib.load().dana_add_pe_split(_p(x_f32), _p(pe), rows, c, period, out_pitch, _p(out.hi), _p(out.lo),
+                                        _stream()), "dana_add_pe_split")
+    return out
+
+
+def split_f32(x_f32, split=True):
+    out = Pair.empty(tuple(x_f32.shape), x_f32.device, split=split)
+    check(_lib.load().dana_split_f32(_p(x_f32.contiguous()), x_f32.numel(), _p(out.hi), _p(out.lo), _stream()),
+          "dana_split_f32")
+    return out
+
+
+def merge_pair(x: Pair):
+    out = torch.empty(tuple(x.hi.shape), dtype=torch.float32, device=x.hi.device)
+    check(_lib.load().dana_merge_pair(_p(x.hi), _p(x.lo), x.hi.numel(), _p(out), _stream()), "dana_merge_pair")
+    return out
+
+
+def spatial_mean(x: Pair, split=True):
+    items, sp, c = x.hi.shape
+    dev = x.hi.device
+    out = torch.empty((items, c), dtype=torch.float32, device=dev)
+    pair = Pair.empty((items, c), dev, split=split)
+    check(_lib.load().dana_spatial_mean(_p(x.hi), _p(x.lo), items, sp, c, _p(out), _p(pair.hi), _p(pair.lo),
+                                        _stream()), "dana_spatial_mean")
+    return out, pair
+
+
+def softmax2(x_f32):
+    out = torch.empty_like(x_f32)
+    check(_lib.load().dana_softmax2(_p(x_f32.contiguous()), x_f32.shape[0], _p(out), _stream()), "dana_softmax2")
+    return out
+
+
+def nhwc_pair_to_nchw(x: Pair):
+    n, h, w, c = x.hi.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.hi.device)
+    check(_lib.load().dana_nhwc_pair_to_nchw(_p(x.hi), _p(x.lo), n, c, h * w, _p(out), _stream()),
+          "dana_nhwc_pair_to_nchw")
+    return out
+
+
+def device_error():
+    return _lib.load().dana_device_error()

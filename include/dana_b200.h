@@ -1,0 +1,169 @@
+/* dana_b200 -- C ABI of the Blackwell-native DAnA forward hot path.
+ *
+ * Every entry point takes raw device pointers, plain sizes and a CUDA stream
+ * (passed as void* so the header needs no CUDA include).  Rules shared by all
+ * calls: inputs are never mutated; outputs and workspaces are caller-allocated
+ * (sized by the matching *_workspace_bytes query); nothing allocates, nothing
+ * synchronises the stream, nothing throws.  Return value: 0 on success, a
+ * negative DANA_E* code otherwise (dana_error_string() names it).
+ *
+ * Each declaration cites the reference interface it replaces
+ * (paths relative to the reference repo root).
+ */
+#ifndef DANA_B200_H_
+#define DANA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DANA_OK 0
+#define DANA_EINVAL (-1)   /* bad argument (shape, alignment, null pointer)          */
+#define DANA_ECUDA (-2)    /* CUDA runtime / driver error, see dana_last_cuda_error  */
+#define DANA_EDEVICE (-3)  /* device-side protocol error recorded by a kernel        */
+#define DANA_ENOTSUP (-4)  /* valid request this build does not implement           */
+
+int dana_abi_version(void);
+const char* dana_error_string(int code);
+/* Last CUDA error code seen by the library on this thread (cudaError_t as int). */
+int dana_last_cuda_error(void);
+/* Reads (and clears) the sticky device-side error word; synchronises the device. */
+int dana_device_error(void);
+
+/* ------------------------------------------------------------------------
+ * NMS -- replaces model._C.nms  (lib/model/csrc/vision.cpp:8, csrc/nms.h:10-28,
+ * algorithm and comparison semantics of csrc/cpu/nms_cpu.cpp:6-75: "+1" box
+ * extents, fp32, IoU >= thresh suppresses, ties broken by lower input index).
+ *
+ * boxes  [n,4] fp32 (x1,y1,x2,y2), scores [n] fp32.
+ * keep   [n]   int64 out: kept INPUT indices in ascending order (first *count valid)
+ * count  [1]   int32 out (device memory).
+ * If scores == NULL the boxes are taken as already sorted by descending score.
+ * ------------------------------------------------------------------------ */
+int64_t dana_nms_workspace_bytes(int n);
+int dana_nms(const float* boxes, const float* scores, int n, float thresh, int64_t* keep, int32_t* count,
+             void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * RPN proposals -- replaces _ProposalLayer.forward
+ * (lib/model/rpn/proposal_layer.py:49-190 with bbox_transform_inv / clip_boxes of
+ * lib/model/rpn/bbox_transform.py:77-103,125-133 and the anchor grid of
+ * lib/model/rpn/generate_anchors.py:45-105 + proposal_layer.py:79-93).
+ *
+ * fg_scores [B, H*W*A] fp32 in (h, w, a) order; deltas [B, H*W*A, 4] fp32, same order.
+ * base_anchors [A,4] fp32; im_info [B,3] fp32 (height, width, scale).
+ * rois [B, post_nms_top_n, 5] fp32 out: (batch index, x1, y1, x2, y2), zero padded.
+ * roi_scores [B, post_nms_top_n] fp32 out (may be NULL); roi_counts [B] int32 out (may be NULL).
+ * ------------------------------------------------------------------------ */
+int64_t dana_proposals_workspace_bytes(int batch, int num_anchors_total, int pre_nms_top_n);
+int dana_proposals(const float* fg_scores, const float* deltas, const float* base_anchors, const float* im_info,
+                   int batch, int feat_h, int feat_w, int num_base_anchors, int feat_stride, int pre_nms_top_n,
+                   int post_nms_top_n, float nms_thresh, float* rois, float* roi_scores, int32_t* roi_counts,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * RoIAlign -- replaces model._C.roi_align_forward / roi_align_backward
+ * (lib/model/csrc/vision.cpp:9-10, csrc/ROIAlign.h:11-45; sampling rules of
+ * csrc/cpu/ROIAlign_cpu.cpp:18-219: no rounding, no half-pixel shift, adaptive
+ * ceil(roi/pooled) grid when sampling_ratio <= 0).
+ *
+ * layout: 0 = NCHW fp32 in / [R,C,ph,pw] fp32 out (the reference's layout)
+ *         1 = NHWC fp32 in / [R,ph,pw,C] out, written as fp32 (out) and/or as a
+ *             bf16 hi/lo pair (out_hi/out_lo) for the tensor-core head.
+ * rois [R,5] fp32 (batch index, x1, y1, x2, y2) in image pixels.
+ * ------------------------------------------------------------------------ */
+int64_t dana_roi_align_workspace_bytes(int batch, int channels, int height, int width, int layout);
+int dana_roi_align_forward(const float* input, const float* rois, int num_rois, int batch, int channels, int height,
+                           int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int layout,
+                           float* out, void* out_hi, void* out_lo, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+/* grad_input [B,C,H,W] fp32 is ZEROED by the call and then accumulated (NCHW only). */
+int dana_roi_align_backward(const float* grad_out, const float* rois, int num_rois, int batch, int channels,
+                            int height, int width, int pooled_h, int pooled_w, float spatial_scale,
+                            int sampling_ratio, float* grad_input, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Tensor-core implicit-GEMM convolution / GEMM (tcgen05 + TMA).  Replaces the
+ * cuDNN / cuBLAS calls behind nn.Conv2d + BatchNorm2d(eval) + ReLU + residual
+ * (lib/model/framework/resnet.py:66-102, lib/model/rpn/rpn.py:28-36,63-72) and
+ * nn.Linear / torch.bmm of the attention block (lib/model/framework/dana.py:124,
+ * 140,142,147,266-290).
+ *
+ * A is an NHWC activation seen as a 4-D tensor (c, x, y, n) with arbitrary
+ * x/y/n element strides (a stride-2 1x1 convolution is a strided view); a plain
+ * GEMM uses x = row, y = 1.  B is [n_out][taps*c_in] (tap-major, then channel),
+ * optionally one matrix per n (b_batch_stride != 0).  Operands are bf16; when the
+ * *_lo planes are given each product is evaluated as hi*hi + hi*lo + lo*hi
+ * (fp32-equivalent).  Output = relu?(alpha * acc * scale[co] + bias[co] + residual).
+ * ------------------------------------------------------------------------ */
+typedef struct dana_conv_gemm_args {
+  const void* a_hi;
+  const void* a_lo; /* NULL -> plain bf16 */
+  int64_t a_c, a_w, a_h, a_n;       /* extents of the (strided) input view        */
+  int64_t a_sx, a_sy, a_sn;         /* element strides of x, y, n (c stride is 1) */
+  int32_t taps_r, taps_s, pad;      /* 1,1,0 or 3,3,1                             */
+  const void* b_hi;
+  const void* b_lo;
+  int64_t b_pitch;        /* elements between consecutive output channels (>= taps*c_in) */
+  int64_t b_batch_stride; /* elements between per-n matrices, 0 = shared                 */
+  int32_t n_out;
+  int32_t tile_w, tile_h, tile_n; /* output tile, tile_w*tile_h*tile_n == 128 (0 = choose) */
+  int32_t out_w, out_h, out_n;    /* output grid                                           */
+  int64_t o_sx, o_sy, o_sn;       /* output element strides (channel stride 1)             */
+  void* out_hi;
+  void* out_lo;
+  float* out_f32;
+  const float* scale; /* [n_out] or NULL */
+  const float* bias;  /* [n_out] or NULL */
+  int64_t bias_sn;    /* elements between per-n bias vectors, 0 = shared */
+  const void* res_hi; /* residual, bf16 hi (+lo) or fp32, strides r_s* */
+  const void* res_lo;
+  const float* res_f32;
+  int64_t r_sx, r_sy, r_sn;
+  float alpha;
+  int32_t relu;
+} dana_conv_gemm_args;
+int dana_conv_gemm(const dana_conv_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * CUDA-core stages of the path (each replaces the torch ops named).
+ * bf16 "pairs" are (hi, lo) planes with x ~= hi + lo; lo may be NULL.
+ * ------------------------------------------------------------------------ */
+/* conv1 7x7/2 + frozen BN + ReLU + MaxPool 3x3/2 ceil_mode (lib/model/framework/resnet.py:109-113).
+ * in [B,3,H,W] fp32 NCHW; weight [64,3,7,7]; out NHWC pair [B, Hp, Wp, 64]. */
+int dana_stem(const float* in_nchw, const float* weight, const float* scale, const float* bias, int batch, int height,
+              int width, void* out_hi, void* out_lo, void* stream);
+/* nn.AvgPool2d(k, stride=1) on NHWC pairs -> fp32 NHWC (lib/model/framework/dana.py:42,114). */
+int dana_avgpool(const void* in_hi, const void* in_lo, int maps, int h, int w, int c, int k, float* out, void* stream);
+/* Support side of BA + CISA (dana.py:126-147; rcnn_head :255-276 with ba_w == NULL): positional
+ * encoding, background-attenuation gate, unary term r, mean-centred k-projection input (vc) and the
+ * transposed values vt[set][c][shot*ns + n] (row pitch vt_pitch) for the P.V contraction. */
+int dana_support_prepare(const void* in_hi, const void* in_lo, const float* in_f32, const float* pe, int maps,
+                         int shots, int ns, int c, const float* ba_w, const float* ba_b, float gamma,
+                         const float* un_w, const float* un_b, float unary_gamma, float* v, float* logit, float* g,
+                         float* r, float* colmean, void* vc_hi, void* vc_lo, void* vt_hi, void* vt_lo,
+                         int64_t vt_pitch, float* rbar, void* stream);
+/* x - x.mean(1, keepdim=True) over groups of rows (dana.py:125,141,267,272) -> pair. */
+int dana_center_rows(const float* in, int groups, int group_rows, int c, void* out_hi, void* out_lo, float* sums,
+                     void* stream);
+/* F.softmax(logits, dim=2) per shot segment (dana.py:143,274) -> pair, pad columns zeroed. */
+int dana_attn_softmax(const float* logits, int64_t rows, int segs, int ns, int pitch, void* p_hi, void* p_lo,
+                      void* stream);
+/* RPN (bg, fg) pair softmax + delta repack (lib/model/rpn/rpn.py:47-72, proposal_layer.py:67,97-103). */
+int dana_rpn_fg_prob(const float* in, int64_t pixels, int num_a, int pitch, float* fg, float* deltas, void* stream);
+int dana_add_pe_split(const float* in, const float* pe, int64_t rows, int c, int period, int64_t out_pitch,
+                      void* out_hi, void* out_lo, void* stream);
+int dana_split_f32(const float* in, int64_t n, void* out_hi, void* out_lo, void* stream);
+int dana_merge_pair(const void* in_hi, const void* in_lo, int64_t n, float* out, void* stream);
+/* .mean(3).mean(2) of the layer4 output (dana.py:387-389): pair [items][sp][c] -> [items][c]. */
+int dana_spatial_mean(const void* in_hi, const void* in_lo, int64_t items, int sp, int c, float* out, void* out_hi,
+                      void* out_lo, void* stream);
+int dana_softmax2(const float* in, int64_t rows, float* out, void* stream);
+int dana_nhwc_pair_to_nchw(const void* in_hi, const void* in_lo, int batch, int c, int hw, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DANA_B200_H_ */
