@@ -69,7 +69,7 @@ SIGNATURES = {
     "dana_rpn_fg_prob": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dana_add_pe_split": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "dana_split_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "dana_merge_pair": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dana_merge_pair": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "dana_spatial_mean": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_softmax2": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dana_nhwc_pair_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

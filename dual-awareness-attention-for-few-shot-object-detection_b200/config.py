@@ -1,0 +1,124 @@
+"""The `cfg` surface of the reference (lib/model/utils/config.py): a global, mutable attribute
+dictionary of defaults, merged from `cfgs/*.yml` with strict key and type checks and overridable
+from a flat `[key, value, ...]` list (the CLI path, utils.py:68-73).
+
+The hot path reads `cfg` at CALL time (callers mutate it after import, e.g. train.py:48-49), so
+nothing here is snapshotted.  Only the keys are shared with the reference; the implementation is
+a small table-driven container."""
+import ast
+import os
+
+import numpy as np
+import yaml
+
+
+class CfgNode(dict):
+    """dict with attribute access; nested dicts are wrapped on assignment."""
+
+    def __init__(self, init=None):
+        super().__init__()
+        for k, v in (init or {}).items():
+            self[k] = v
+
+    def __setitem__(self, key, value):
+        if isinstance(value, dict) and not isinstance(value, CfgNode):
+            value = CfgNode(value)
+        super().__setitem__(key, value)
+
+    def __getattr__(self, key):
+        try:
+            return self[key]
+        except KeyError as e:
+            raise AttributeError(key) from e
+
+    __setattr__ = __setitem__
+
+
+_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+_DEFAULTS = {
+    "TRAIN": {
+        "LEARNING_RATE": 0.001, "MOMENTUM": 0.9, "WEIGHT_DECAY": 0.0005, "GAMMA": 0.1, "STEPSIZE": [30000],
+        "DISPLAY": 10, "DOUBLE_BIAS": True, "TRUNCATED": False, "BIAS_DECAY": False, "USE_GT": False,
+        "ASPECT_GROUPING": False, "SNAPSHOT_KEPT": 3, "SUMMARY_INTERVAL": 180, "SCALES": (600,), "MAX_SIZE": 1000,
+        "TRIM_HEIGHT": 600, "TRIM_WIDTH": 600, "IMS_PER_BATCH": 1, "BATCH_SIZE": 128, "FG_FRACTION": 0.25,
+        "FG_THRESH": 0.5, "BG_THRESH_HI": 0.5, "BG_THRESH_LO": 0.1, "USE_FLIPPED": True, "BBOX_REG": True,
+        "BBOX_THRESH": 0.5, "SNAPSHOT_ITERS": 5000, "SNAPSHOT_PREFIX": "res101_faster_rcnn",
+        "BBOX_NORMALIZE_TARGETS": True, "BBOX_INSIDE_WEIGHTS": (1.0, 1.0, 1.0, 1.0),
+        "BBOX_NORMALIZE_TARGETS_PRECOMPUTED": True, "BBOX_NORMALIZE_MEANS": (0.0, 0.0, 0.0, 0.0),
+        "BBOX_NORMALIZE_STDS": (0.1, 0.1, 0.2, 0.2), "PROPOSAL_METHOD": "gt", "HAS_RPN": True,
+        "RPN_POSITIVE_OVERLAP": 0.7, "RPN_NEGATIVE_OVERLAP": 0.3, "RPN_CLOBBER_POSITIVES": False,
+        "RPN_FG_FRACTION": 0.5, "RPN_BATCHSIZE": 256, "RPN_NMS_THRESH": 0.7, "RPN_PRE_NMS_TOP_N": 12000,
+        "RPN_POST_NMS_TOP_N": 2000, "RPN_MIN_SIZE": 8, "RPN_BBOX_INSIDE_WEIGHTS": (1.0, 1.0, 1.0, 1.0),
+        "RPN_POSITIVE_WEIGHT": -1.0, "USE_ALL_GT": True, "BN_TRAIN": False,
+    },
+    "TEST": {
+        "SCALES": (600,), "MAX_SIZE": 1000, "NMS": 0.3, "SVM": False, "BBOX_REG": True, "HAS_RPN": False,
+        "PROPOSAL_METHOD": "gt", "RPN_NMS_THRESH": 0.7, "RPN_PRE_NMS_TOP_N": 6000, "RPN_POST_NMS_TOP_N": 300,
+        "RPN_MIN_SIZE": 16, "MODE": "nms", "RPN_TOP_N": 5000,
+    },
+    "RESNET": {"MAX_POOL": False, "FIXED_BLOCKS": 1},
+    "MOBILENET": {"REGU_DEPTH": False, "FIXED_LAYERS": 5, "WEIGHT_DECAY": 0.00004, "DEPTH_MULTIPLIER": 1.0},
+    "DEDUP_BOXES": 1.0 / 16.0,
+    "PIXEL_MEANS": np.array([[[102.9801, 115.9465, 122.7717]]]),
+    "RNG_SEED": 3, "EPS": 1e-14, "ROOT_DIR": _ROOT, "DATA_DIR": os.path.join(_ROOT, "data"), "MATLAB": "matlab",
+    "EXP_DIR": "default", "USE_GPU_NMS": True, "GPU_ID": 0, "POOLING_MODE": "crop", "POOLING_SIZE": 7,
+    "MAX_NUM_GT_BOXES": 20, "ANCHOR_SCALES": [8, 16, 32], "ANCHOR_RATIOS": [0.5, 1, 2], "FEAT_STRIDE": [16, ],
+    "CUDA": False, "CROP_RESIZE_WITH_MAX_POOL": True,
+}
+
+cfg = CfgNode(_DEFAULTS)
+
+
+def reset_cfg():
+    """Restore the defaults in place (tests)."""
+    cfg.clear()
+    for k, v in CfgNode(_DEFAULTS).items():
+        cfg[k] = v
+
+
+def _merge(src, dst, path=""):
+    for key, val in src.items():
+        where = path + key
+        if key not in dst:
+            raise KeyError("{} is not a valid config key".format(where))
+        cur = dst[key]
+        if isinstance(cur, CfgNode):
+            if not isinstance(val, dict):
+                raise ValueError("Type mismatch ({} vs. {}) for config key: {}".format(type(cur), type(val), where))
+            _merge(val, cur, where + ".")
+            continue
+        if type(cur) is not type(val):
+            if isinstance(cur, np.ndarray):
+                val = np.array(val, dtype=cur.dtype)
+            else:
+                raise ValueError("Type mismatch ({} vs. {}) for config key: {}".format(type(cur), type(val), where))
+        dst[key] = val
+
+
+def cfg_from_file(filename):
+    """Merge a yml file into the global cfg (unknown keys and type changes are errors)."""
+    with open(filename, "r") as f:
+        loaded = yaml.safe_load(f) or {}
+    _merge(loaded, cfg)
+
+
+def cfg_from_list(pairs):
+    """Override cfg from ['A.B', 'value', ...]; values are python literals when they parse as such."""
+    if len(pairs) % 2 != 0:
+        raise AssertionError("cfg_from_list needs key/value pairs")
+    for dotted, raw in zip(pairs[0::2], pairs[1::2]):
+        node = cfg
+        parts = dotted.split(".")
+        for part in parts[:-1]:
+            assert part in node, "unknown config section %s" % part
+            node = node[part]
+        leaf = parts[-1]
+        assert leaf in node, "unknown config key %s" % dotted
+        try:
+            value = ast.literal_eval(raw) if isinstance(raw, str) else raw
+        except (ValueError, SyntaxError):
+            value = raw
+        assert type(value) == type(node[leaf]), "type {} does not match original type {}".format(
+            type(value), type(node[leaf]))
+        node[leaf] = value

@@ -388,12 +388,14 @@ __global__ void split_f32_kernel(const float* __restrict__ in, long long n, __nv
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     st_pair(hi, lo, i, in[i]);
 }
-// bf16 pair -> fp32
+// bf16 pair [rows][c] with row pitch in_pitch -> fp32 contiguous [rows][c]
 __global__ void merge_pair_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                  long long n, float* __restrict__ out) {
+                                  long long n, int c, long long in_pitch, float* __restrict__ out) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    out[i] = ld_pair(hi, lo, i);
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / c;
+    out[i] = ld_pair(hi, lo, row * in_pitch + (i - row * c));
+  }
 }
 // mean over `sp` spatial positions: in pair [items][sp][c] -> fp32 [items][c] and pair
 __global__ void spatial_mean_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,

@@ -1,0 +1,307 @@
+"""Forward engine of the DAnA hot path on B200: packs a reference-compatible state-dict into
+tensor-core friendly device buffers (NHWC, bf16 hi/lo planes, folded BN) and sequences the C-ABI
+kernels for `_DAnARCNN.forward` in eval mode (lib/model/framework/dana.py:87-220).
+
+Python here is host orchestration only: shapes, buffer allocation (torch caching allocator) and
+kernel order.  Every FLOP runs in libdana_b200.so."""
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .anchors import generate_anchors
+from .ops import Pair
+
+BN_EPS = 1e-5
+RES_LAYERS = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+
+
+def positional_encoding(max_len, d_model=1024):
+    """Sinusoid over the flattened position index (dana.py:311-320); host-side constant table."""
+    pe = torch.zeros(max_len, d_model)
+    pos = torch.arange(0., max_len).unsqueeze(1)
+    div = torch.exp(torch.arange(0., d_model, 2) * -(math.log(10000.0) / float(d_model)))
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+class _Conv:
+    """One conv (+ frozen BN) packed for the implicit-GEMM kernel: weight [co, kh*kw*ci] (tap-major)."""
+
+    def __init__(self, w, bn, device, split, conv_bias=None):
+        co, ci, kh, kw = w.shape
+        self.n_out, self.ksize = co, kh
+        self.w = Pair.from_float(w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(device), split)
+        if bn is not None:
+            g, b, m, v = [t.to(device=device, dtype=torch.float32) for t in bn]
+            self.scale = (g / torch.sqrt(v + BN_EPS)).contiguous()
+            self.bias = (b - m * self.scale).contiguous()
+        else:
+            self.scale = None
+            self.bias = None if conv_bias is None else conv_bias.to(device=device, dtype=torch.float32).contiguous()
+
+
+class _Block:
+    def __init__(self, sd, name, device, split):
+        def bn(n):
+            return (sd[n + ".weight"], sd[n + ".bias"], sd[n + ".running_mean"], sd[n + ".running_var"])
+        self.c1 = _Conv(sd[name + ".conv1.weight"], bn(name + ".bn1"), device, split)
+        self.c2 = _Conv(sd[name + ".conv2.weight"], bn(name + ".bn2"), device, split)
+        self.c3 = _Conv(sd[name + ".conv3.weight"], bn(name + ".bn3"), device, split)
+        self.down = None
+        if (name + ".downsample.0.weight") in sd:
+            self.down = _Conv(sd[name + ".downsample.0.weight"], bn(name + ".downsample.1"), device, split)
+
+
+class DanaEngine:
+    """precision: 'bf16x3' (hi/lo operands, fp32-equivalent products -- the parity mode) or 'bf16'."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", num_layers=50, n_shot=3,
+                 semantic_enhance=True, channel_gamma=0.1, unary_gamma=0.1, precision="bf16x3",
+                 anchor_scales=(4, 8, 16, 32), anchor_ratios=(0.5, 1, 2), feat_stride=16):
+        assert precision in ("bf16x3", "bf16")
+        self.device = torch.device(device)
+        self.split = precision == "bf16x3"
+        self.precision = precision
+        self.num_layers = num_layers
+        self.n_shot = n_shot
+        self.semantic_enhance = semantic_enhance
+        self.channel_gamma, self.unary_gamma = channel_gamma, unary_gamma
+        self.feat_stride = feat_stride
+        self.base_anchors = torch.from_numpy(
+            generate_anchors(ratios=anchor_ratios, scales=anchor_scales)).float().to(self.device)
+        self.num_a = self.base_anchors.shape[0]
+        self._pe = {}
+        self._prop_ws = None
+        self.load_state_dict(state_dict)
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd):
+        dev, split = self.device, self.split
+        sd = {k: v.detach().float() for k, v in sd.items()}
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        self.stem_w = f32(sd["RCNN_base.0.weight"])
+        g, b, m, v = [f32(sd["RCNN_base.1." + n]) for n in ("weight", "bias", "running_mean", "running_var")]
+        self.stem_scale = (g / torch.sqrt(v + BN_EPS)).contiguous()
+        self.stem_bias = (b - m * self.stem_scale).contiguous()
+        layers = RES_LAYERS[self.num_layers]
+        self.stages = []
+        for prefix, blocks in (("RCNN_base.4", layers[0]), ("RCNN_base.5", layers[1]), ("RCNN_base.6", layers[2])):
+            self.stages.append([_Block(sd, "%s.%d" % (prefix, i), dev, split) for i in range(blocks)])
+        self.top = [_Block(sd, "RCNN_top.0.%d" % i, dev, split) for i in range(layers[3])]
+
+        def lin(name):
+            return Pair.from_float(f32(sd[name + ".weight"]), split), f32(sd[name + ".bias"])
+        self.rpn_q_w, _ = lin("rpn_adapt_q_layer")      # biases cancel under the mean-centering (dana.py:125,141)
+        self.rpn_k_w, _ = lin("rpn_adapt_k_layer")
+        self.rcnn_q_w, _ = lin("rcnn_adapt_q_layer")
+        self.rcnn_k_w, _ = lin("rcnn_adapt_k_layer")
+        self.rpn_un_w, self.rpn_un_b = f32(sd["rpn_unary_layer.weight"]).view(-1), f32(sd["rpn_unary_layer.bias"])
+        self.rcnn_un_w, self.rcnn_un_b = f32(sd["rcnn_unary_layer.weight"]).view(-1), f32(sd["rcnn_unary_layer.bias"])
+        if self.semantic_enhance:
+            self.ba_w, self.ba_b = f32(sd["rpn_channel_k_layer.weight"]).view(-1), f32(sd["rpn_channel_k_layer.bias"])
+        else:
+            self.ba_w = self.ba_b = None
+        self.rpn_conv = _Conv(sd["RCNN_rpn.RPN_Conv.weight"], None, dev, split, sd["RCNN_rpn.RPN_Conv.bias"])
+        w_cb = torch.cat([sd["RCNN_rpn.RPN_cls_score.weight"], sd["RCNN_rpn.RPN_bbox_pred.weight"]], 0)
+        b_cb = torch.cat([sd["RCNN_rpn.RPN_cls_score.bias"], sd["RCNN_rpn.RPN_bbox_pred.bias"]], 0)
+        assert w_cb.shape[0] == 6 * self.num_a, "RPN head does not match the anchor configuration"
+        self.rpn_out = _Conv(w_cb, None, dev, split, b_cb)
+        wt = f32(sd["rcnn_transform_layer.weight"])                       # [64, 2048] on cat[query, dense]
+        self.tr_wq = Pair.from_float(wt[:, :1024].contiguous(), split)
+        self.tr_wd = Pair.from_float(wt[:, 1024:].contiguous(), split)
+        self.tr_b = f32(sd["rcnn_transform_layer.bias"])
+        self.ffn1_w, self.ffn1_b = lin("output_score_layer.linear1")
+        self.ffn2_w, self.ffn2_b = lin("output_score_layer.linear2")
+        self.bbox_w, self.bbox_b = lin("RCNN_bbox_pred")
+
+    def pe(self, n):
+        if n not in self._pe:
+            self._pe[n] = positional_encoding(n).to(self.device).contiguous()
+        return self._pe[n]
+
+    # ------------------------------------------------------------------ trunk
+    def _conv(self, x, c: _Conv, stride=1, relu=True, res=None, out=None):
+        return ops.conv_nhwc(x, c.w, c.n_out, ksize=c.ksize, stride=stride, scale=c.scale, bias=c.bias, res=res,
+                             relu=relu, out=out, split=self.split)
+
+    def _bottleneck(self, x, blk: _Block, stride, out=None):
+        y = self._conv(x, blk.c1, stride=stride)
+        y = self._conv(y, blk.c2)
+        res = self._conv(x, blk.down, stride=stride, relu=False) if blk.down is not None else x
+        return self._conv(y, blk.c3, res=res, out=out)
+
+    def trunk(self, im_nchw, out=None):
+        """RCNN_base (dana.py:344-345).  NCHW fp32 image batch -> NHWC pair, stride 16, 1024 channels.
+        `out` optionally receives the last block's output (e.g. a channel slice of the RPN input)."""
+        x = ops.stem(im_nchw, self.stem_w, self.stem_scale, self.stem_bias, split=self.split)
+        for si, blocks in enumerate(self.stages):
+            for bi, blk in enumerate(blocks):
+                last = (si == len(self.stages) - 1) and (bi == len(blocks) - 1)
+                x = self._bottleneck(x, blk, 2 if (bi == 0 and si > 0) else 1, out=out if last else None)
+        return x
+
+    def layer4(self, pooled: Pair):
+        """RCNN_top (dana.py:346): [R,7,7,1024] -> [R,4,4,2048]."""
+        x = pooled
+        for bi, blk in enumerate(self.top):
+            x = self._bottleneck(x, blk, 2 if bi == 0 else 1)
+        return x
+
+    # ------------------------------------------------------------------ attention
+    def _attention(self, qc: Pair, kc_all: Pair, vt_all: Pair, rbar_all, set_index, sets, batch, ns, out: Pair):
+        """CISA contractions for one support set (dana.py:142-150 / :273-281).
+        qc [batch*rows, 256] centred queries; kc_all [batch*sets*K*ns, 256]; vt_all [batch*sets, C, pitch];
+        rbar_all [batch*sets, C].  Writes the attended feature into `out` [batch*rows, C] (any row pitch)."""
+        k = self.n_shot
+        d = qc.hi.shape[1]
+        c = vt_all.hi.shape[1]
+        pitch = vt_all.hi.shape[2]
+        kn = k * ns
+        rows_total = qc.hi.shape[0]
+        kc = kc_all[set_index * kn:]
+        logits = torch.empty((rows_total, pitch), dtype=torch.float32, device=self.device)
+        ops.linear(qc, kc, kn, alpha=1.0 / math.sqrt(d), out_f32=logits, batch=batch, b_batch_stride=sets * kn * d)
+        p = ops.attn_softmax(logits, k, ns, split=self.split)
+        p_view = Pair(p.hi[:, :kn], None if p.lo is None else p.lo[:, :kn])
+        vt = vt_all[set_index:]
+        vt2 = Pair(vt.hi.view(-1, pitch), None if vt.lo is None else vt.lo.view(-1, pitch))
+        ops.linear(p_view, vt2, c, alpha=1.0 / k, bias=rbar_all[set_index:], bias_sn=sets * c, out=out, batch=batch,
+                   b_batch_stride=sets * c * pitch)
+        return out
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, im_data, im_info, support_ims, pre_nms_top_n=6000, post_nms_top_n=300, nms_thresh=0.7,
+                pooling_size=7, want=None, teacher=None):
+        """Eval forward.  im_data [B,3,H,W] fp32, im_info [B,3], support_ims [B, sets*K, 3, Hs, Ws].
+        Returns (rois [B,post,5], cls_prob [sets*B*post, 2], bbox_pred [B*post, 4]); with `want` (a set of
+        stage names) also a dict of intermediates exported in the reference's layouts."""
+        dev, split, k = self.device, self.split, self.n_shot
+        b = im_data.shape[0]
+        n_sup = support_ims.shape[1]
+        assert n_sup % k == 0, "support_ims must hold sets*n_shot crops per image"
+        sets = n_sup // k
+        want = want or ()
+        extra = {}
+
+        # ---- trunk over the query and the support crops (dana.py:98,111)
+        qh, qw = self._trunk_hw(im_data.shape[2], im_data.shape[3])
+        corr = Pair.empty((b, qh, qw, 2048), dev, split)             # [base | dense]: removes the cat (:154)
+        base = self.trunk(im_data.float().contiguous(), out=corr[..., :1024])
+        sup = self.trunk(support_ims.reshape(-1, *support_ims.shape[2:]).float().contiguous())
+        maps, sh, sw, c = sup.hi.shape
+        ns = sh * sw
+        nq = qh * qw
+        if "base_feat" in want:
+            extra["base_feat"] = ops.merge_pair(base).permute(0, 3, 1, 2)
+        if "support_feat" in want:
+            extra["support_feat"] = ops.merge_pair(sup).permute(0, 3, 1, 2)
+        if teacher and "base_feat" in teacher:                       # teacher forcing for per-stage parity
+            tb = ops.split_f32(teacher["base_feat"].permute(0, 2, 3, 1).contiguous(), split)
+            base.hi.copy_(tb.hi)
+            if split:
+                base.lo.copy_(tb.lo)
+        if teacher and "support_feat" in teacher:
+            sup = ops.split_f32(teacher["support_feat"].reshape(maps, c, sh, sw).permute(0, 2, 3, 1).contiguous(), split)
+
+        # ---- support side, RPN level (dana.py:126-147), all sets*K maps at once
+        pitch = (k * ns + 7) // 8 * 8
+        vc, vt, rbar = ops.support_prepare(sup.view(maps, ns, c), self.pe(ns), k, ba_w=self.ba_w, ba_b=self.ba_b,
+                                           gamma=self.channel_gamma, un_w=self.rpn_un_w, un_b=self.rpn_un_b,
+                                           unary_gamma=self.unary_gamma, vt_pitch=pitch, split=split)
+        kc = ops.linear(vc, self.rpn_k_w, 256, split=split)
+        # ---- query side (dana.py:118,124-125)
+        x2d = Pair(corr.hi.view(b * nq, 2048)[:, :1024], None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, :1024])
+        q = torch.empty((b * nq, 256), dtype=torch.float32, device=dev)
+        ops.linear(x2d, self.rpn_q_w, 256, out_f32=q)
+        qc = ops.center_rows(q, b, nq, split=split)
+        dense_view = Pair(corr.hi.view(b * nq, 2048)[:, 1024:], None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, 1024:])
+        self._attention(qc, kc, vt, rbar, 0, sets, b, ns, dense_view)
+        if "dense" in want:
+            extra["dense"] = ops.merge_pair(corr).permute(0, 3, 1, 2)[:, 1024:]
+        if teacher and "dense" in teacher:
+            td = ops.split_f32(teacher["dense"].permute(0, 2, 3, 1).contiguous(), split)
+            corr.hi[..., 1024:].copy_(td.hi)
+            if split:
+                corr.lo[..., 1024:].copy_(td.lo)
+
+        # ---- RPN head + proposal layer (rpn.py:58-78)
+        r1 = self._conv(corr, self.rpn_conv, relu=True)
+        rpn_raw = torch.empty((b, qh, qw, 6 * self.num_a), dtype=torch.float32, device=dev)
+        ops.conv_nhwc(r1, self.rpn_out.w, 6 * self.num_a, ksize=1, bias=self.rpn_out.bias, out_f32=rpn_raw)
+        fg, deltas = ops.rpn_fg_prob(rpn_raw, self.num_a)
+        if "rpn_fg" in want:
+            extra["rpn_fg"], extra["rpn_deltas"] = fg, deltas
+        if teacher and "rpn_fg" in teacher:
+            fg, deltas = teacher["rpn_fg"].contiguous(), teacher["rpn_deltas"].contiguous()
+        hwa = nq * self.num_a
+        if self._prop_ws is None or self._prop_ws.key != (b, hwa, pre_nms_top_n):
+            self._prop_ws = ops.ProposalWorkspace(b, hwa, pre_nms_top_n, dev)
+        rois = ops.proposals(fg, deltas, self.base_anchors, im_info.to(dev).float(), qh, qw, self.feat_stride,
+                             pre_nms_top_n, post_nms_top_n, nms_thresh, workspace=self._prop_ws)
+        if teacher and "rois" in teacher:
+            rois = teacher["rois"].to(dev).float().contiguous()
+
+        # ---- RoIAlign on the query feature (dana.py:183)
+        base_f32 = ops.merge_pair(Pair(corr.hi[..., :1024], None if corr.lo is None else corr.lo[..., :1024]))
+        r = b * post_nms_top_n
+        pooled_f32, pooled = ops.roi_align_nhwc(base_f32, rois.view(-1, 5), 1.0 / 16.0, pooling_size, 0, split=split)
+        if "pooled" in want:
+            extra["pooled"] = pooled_f32.permute(0, 3, 1, 2)
+        if teacher and "pooled" in teacher:
+            pooled_f32 = teacher["pooled"].permute(0, 2, 3, 1).contiguous()
+            pooled = ops.split_f32(pooled_f32, split)
+
+        # ---- head: box regression (dana.py:246,387-389)
+        top = self.layer4(pooled)
+        fc7_f32, fc7 = ops.spatial_mean(top.view(r, top.hi.shape[1] * top.hi.shape[2], top.hi.shape[3]), split=split)
+        bbox_pred = torch.empty((r, 4), dtype=torch.float32, device=dev)
+        ops.linear(fc7, self.bbox_w, 4, bias=self.bbox_b, out_f32=bbox_pred)
+        if "fc7" in want:
+            extra["fc7"] = fc7_f32
+
+        # ---- head: per-RoI CISA (dana.py:247-290); support projections hoisted out of the RoI loop
+        bins = pooling_size * pooling_size
+        sp_k = sh - pooling_size + 1
+        s_pooled = ops.avgpool(sup, sp_k)                                 # dana.py:114  [maps,7,7,C] fp32
+        if "support_pooled" in want:
+            extra["support_pooled"] = s_pooled.permute(0, 3, 1, 2)
+        pitch_h = (k * bins + 7) // 8 * 8
+        vc_h, vt_h, rbar_h = ops.support_prepare(s_pooled.view(maps, bins, c), self.pe(bins), k, un_w=self.rcnn_un_w,
+                                                 un_b=self.rcnn_un_b, unary_gamma=self.unary_gamma, vt_pitch=pitch_h,
+                                                 split=split)
+        kc_h = ops.linear(vc_h, self.rcnn_k_w, 256, split=split)
+        qpe = Pair.empty((r * bins, c), dev, split)
+        ops.add_pe_split(pooled_f32, self.pe(bins), bins, qpe, c)         # :259
+        q_h = torch.empty((r * bins, 256), dtype=torch.float32, device=dev)
+        ops.linear(qpe, self.rcnn_q_w, 256, out_f32=q_h)                  # :266
+        qc_h = ops.center_rows(q_h, r, bins, split=split)                 # :267
+        t_q = torch.empty((r * bins, 64), dtype=torch.float32, device=dev)
+        ops.linear(qpe, self.tr_wq, 64, bias=self.tr_b, out_f32=t_q)      # query half of :288 (shared by all sets)
+        cls_scores = torch.empty((sets * r, 2), dtype=torch.float32, device=dev)
+        for s in range(sets):
+            dense_h = Pair.empty((r * bins, c), dev, split)
+            self._attention(qc_h, kc_h, vt_h, rbar_h, s, sets, b, bins, dense_h)
+            t = Pair.empty((r * bins, 64), dev, split)
+            ops.linear(dense_h, self.tr_wd, 64, out=t, res_f32=t_q)        # dense half of :288
+            hid = ops.linear(t.view(r, bins * 64), self.ffn1_w, 1024, bias=self.ffn1_b, relu=True, split=split)
+            ops.linear(hid, self.ffn2_w, 2, bias=self.ffn2_b, out_f32=cls_scores[s * r:(s + 1) * r])
+        cls_prob = ops.softmax2(cls_scores)                               # :290
+        if "cls_score" in want:
+            extra["cls_score"] = cls_scores
+        if want:
+            return rois, cls_prob, bbox_pred, extra
+        return rois, cls_prob, bbox_pred
+
+    @staticmethod
+    def _trunk_hw(h, w):
+        def down(v):
+            v = (v - 1) // 2 + 1          # conv1 7x7/2 pad 3
+            v = (v - 2) // 2 + 1          # maxpool 3x3/2 ceil
+            v = (v - 1) // 2 + 1          # layer2
+            return (v - 1) // 2 + 1       # layer3
+        return down(h), down(w)

@@ -134,7 +134,7 @@ def conv_nhwc(x: Pair, w: Pair, n_out: int, *, ksize=1, stride=1, scale=None, bi
 
 
 def linear(x: Pair, w: Pair, n_out: int, *, bias=None, scale=None, relu=False, alpha=1.0, out: Optional[Pair] = None,
-           out_f32=None, split=True, batch=1, b_batch_stride=0, bias_sn=0):
+           out_f32=None, split=True, batch=1, b_batch_stride=0, bias_sn=0, res_f32=None):
     """y = alpha * x @ w.T (* scale) + bias on a row-major pair x [batch*rows, K] (nn.Linear / torch.bmm,
     dana.py:124,140,142,147).  With batch > 1 the rows are split evenly and w / bias may differ per batch."""
     rows_total, k = x.hi.shape
@@ -145,9 +145,14 @@ def linear(x: Pair, w: Pair, n_out: int, *, bias=None, scale=None, relu=False, a
         out = Pair.empty((rows_total, n_out), x.hi.device, split=split)
     ref = out.hi if out is not None else out_f32
     opitch = ref.stride(0)
+    r_strides = (0, 0, 0)
+    if res_f32 is not None:
+        rp = res_f32.stride(0)
+        r_strides = (rp, rp * rows, rp * rows)
     conv_gemm(x, (k, rows, 1, batch), (pitch, pitch * rows, pitch * rows), w, n_out, (rows, 1, batch),
               (opitch, opitch * rows, opitch * rows), out=out, out_f32=out_f32, scale=scale, bias=bias,
-              bias_sn=bias_sn, relu=relu, alpha=alpha, b_batch_stride=b_batch_stride)
+              bias_sn=bias_sn, relu=relu, alpha=alpha, b_batch_stride=b_batch_stride, res_f32=res_f32,
+              r_strides=r_strides)
     return out if out is not None else out_f32
 
 
@@ -346,8 +351,13 @@ def split_f32(x_f32, split=True):
 
 
 def merge_pair(x: Pair):
-    out = torch.empty(tuple(x.hi.shape), dtype=torch.float32, device=x.hi.device)
-    check(_lib.load().dana_merge_pair(_p(x.hi), _p(x.lo), x.hi.numel(), _p(out), _stream()), "dana_merge_pair")
+    """pair [..., c] (last dim contiguous, uniform row pitch) -> contiguous fp32 of the same shape."""
+    shape = tuple(x.hi.shape)
+    c = shape[-1]
+    rows = x.hi.numel() // c
+    pitch = x.hi.stride(-2) if x.hi.dim() > 1 else c
+    out = torch.empty(shape, dtype=torch.float32, device=x.hi.device)
+    check(_lib.load().dana_merge_pair(_p(x.hi), _p(x.lo), rows, c, pitch, _p(out), _stream()), "dana_merge_pair")
     return out
 
 

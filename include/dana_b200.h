@@ -156,7 +156,9 @@ int dana_rpn_fg_prob(const float* in, int64_t pixels, int num_a, int pitch, floa
 int dana_add_pe_split(const float* in, const float* pe, int64_t rows, int c, int period, int64_t out_pitch,
                       void* out_hi, void* out_lo, void* stream);
 int dana_split_f32(const float* in, int64_t n, void* out_hi, void* out_lo, void* stream);
-int dana_merge_pair(const void* in_hi, const void* in_lo, int64_t n, float* out, void* stream);
+/* pair [rows][c] (row pitch in_pitch elements) -> contiguous fp32 [rows][c] */
+int dana_merge_pair(const void* in_hi, const void* in_lo, int64_t rows, int c, int64_t in_pitch, float* out,
+                    void* stream);
 /* .mean(3).mean(2) of the layer4 output (dana.py:387-389): pair [items][sp][c] -> [items][c]. */
 int dana_spatial_mean(const void* in_hi, const void* in_lo, int64_t items, int sp, int c, float* out, void* out_hi,
                       void* out_lo, void* stream);

@@ -325,8 +325,72 @@ def g_proposals():
     return ok
 
 
+def g_engine():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import dana_oracle as O
+    from dana_b200.engine import DanaEngine
+    ok = True
+    k, sets = 2, 2
+    p = O.make_params(1996, attn_std=0.05)
+    im, info, sup = O.synth_inputs(7, 1, 128, 192, k * sets)
+    with torch.no_grad():
+        ref = O.dana_forward_eval(p, im, info, sup, k)
+    want = ("base_feat", "support_feat", "dense", "pooled", "fc7", "cls_score", "support_pooled", "rpn_fg")
+    for prec in ("bf16x3", "bf16"):
+        eng = DanaEngine(p, n_shot=k, precision=prec)
+        t0 = time.time()
+        rois, cls_prob, bbox, ex = eng.forward(im.to(DEV), info.to(DEV), sup.to(DEV), want=want)
+        torch.cuda.synchronize()
+        print("engine %s forward %.1f ms" % (prec, (time.time() - t0) * 1e3))
+        tol = 1e-3 if prec == "bf16x3" else 5e-2
+        ok &= report(prec + " base_feat", relerr(ex["base_feat"].cpu(), ref["base_feat"]), tol)
+        ok &= report(prec + " support_feat", relerr(ex["support_feat"].cpu(), ref["support_feat"].reshape(-1, 1024, 20, 20)), tol)
+        ok &= report(prec + " support_pooled", relerr(ex["support_pooled"].cpu(), ref["support_pooled"].reshape(-1, 1024, 7, 7)), tol)
+        ok &= report(prec + " dense", relerr(ex["dense"].cpu(), ref["dense"]), tol)
+        fg_ref = ref["rpn_cls_prob"][:, 12:].permute(0, 2, 3, 1).reshape(1, -1)
+        ok &= report(prec + " rpn_fg", relerr(ex["rpn_fg"].cpu(), fg_ref), tol)
+        dl_ref = ref["rpn_bbox_pred"].permute(0, 2, 3, 1).reshape(1, -1, 4)
+        ok &= report(prec + " rpn_deltas", relerr(ex["rpn_deltas"].cpu(), dl_ref), tol)
+        same_rois = (rois.cpu() - ref["rois"]).abs().max().item()
+        print("    rois max abs diff (free running) %.3e" % same_rois)
+        # teacher-forced rois so that the per-RoI stages are comparable row by row
+        rois, cls_prob, bbox, ex = eng.forward(im.to(DEV), info.to(DEV), sup.to(DEV), want=want,
+                                               teacher={"rois": ref["rois"].to(DEV)})
+        ok &= report(prec + " pooled (teacher rois)", relerr(ex["pooled"].cpu(), ref["pooled"]), tol)
+        ok &= report(prec + " fc7", relerr(ex["fc7"].cpu(), ref["fc7"]), tol)
+        ok &= report(prec + " bbox_pred", relerr(bbox.cpu(), ref["bbox_pred"]), tol)
+        ok &= report(prec + " cls_score", relerr(ex["cls_score"].cpu(), ref["cls_score"]), tol)
+        ok &= report(prec + " cls_prob", relerr(cls_prob.cpu(), ref["cls_prob"]), tol)
+    return ok
+
+
+def g_bench():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import dana_oracle as O
+    from dana_b200.engine import DanaEngine
+    p = O.make_params(1996)
+    im, info, sup = O.synth_inputs(3, 4, 600, 1000, 6)
+    im, info, sup = im.to(DEV), info.to(DEV), sup.to(DEV)
+    for prec in ("bf16x3", "bf16"):
+        eng = DanaEngine(p, n_shot=3, precision=prec)
+        for _ in range(2):
+            eng.forward(im, info, sup)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 5
+        for _ in range(n):
+            eng.forward(im, info, sup)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        print("bench %s: %.2f ms/step (bs 4) -> %.1f img/s ; peak mem %.1f GB" %
+              (prec, ms, 4e3 / ms, torch.cuda.max_memory_allocated() / 2**30), flush=True)
+    return True
+
+
 GROUPS = {"gemm": g_gemm, "conv": g_conv, "batched": g_gemm_batched, "nms": g_nms, "roialign": g_roialign,
-          "stem": g_stem, "misc": g_misc, "proposals": g_proposals}
+          "stem": g_stem, "misc": g_misc, "proposals": g_proposals, "engine": g_engine, "bench": g_bench}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(GROUPS)

@@ -105,8 +105,10 @@ def test_ref_extension_matches_oracle_when_present():
     np.testing.assert_array_equal(O.nms(boxes, scores, 0.6).numpy(),
                                   ref_c.nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.6).numpy())
     feat = rs.standard_normal((1, 5, 20, 31)).astype(np.float32)
-    rois = np.concatenate([np.zeros((30, 1)), np.sort(rs.uniform(-10, 500, (30, 4)), 1)[:, [0, 1, 2, 3]]], 1)
-    rois = rois[:, [0, 1, 2, 3, 4]].astype(np.float32)
+    # NB the reference CPU kernel reads rois.data<T>() without .contiguous() (ROIAlign_cpu.cpp:254):
+    # hand it C-contiguous rois
+    rois = np.ascontiguousarray(
+        np.concatenate([np.zeros((30, 1)), np.sort(rs.uniform(-10, 500, (30, 4)), 1)], 1).astype(np.float32))
     a = O.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0).numpy()
     b = ref_c.roi_align_forward(torch.from_numpy(feat), torch.from_numpy(rois), 1.0 / 16, 7, 7, 0).numpy()
     np.testing.assert_array_equal(a, b)
