@@ -91,6 +91,10 @@ def _merge(src, dst, path=""):
         if type(cur) is not type(val):
             if isinstance(cur, np.ndarray):
                 val = np.array(val, dtype=cur.dtype)
+            elif isinstance(cur, tuple) and isinstance(val, list):
+                # yml has no tuples: the reference's own cfgs/res101_ls.yml (SCALES: [800]) trips its strict
+                # check (config.py:352-359); accept the list here so that file is usable
+                val = tuple(val)
             else:
                 raise ValueError("Type mismatch ({} vs. {}) for config key: {}".format(type(cur), type(val), where))
         dst[key] = val

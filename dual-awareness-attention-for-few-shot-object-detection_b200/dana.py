@@ -1,0 +1,196 @@
+"""`DAnARCNN` -- the module boundary of the reference (lib/model/framework/dana.py:327-389): same
+constructor, `create_architecture()`, parameter names / shapes (346-key state-dict, so reference
+checkpoints load with `load_state_dict`), `train()` semantics (BatchNorm always in eval) and
+`forward(im_data, im_info, gt_boxes, num_boxes, support_ims, all_cls_gt_boxes=None)` 8-tuple.
+
+The eval forward runs on `engine.DanaEngine` (hand-written sm_100a kernels behind the C ABI); the
+nn.Module only owns the parameters.  The training branch (losses, target layers, backward) is
+row a15 of SURVEY.md section 8 and is not built in this round: calling forward in train mode raises."""
+import math
+
+import torch
+import torch.nn as nn
+
+from .config import cfg
+from .engine import RES_LAYERS, DanaEngine
+
+
+class _Bottleneck(nn.Module):
+    """Caffe-style bottleneck: the stride sits on the first 1x1 (resnet.py:66-102)."""
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, stride=stride, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+
+def _stage(inplanes, planes, blocks, stride):
+    down = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False), nn.BatchNorm2d(planes * 4))
+    layers = [_Bottleneck(inplanes, planes, stride, down)]
+    layers += [_Bottleneck(planes * 4, planes) for _ in range(1, blocks)]
+    return nn.Sequential(*layers)
+
+
+class _FFN(nn.Module):
+    def __init__(self, in_channel, hidden):
+        super().__init__()
+        self.linear1 = nn.Linear(in_channel, hidden)
+        self.linear2 = nn.Linear(hidden, 2)
+        self.relu = nn.ReLU()
+
+
+class _RPNParams(nn.Module):
+    """Parameter holder with the names of `_RPN` (lib/model/rpn/rpn.py:28-36)."""
+
+    def __init__(self, din, num_anchors):
+        super().__init__()
+        self.RPN_Conv = nn.Conv2d(din, 512, 3, 1, 1, bias=True)
+        self.RPN_cls_score = nn.Conv2d(512, 2 * num_anchors, 1, 1, 0)
+        self.RPN_bbox_pred = nn.Conv2d(512, 4 * num_anchors, 1, 1, 0)
+
+
+class DAnARCNN(nn.Module):
+    def __init__(self, classes, attention_type, rpn_reduce_dim=256, rcnn_reduce_dim=256, gamma=0.1,
+                 semantic_enhance=False, num_layers=50, pretrained=False, num_way=2, num_shot=5, pos_encoding=True,
+                 precision="bf16x3"):
+        super().__init__()
+        if attention_type != "concat":
+            raise NotImplementedError("only attention_type='concat' (the shipped configuration, utils.py:119) is built")
+        if not pos_encoding:
+            raise NotImplementedError("pos_encoding=False hits a typo in the reference (dana.py:130) and is not built")
+        if rpn_reduce_dim != 256 or rcnn_reduce_dim != 256:
+            raise NotImplementedError("reduce dims other than 256 are not built")
+        self.model_path = "data/pretrained_model/resnet50_caffe.pth"
+        self.dout_base_model = 1024
+        self.pretrained = pretrained
+        self.classes = classes
+        self.n_classes = len(classes)
+        self.n_way, self.n_shot = num_way, num_shot
+        self.attention_type = attention_type
+        self.channel_gamma, self.unary_gamma = gamma, 0.1
+        self.semantic_enhance = semantic_enhance
+        self.rpn_reduce_dim, self.rcnn_reduce_dim = rpn_reduce_dim, rcnn_reduce_dim
+        # the reference ignores num_layers and always builds resnet50 (dana.py:337); 101 is the stated extension
+        self.num_layers = num_layers if num_layers in RES_LAYERS else 50
+        self.precision = precision
+        dim_in = 1024
+
+        def lin(i, o, std=0.01):
+            m = nn.Linear(i, o)
+            nn.init.normal_(m.weight, std=std)
+            nn.init.constant_(m.bias, 0)
+            return m
+        self.rpn_unary_layer = lin(dim_in, 1)
+        self.rcnn_unary_layer = lin(dim_in, 1)
+        self.rpn_adapt_q_layer = lin(dim_in, rpn_reduce_dim)
+        self.rpn_adapt_k_layer = lin(dim_in, rpn_reduce_dim)
+        self.rcnn_adapt_q_layer = lin(dim_in, rcnn_reduce_dim)
+        self.rcnn_adapt_k_layer = lin(dim_in, rcnn_reduce_dim)
+        if semantic_enhance:
+            self.rpn_channel_k_layer = lin(dim_in, 1)
+        num_anchors = len(cfg.ANCHOR_SCALES) * len(cfg.ANCHOR_RATIOS)
+        self.RCNN_rpn = _RPNParams(2048, num_anchors)
+        self.rcnn_transform_layer = nn.Linear(2048, 64)
+        self.output_score_layer = _FFN(64 * 49, dim_in)
+        self._engine = None
+        self._engine_key = None
+
+    # ---- reference API --------------------------------------------------------------------
+    def create_architecture(self):
+        self._init_modules()
+        self._init_weights()
+
+    def _init_modules(self):
+        l = RES_LAYERS[self.num_layers]
+        conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.RCNN_base = nn.Sequential(conv1, nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+                                       nn.MaxPool2d(3, 2, 0, ceil_mode=True), _stage(64, 64, l[0], 1),
+                                       _stage(256, 128, l[1], 2), _stage(512, 256, l[2], 2))
+        self.RCNN_top = nn.Sequential(_stage(1024, 512, l[3], 2))
+        self.RCNN_bbox_pred = nn.Linear(2048, 4)
+        for m in list(self.RCNN_base.modules()) + list(self.RCNN_top.modules()):
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+        if self.pretrained:
+            sd = torch.load(self.model_path)
+            own = dict(self.RCNN_base.named_parameters())
+            raise NotImplementedError("pretrained caffe weights: load them with load_state_dict (%d tensors)" % len(own))
+        # frozen parts (dana.py:350-368): conv1, bn1, the first FIXED_BLOCKS stages and every BatchNorm
+        for p in self.RCNN_base[0].parameters():
+            p.requires_grad = False
+        for p in self.RCNN_base[1].parameters():
+            p.requires_grad = False
+        assert 0 <= cfg.RESNET.FIXED_BLOCKS < 4
+        for idx, need in ((6, 3), (5, 2), (4, 1)):
+            if cfg.RESNET.FIXED_BLOCKS >= need:
+                for p in self.RCNN_base[idx].parameters():
+                    p.requires_grad = False
+        for m in list(self.RCNN_base.modules()) + list(self.RCNN_top.modules()):
+            if isinstance(m, nn.BatchNorm2d):
+                for p in m.parameters():
+                    p.requires_grad = False
+
+    def _init_weights(self):
+        def normal_init(m, mean, stddev, truncated=False):
+            if truncated:
+                m.weight.data.normal_().fmod_(2).mul_(stddev).add_(mean)
+            else:
+                m.weight.data.normal_(mean, stddev)
+                m.bias.data.zero_()
+        normal_init(self.RCNN_rpn.RPN_Conv, 0, 0.01, cfg.TRAIN.TRUNCATED)
+        normal_init(self.RCNN_rpn.RPN_cls_score, 0, 0.01, cfg.TRAIN.TRUNCATED)
+        normal_init(self.RCNN_rpn.RPN_bbox_pred, 0, 0.01, cfg.TRAIN.TRUNCATED)
+        normal_init(self.RCNN_bbox_pred, 0, 0.001, cfg.TRAIN.TRUNCATED)
+
+    def train(self, mode=True):
+        nn.Module.train(self, mode)
+        if mode and hasattr(self, "RCNN_base"):
+            self.RCNN_base.eval()
+            self.RCNN_base[5].train()
+            self.RCNN_base[6].train()
+            for m in list(self.RCNN_base.modules()) + list(self.RCNN_top.modules()):
+                if isinstance(m, nn.BatchNorm2d):
+                    m.eval()
+        return self
+
+    # ---- engine cache ---------------------------------------------------------------------
+    def _param_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in self.buffers())
+
+    def engine(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("DAnARCNN (dana_b200) runs on CUDA only: call .cuda() first (there is no CPU fallback)")
+        key = (dev, self._param_version(), tuple(cfg.ANCHOR_SCALES), tuple(cfg.ANCHOR_RATIOS), cfg.FEAT_STRIDE[0])
+        if self._engine is None or key != self._engine_key:
+            self._engine = DanaEngine(self.state_dict(), device=dev, num_layers=self.num_layers, n_shot=self.n_shot,
+                                      semantic_enhance=self.semantic_enhance, channel_gamma=self.channel_gamma,
+                                      unary_gamma=self.unary_gamma, precision=self.precision,
+                                      anchor_scales=tuple(cfg.ANCHOR_SCALES), anchor_ratios=tuple(cfg.ANCHOR_RATIOS),
+                                      feat_stride=cfg.FEAT_STRIDE[0])
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, im_data, im_info, gt_boxes, num_boxes, support_ims, all_cls_gt_boxes=None):
+        if self.training:
+            raise NotImplementedError("dana_b200: the training branch of DAnARCNN.forward (target layers, losses, "
+                                      "backward; dana.py:100-108,166-215) is not built yet -- call .eval()")
+        if cfg.POOLING_MODE != "align":
+            raise NotImplementedError("POOLING_MODE %r is not built (shipped configs use 'align')" % cfg.POOLING_MODE)
+        rois, cls_prob, bbox_pred = self.engine().forward(
+            im_data, im_info.data, support_ims, pre_nms_top_n=cfg.TEST.RPN_PRE_NMS_TOP_N,
+            post_nms_top_n=cfg.TEST.RPN_POST_NMS_TOP_N, nms_thresh=cfg.TEST.RPN_NMS_THRESH,
+            pooling_size=cfg.POOLING_SIZE)
+        # eval: losses are python 0 and rois_label is None (dana.py:173-179,216-220)
+        return rois, cls_prob, bbox_pred, 0, 0, 0, 0, None

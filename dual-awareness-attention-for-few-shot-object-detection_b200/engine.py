@@ -173,6 +173,46 @@ class DanaEngine:
                    b_batch_stride=sets * c * pitch)
         return out
 
+    def rpn_attention(self, corr: Pair, sup: Pair, sets=1):
+        """RPN-level BA + CISA (dana.py:117-151).  corr [B,h,w,2048]: channels [0,1024) hold the query
+        feature, channels [1024,2048) receive the attended support feature (the `cat` of :154 for free).
+        sup [B*sets*K, hs, ws, 1024]: support maps, image-major; set 0 of every image drives the block."""
+        split, k, dev = self.split, self.n_shot, self.device
+        b, qh, qw, _ = corr.hi.shape
+        maps, sh, sw, c = sup.hi.shape
+        ns, nq = sh * sw, qh * qw
+        # support side, all sets*K maps at once (:126-147)
+        pitch = (k * ns + 7) // 8 * 8
+        vc, vt, rbar = ops.support_prepare(sup.view(maps, ns, c), self.pe(ns), k, ba_w=self.ba_w, ba_b=self.ba_b,
+                                           gamma=self.channel_gamma, un_w=self.rpn_un_w, un_b=self.rpn_un_b,
+                                           unary_gamma=self.unary_gamma, vt_pitch=pitch, split=split)
+        kc = ops.linear(vc, self.rpn_k_w, 256, split=split)
+        # query side (:118,124-125)
+        x2d = Pair(corr.hi.view(b * nq, 2048)[:, :1024], None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, :1024])
+        q = torch.empty((b * nq, 256), dtype=torch.float32, device=dev)
+        ops.linear(x2d, self.rpn_q_w, 256, out_f32=q)
+        qc = ops.center_rows(q, b, nq, split=split)
+        dense_view = Pair(corr.hi.view(b * nq, 2048)[:, 1024:],
+                          None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, 1024:])
+        self._attention(qc, kc, vt, rbar, 0, sets, b, ns, dense_view)
+
+    @torch.no_grad()
+    def ba_cisa_block(self, base_feat_nchw, support_feat_nchw):
+        """The lifted BA+CISA block (BASELINE.json configs 1 and 5): base_feat [B,1024,h,w] fp32,
+        support_feat [B,K,1024,hs,ws] fp32 (positive set) -> dense support feature [B,1024,h,w] fp32."""
+        b, c, h, w = base_feat_nchw.shape
+        k = support_feat_nchw.shape[1]
+        assert k == self.n_shot and c == 1024
+        corr = Pair.zeros((b, h, w, 2048), self.device, self.split)
+        base = ops.split_f32(base_feat_nchw.permute(0, 2, 3, 1).contiguous(), self.split)
+        corr.hi[..., :1024].copy_(base.hi)
+        if self.split:
+            corr.lo[..., :1024].copy_(base.lo)
+        hs, ws = support_feat_nchw.shape[3], support_feat_nchw.shape[4]
+        sup = ops.split_f32(support_feat_nchw.reshape(b * k, c, hs, ws).permute(0, 2, 3, 1).contiguous(), self.split)
+        self.rpn_attention(corr, sup, 1)
+        return ops.merge_pair(corr).permute(0, 3, 1, 2)[:, 1024:]
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, im_data, im_info, support_ims, pre_nms_top_n=6000, post_nms_top_n=300, nms_thresh=0.7,
@@ -208,19 +248,7 @@ class DanaEngine:
         if teacher and "support_feat" in teacher:
             sup = ops.split_f32(teacher["support_feat"].reshape(maps, c, sh, sw).permute(0, 2, 3, 1).contiguous(), split)
 
-        # ---- support side, RPN level (dana.py:126-147), all sets*K maps at once
-        pitch = (k * ns + 7) // 8 * 8
-        vc, vt, rbar = ops.support_prepare(sup.view(maps, ns, c), self.pe(ns), k, ba_w=self.ba_w, ba_b=self.ba_b,
-                                           gamma=self.channel_gamma, un_w=self.rpn_un_w, un_b=self.rpn_un_b,
-                                           unary_gamma=self.unary_gamma, vt_pitch=pitch, split=split)
-        kc = ops.linear(vc, self.rpn_k_w, 256, split=split)
-        # ---- query side (dana.py:118,124-125)
-        x2d = Pair(corr.hi.view(b * nq, 2048)[:, :1024], None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, :1024])
-        q = torch.empty((b * nq, 256), dtype=torch.float32, device=dev)
-        ops.linear(x2d, self.rpn_q_w, 256, out_f32=q)
-        qc = ops.center_rows(q, b, nq, split=split)
-        dense_view = Pair(corr.hi.view(b * nq, 2048)[:, 1024:], None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, 1024:])
-        self._attention(qc, kc, vt, rbar, 0, sets, b, ns, dense_view)
+        self.rpn_attention(corr, sup, sets)
         if "dense" in want:
             extra["dense"] = ops.merge_pair(corr).permute(0, 3, 1, 2)[:, 1024:]
         if teacher and "dense" in teacher:

@@ -1,0 +1,219 @@
+"""GPU parity tests of the operator-level C ABI (dana_nms, dana_proposals, dana_roi_align_*,
+dana_conv_gemm, stem) against the oracle and the golden vectors of the unmodified reference.
+
+Bars: bit-exact for NMS keep indices and proposal selection on identical inputs; 1e-5 relative
+(max-norm) for fp32 gathers; the tensor-core GEMM is checked operand-exact (against the same
+bf16-rounded operands in fp64) and, in bf16x3 mode, against unrounded fp32 operands at 2e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dana_oracle as O
+import make_golden as MG
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import dana_b200  # noqa: F401
+    from dana_b200 import ops as _ops
+    assert torch.cuda.is_available()
+    return _ops
+
+
+def relerr(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("case", ["random300", "clustered1000", "ties", "big6000"])
+def test_nms_golden(ops, golden_dir, case):
+    boxes, scores, thr = MG.nms_case(case)
+    keep = ops.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr)
+    assert keep.dtype == torch.int64 and keep.is_cuda
+    want = np.load(os.path.join(golden_dir, "nms.npz"))[case]
+    np.testing.assert_array_equal(keep.cpu().numpy(), want)          # reference's own CPU kernel
+    np.testing.assert_array_equal(keep.cpu().numpy(), O.nms(boxes, scores, thr).numpy())
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 129, 1000, 12000])
+@pytest.mark.parametrize("thr", [0.3, 0.7])
+def test_nms_random_vs_oracle(ops, n, thr):
+    rs = np.random.RandomState(100 + n)
+    x1, y1 = rs.uniform(0, 900, n), rs.uniform(0, 500, n)
+    boxes = np.stack([x1, y1, x1 + rs.uniform(1, 200, n), y1 + rs.uniform(1, 200, n)], 1).astype(np.float32)
+    if n >= 129:  # jittered copies: more than half get suppressed
+        boxes[n // 2:] = boxes[: n - n // 2] + rs.normal(0, 2, (n - n // 2, 4)).astype(np.float32)
+    scores = (rs.permutation(n) / max(n, 1)).astype(np.float32)
+    keep = ops.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr)
+    np.testing.assert_array_equal(keep.cpu().numpy(), O.nms(boxes, scores, thr).numpy())
+
+
+def test_nms_edge_cases(ops):
+    e = ops.nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), 0.5)
+    assert e.numel() == 0 and e.dtype == torch.int64 and e.device.type == "cpu"   # csrc/nms.h:17-18
+    # IoU == thr suppresses (>=): the CUDA kernel of the reference used >
+    k = ops.nms(torch.tensor([[0., 0, 9, 9], [0, 0, 9, 4]]).cuda(), torch.tensor([.9, .8]).cuda(), 0.5)
+    assert k.tolist() == [0]
+    # tied scores: lower input index wins on both sides
+    b = torch.tensor([[0., 0, 9, 9], [0, 0, 9, 9], [50, 50, 60, 60], [50, 50, 60, 60]])
+    s = torch.tensor([.5, .5, .7, .7])
+    assert ops.nms(b.cuda(), s.cuda(), 0.5).tolist() == O.nms(b.numpy(), s.numpy(), 0.5).tolist() == [0, 2]
+    # saturated scores (softmax exactly 1.0f): many ties
+    rs = np.random.RandomState(3)
+    n = 500
+    x1, y1 = rs.uniform(0, 300, n), rs.uniform(0, 300, n)
+    bb = np.stack([x1, y1, x1 + rs.uniform(5, 80, n), y1 + rs.uniform(5, 80, n)], 1).astype(np.float32)
+    ss = np.where(rs.uniform(size=n) < 0.5, 1.0, rs.uniform(size=n)).astype(np.float32)
+    np.testing.assert_array_equal(ops.nms(torch.from_numpy(bb).cuda(), torch.from_numpy(ss).cuda(), 0.7).cpu().numpy(),
+                                  O.nms(bb, ss, 0.7).numpy())
+
+
+# ------------------------------------------------------------------------------------ RoIAlign
+def test_roi_align_golden(ops, golden_dir):
+    feat, rois = MG.roi_align_case()
+    g = np.load(os.path.join(golden_dir, "roi_align.npz"))
+    f, r = torch.from_numpy(feat).cuda(), torch.from_numpy(rois).cuda()
+    for ratio, key in ((0, "adaptive"), (2, "ratio2")):
+        out = ops.roi_align_forward(f, r, 1.0 / 16, 7, 7, ratio)
+        assert relerr(out, torch.from_numpy(g[key])) <= 1e-5
+    out_f32, pair = ops.roi_align_nhwc(f.permute(0, 2, 3, 1).contiguous(), r, 1.0 / 16, 7, 0)
+    assert relerr(out_f32.permute(0, 3, 1, 2), torch.from_numpy(g["adaptive"])) <= 1e-5
+    assert relerr(pair.float().permute(0, 3, 1, 2), torch.from_numpy(g["adaptive"])) <= 2e-5
+
+
+def test_roi_align_full_size_vs_oracle(ops):
+    """SURVEY.md 8d KAT: map [2,1024,38,63], 300 rois incl. sub-pixel, full-image, out-of-bounds, degenerate."""
+    rs = np.random.RandomState(42)
+    feat = rs.standard_normal((2, 1024, 38, 63)).astype(np.float32)
+    r = 300
+    x1, y1 = rs.uniform(-30, 980, r), rs.uniform(-30, 590, r)
+    rois = np.stack([rs.randint(0, 2, r).astype(np.float64), x1, y1, x1 + rs.uniform(0.3, 600, r),
+                     y1 + rs.uniform(0.3, 400, r)], 1).astype(np.float32)
+    rois[0, 1:] = [0, 0, 999, 599]
+    rois[1, 1:] = [500, 300, 400, 200]
+    rois[2, 1:] = [1500, 900, 1600, 950]
+    rois[3, 1:] = [10.2, 10.7, 10.9, 11.1]
+    want = O.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0)
+    got = ops.roi_align_forward(torch.from_numpy(feat).cuda(), torch.from_numpy(rois).cuda(), 1.0 / 16, 7, 7, 0)
+    assert tuple(got.shape) == (300, 1024, 7, 7)
+    assert relerr(got, want) <= 1e-5
+    # empty roi list
+    e = ops.roi_align_forward(torch.from_numpy(feat).cuda(), torch.zeros(0, 5).cuda(), 1.0 / 16, 7, 7, 0)
+    assert tuple(e.shape) == (0, 1024, 7, 7)
+
+
+def test_roi_align_backward_vs_autograd(ops):
+    import torchvision
+    rs = np.random.RandomState(9)
+    feat = torch.from_numpy(rs.standard_normal((2, 16, 20, 31))).cuda()
+    rois = torch.from_numpy(np.concatenate([rs.randint(0, 2, (25, 1)).astype(np.float64),
+                                            np.sort(rs.uniform(0, 300, (25, 2)), 1)[:, [0]],
+                                            rs.uniform(0, 150, (25, 1)), rs.uniform(300, 480, (25, 1)),
+                                            rs.uniform(150, 310, (25, 1))], 1)).cuda()
+    f = feat.clone().requires_grad_(True)
+    o = torchvision.ops.roi_align(f, rois, (7, 7), 1.0 / 16, 0, False)    # same sampling rules, fp64 autograd
+    go = torch.randn_like(o)
+    o.backward(go)
+    got = ops.roi_align_backward(go.float(), rois.float(), 1.0 / 16, 7, 7, 2, 16, 20, 31, 0)
+    assert relerr(got, f.grad) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------ proposals
+def test_proposals_golden(ops, golden_dir):
+    prob, bbox, im_info = MG.proposal_case()
+    a = 12
+    b, _, fh, fw = bbox.shape
+    fg = torch.from_numpy(prob[:, a:]).permute(0, 2, 3, 1).reshape(b, -1).contiguous().cuda()
+    deltas = torch.from_numpy(bbox).permute(0, 2, 3, 1).reshape(b, -1, 4).contiguous().cuda()
+    base = torch.from_numpy(O.generate_anchors(scales=(4, 8, 16, 32))).float().cuda()
+    rois = ops.proposals(fg, deltas, base, torch.from_numpy(im_info).cuda(), fh, fw, 16, 6000, 300, 0.7)
+    want = torch.from_numpy(np.load(os.path.join(golden_dir, "proposals.npz"))["rois_test"])
+    # boxes go through expf on the device vs. torch's CPU exp: <= 2 ulp on coordinates of O(100)
+    assert (rois.cpu() - want).abs().max().item() <= 1e-3
+    assert torch.equal(rois.cpu()[:, :, 0], want[:, :, 0])
+
+
+@pytest.mark.parametrize("b,fh,fw,pre,post", [(4, 38, 63, 6000, 300), (1, 38, 50, 12000, 2000), (2, 50, 84, 6000, 1000)])
+def test_proposals_full_size_vs_oracle(ops, b, fh, fw, pre, post):
+    rs = np.random.RandomState(fh * fw + b)
+    a = 12
+    prob = torch.from_numpy(rs.uniform(0, 1, (b, 2 * a, fh, fw)).astype(np.float32))
+    bbox = torch.from_numpy((rs.standard_normal((b, 4 * a, fh, fw)) * 0.3).astype(np.float32))
+    im_info = torch.tensor([[fh * 16.0 - 8, fw * 16.0 - 5, 1.0]] * b)
+    base = O.generate_anchors(scales=(4, 8, 16, 32))
+    want, want_sc = O.proposal_layer(prob, bbox, im_info, base, 16, pre, post, 0.7, return_scores=True)
+    fg = prob[:, a:].permute(0, 2, 3, 1).reshape(b, -1).contiguous().cuda()
+    deltas = bbox.permute(0, 2, 3, 1).reshape(b, -1, 4).contiguous().cuda()
+    rois, sc, cnt = ops.proposals(fg, deltas, torch.from_numpy(base).float().cuda(), im_info.cuda(), fh, fw, 16, pre,
+                                  post, 0.7, want_scores=True)
+    # selection is bit-exact: the kept scores (inputs, untouched) must be identical, row by row
+    assert torch.equal(sc.cpu(), want_sc)
+    assert (rois.cpu() - want).abs().max().item() <= 1e-3
+    assert cnt.cpu().tolist() == [int((want_sc[i] > 0).sum()) for i in range(b)]
+
+
+# ------------------------------------------------------------------------------------ tensor-core GEMM / conv
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("m,k,n", [(128, 64, 64), (300, 192, 72), (2394, 1024, 256), (1000, 1200, 1024), (77, 3136, 1024),
+                                   (1200, 2048, 4), (14700, 147, 1024)])
+def test_linear(ops, split, m, k, n):
+    torch.manual_seed(m + k + n)
+    kp = (k + 7) // 8 * 8                                                   # row pitch (TMA wants 16-byte strides)
+    xf = torch.randn(m, kp, device="cuda")
+    wf = torch.randn(n, kp, device="cuda") * 0.05
+    bias = torch.randn(n, device="cuda")
+    P = ops.Pair
+    xh, wh = xf.to(torch.bfloat16), wf.to(torch.bfloat16)
+    xl, wl = (xf - xh.float()).to(torch.bfloat16), (wf - wh.float()).to(torch.bfloat16)
+    x, w = xf[:, :k], wf[:, :k]
+    xp = P(xh[:, :k], xl[:, :k] if split else None)                         # strided (pitch >= k) operands
+    wp = P(wh[:, :k], wl[:, :k] if split else None)
+    out = torch.empty(m, n, device="cuda")
+    ops.linear(xp, wp, n, bias=bias, out_f32=out, relu=True)
+    ref = torch.relu(xp.float().double() @ wp.float().double().t() + bias.double())
+    assert relerr(out, ref) <= 2e-5
+    if split:  # fp32-equivalent: also close to the unrounded operands
+        ref32 = torch.relu(x.double() @ w.double().t() + bias.double())
+        assert relerr(out, ref32) <= 3e-5
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("n,h,w,cin,cout,ks,stride", [(2, 38, 63, 256, 256, 3, 1), (3, 20, 20, 128, 128, 3, 1),
+                                                      (16, 4, 4, 512, 512, 3, 1), (2, 75, 125, 256, 128, 1, 2),
+                                                      (8, 7, 7, 1024, 512, 1, 2), (1, 150, 250, 64, 256, 1, 1),
+                                                      (1, 38, 63, 2048, 512, 3, 1), (5, 9, 11, 64, 72, 1, 1)])
+def test_conv(ops, split, n, h, w, cin, cout, ks, stride):
+    torch.manual_seed(h * w + cin)
+    F = torch.nn.functional
+    x = torch.randn(n, h, w, cin, device="cuda")
+    wt = torch.randn(cout, cin, ks, ks, device="cuda") / (cin * ks * ks) ** 0.5
+    scale = torch.rand(cout, device="cuda") + 0.5
+    bias = torch.randn(cout, device="cuda") * 0.1
+    xp = ops.Pair.from_float(x, split)
+    wp = ops.Pair.from_float(wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous(), split)
+    oh, ow = (h - 1) // stride + 1, (w - 1) // stride + 1
+    rp = ops.Pair.from_float(torch.randn(n, oh, ow, cout, device="cuda"), split)
+    out = ops.conv_nhwc(xp, wp, cout, ksize=ks, stride=stride, scale=scale, bias=bias, res=rp, relu=True, split=split)
+    xr = xp.float().double().permute(0, 3, 1, 2)
+    wr = wp.float().double().reshape(cout, ks, ks, cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, wr, stride=stride, padding=ks // 2) * scale.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1)
+    ref = torch.relu(ref + rp.float().double().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    tol = (2e-5 if cin * ks * ks < 8192 else 1e-4) if split else 6e-3   # bf16 output rounding dominates when !split
+    assert relerr(out.float(), ref) <= tol
+
+
+def test_stem_vs_oracle(ops):
+    p = O.make_params(5)
+    for (b, h, w) in [(1, 97, 131), (2, 320, 320), (1, 600, 1000)]:
+        im = torch.from_numpy((np.random.RandomState(h).standard_normal((b, 3, h, w)) * 50).astype(np.float32))
+        want = O.stem(im, p).permute(0, 2, 3, 1)
+        g, bb, m, v = [p["RCNN_base.1." + n].cuda() for n in ("weight", "bias", "running_mean", "running_var")]
+        sc = g / torch.sqrt(v + 1e-5)
+        got = ops.stem(im.cuda(), p["RCNN_base.0.weight"].cuda(), sc.contiguous(), (bb - m * sc).contiguous())
+        assert tuple(got.hi.shape) == tuple(want.shape)
+        assert relerr(got.float(), want) <= 2e-5

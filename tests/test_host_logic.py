@@ -1,0 +1,132 @@
+"""CPU tests of the host-side mirror of the reference interfaces (config surface, anchors, module
+state-dict contract, episode sharding incl. a world_size-2 gloo run)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import dana_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def cfgmod():
+    import dana_b200  # noqa: F401
+    from dana_b200 import config
+    config.reset_cfg()
+    yield config
+    config.reset_cfg()
+
+
+def test_cfg_defaults_and_yaml_merge(cfgmod):
+    cfg = cfgmod.cfg
+    assert cfg.POOLING_MODE == "crop" and cfg.TEST.RPN_POST_NMS_TOP_N == 300 and cfg.TRAIN.RPN_PRE_NMS_TOP_N == 12000
+    cfgmod.cfg_from_file(os.path.join(ROOT, "cfgs", "res50.yml"))
+    assert cfg.POOLING_MODE == "align" and cfg.TRAIN.BATCH_SIZE == 128 and cfg.TRAIN.BG_THRESH_LO == 0.0
+    cfgmod.cfg_from_list(["ANCHOR_SCALES", "[4,8,16,32]", "ANCHOR_RATIOS", "[0.5,1,2]", "MAX_NUM_GT_BOXES", "50"])
+    assert cfg.ANCHOR_SCALES == [4, 8, 16, 32] and cfg.MAX_NUM_GT_BOXES == 50
+    cfgmod.cfg_from_list(["TEST.RPN_POST_NMS_TOP_N", "1000"])
+    assert cfg.TEST.RPN_POST_NMS_TOP_N == 1000
+
+
+def test_cfg_strict_keys_and_types(cfgmod, tmp_path):
+    bad = tmp_path / "bad.yml"
+    bad.write_text("NOT_A_KEY: 1\n")
+    with pytest.raises(KeyError):
+        cfgmod.cfg_from_file(str(bad))
+    bad.write_text("POOLING_SIZE: seven\n")
+    with pytest.raises(ValueError):
+        cfgmod.cfg_from_file(str(bad))
+    with pytest.raises(AssertionError):
+        cfgmod.cfg_from_list(["POOLING_SIZE", "7.5"])
+    with pytest.raises(AssertionError):
+        cfgmod.cfg_from_list(["POOLING_SIZE"])
+    cfgmod.cfg_from_file(os.path.join(ROOT, "cfgs", "res101_ls.yml"))
+    assert cfgmod.cfg.TEST.SCALES == (800,) and cfgmod.cfg.TEST.RPN_POST_NMS_TOP_N == 1000
+
+
+def test_anchors_match_oracle():
+    import dana_b200  # noqa: F401
+    from dana_b200.anchors import generate_anchors
+    np.testing.assert_array_equal(generate_anchors(), O.generate_anchors())
+    np.testing.assert_array_equal(generate_anchors(scales=(4, 8, 16, 32)), O.generate_anchors(scales=(4, 8, 16, 32)))
+    # 12 anchors of the shipped CLI default, SURVEY.md section 8a
+    assert generate_anchors(scales=(4, 8, 16, 32))[0].tolist() == [-38, -16, 53, 31]
+    assert generate_anchors(scales=(4, 8, 16, 32))[11].tolist() == [-168, -344, 183, 359]
+
+
+def test_positional_encoding_matches_oracle():
+    import dana_b200  # noqa: F401
+    from dana_b200.engine import DanaEngine, positional_encoding
+    for n in (49, 196, 400):
+        assert torch.equal(positional_encoding(n), O.positional_encoding(n))
+    assert DanaEngine._trunk_hw(600, 1000) == (38, 63)
+    assert DanaEngine._trunk_hw(600, 800) == (38, 50)
+    assert DanaEngine._trunk_hw(800, 1333) == (50, 84)
+    assert DanaEngine._trunk_hw(320, 320) == (20, 20)
+
+
+def test_module_state_dict_contract(cfgmod):
+    """346 keys with the reference's names and shapes; trainable / frozen split of dana.py:350-368."""
+    cfgmod.cfg_from_file(os.path.join(ROOT, "cfgs", "res50.yml"))
+    cfgmod.cfg_from_list(["ANCHOR_SCALES", "[4,8,16,32]", "ANCHOR_RATIOS", "[0.5,1,2]"])
+    from dana_b200.dana import DAnARCNN
+    net = DAnARCNN(["bg", "fg"], "concat", 256, 256, pretrained=False, semantic_enhance=True, num_way=2, num_shot=3)
+    net.create_architecture()
+    sd = net.state_dict()
+    assert len(sd) == 346
+    shapes = {k: tuple(v.shape) for k, v in sd.items() if not k.endswith("num_batches_tracked")}
+    assert shapes == {k: tuple(v) for k, v in O.param_shapes().items()}
+    n_all = sum(p.numel() for p in net.parameters())
+    n_train = sum(p.numel() for p in net.parameters() if p.requires_grad)
+    assert round(n_all / 1e6, 2) == 37.39 and round(n_train / 1e6, 2) == 37.11
+    net.train()
+    assert not net.RCNN_base[1].training and not net.RCNN_base[4].training and net.RCNN_base[6].training
+    assert all(not m.training for m in net.RCNN_top.modules() if isinstance(m, torch.nn.BatchNorm2d))
+    with pytest.raises(RuntimeError):  # CUDA only, loudly
+        net.eval()(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3), torch.zeros(1, 1, 5), torch.zeros(1),
+                   torch.zeros(1, 3, 3, 320, 320))
+
+
+def test_shard_episodes():
+    import dana_b200  # noqa: F401
+    from dana_b200.sharding import shard_range
+    for n, w in ((32, 8), (10, 4), (3, 8), (0, 2)):
+        got = [shard_range(n, r, w) for r in range(w)]
+        flat = [i for a, b in got for i in range(a, b)]
+        assert flat == list(range(n))
+        sizes = [b - a for a, b in got]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import dana_b200  # noqa: F401
+    from dana_b200.sharding import aggregate_throughput, shard_range
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = shard_range(10, rank, world)
+    # rank 1 is "slower": whole-job throughput must use the max time and the summed units
+    value, t_max, units = aggregate_throughput(units=b - a, seconds=1.0 + rank, device="cpu")
+    if rank == 0:
+        out.put((value, t_max, units))
+    dist.destroy_process_group()
+
+
+def test_aggregate_throughput_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    value, t_max, units = q.get(timeout=10)
+    assert units == 10 and t_max == pytest.approx(2.0) and value == pytest.approx(5.0)
