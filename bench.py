@@ -1,0 +1,287 @@
+"""bench.py -- query-images/sec of the DAnA forward hot path (BASELINE.json configs[1]:
+res50 DAnA 2-way 3-shot, bs=4 per GPU, 600x1000 synthetic queries, full eval forward).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|bf16]
+
+One step = one eval forward over a batch of 4 episodes (4 queries + 4 x 6 support crops) per GPU.
+N > 1: launched by torchrun, one rank per GPU; episodes are sharded by rank with NO collective on the
+data path (weak scaling); torch.distributed only agrees on max step time / summed units.
+Prints ONE JSON line (see the task contract): value = device-timed throughput with inputs resident
+in HBM; e2e = same metric through DAnARCNN.forward with pinned-host inputs copied H2D and results
+read back D2H inside the timed region; roofline = the tensor-core implicit-GEMM kernel (dominant
+kernel of the step); cpu_baseline = the oracle port of the reference timed on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 4
+HEIGHT, WIDTH = 600, 1000
+WAYS, SHOTS = 2, 3
+WORKLOAD = "res50 DAnA 2-way 3-shot, bs=4/GPU, 600x1000 synthetic queries, full eval forward"
+# algorithmic-minimum FLOPs of one query: trunk 75.4 + 6 x 12.75 + CISA 9.2 + RPN 45.4
+# + layer4 143.4 + 2 head passes x 19.1
+GF_PER_QUERY = 388.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+
+    import dana_b200  # noqa: F401
+    from dana_b200 import ops
+    from dana_b200.config import cfg, cfg_from_file, cfg_from_list
+    from dana_b200.dana import DAnARCNN
+    from dana_b200.sharding import aggregate_throughput
+    from dana_b200.synthetic import synthetic_episode, synthetic_state_dict
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg_from_file(os.path.join(ROOT, "cfgs", "res50.yml"))
+    cfg_from_list(["ANCHOR_SCALES", "[4,8,16,32]", "ANCHOR_RATIOS", "[0.5,1,2]", "MAX_NUM_GT_BOXES", "50"])
+    net = DAnARCNN(["bg", "fg"], "concat", 256, 256, pretrained=False, semantic_enhance=True, num_way=WAYS,
+                   num_shot=SHOTS, precision=args.precision)
+    net.create_architecture()
+    net.load_state_dict(synthetic_state_dict(1996), strict=False)
+    net.to(dev).eval()
+    eng = net.engine()
+
+    b = BATCH_PER_GPU
+    im_h, info_h, sup_h = synthetic_episode(1000 + rank, b, HEIGHT, WIDTH, WAYS * SHOTS, pin=True)
+    gt_h, nb_h = torch.zeros(b, 1, 5).pin_memory(), torch.zeros(b).pin_memory()
+    im_d, info_d, sup_d = im_h.to(dev), info_h.to(dev), sup_h.to(dev)
+    gt_d, nb_d = gt_h.to(dev), nb_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(args.warmup):
+        net(im_d, info_d, gt_d, nb_d, sup_d)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.LAUNCHES = 0
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()                               # L2 flush between timed iterations (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        net(im_d, info_d, gt_d, nb_d, sup_d)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = ops.LAUNCHES
+    dev_s = sum(a.elapsed_time(c) for a, c in evs) / 1e3
+
+    # ---- end-to-end timing through the public module API (e2e): H2D of the step inputs + D2H of results
+    holders = [torch.empty_like(t, device=dev) for t in (im_h, info_h, gt_h, nb_h, sup_h)]
+
+    def e2e_step():
+        for hld, src in zip(holders, (im_h, info_h, gt_h, nb_h, sup_h)):
+            hld.copy_(src, non_blocking=True)
+        rois, cls_prob, bbox_pred, *_ = net(*holders)
+        return rois.cpu(), cls_prob.cpu(), bbox_pred.cpu()
+
+    for _ in range(max(1, args.warmup // 2)):
+        res = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(2)
+    h2d = sum(t.numel() * t.element_size() for t in (im_h, info_h, gt_h, nb_h, sup_h))
+    d2h = sum(t.numel() * t.element_size() for t in res)
+
+    # ---- roofline of the dominant kernel: one extra instrumented step, CUDA events around every
+    # tensor-core GEMM launch on the launching stream; algorithmic FLOPs = 2*M*N*K from the launch shapes
+    ops.GEMM_TRACE = []
+    net(im_d, info_d, gt_d, nb_d, sup_d)
+    torch.cuda.synchronize()
+    trace, ops.GEMM_TRACE = ops.GEMM_TRACE, None
+    g_ms = sum(a.elapsed_time(c) for a, c, _ in trace)
+    g_flops = sum(f for _, _, f in trace)
+    peaks = load_peaks()
+
+    value, t_max, units = aggregate_throughput(units=b * args.steps, seconds=dev_s, device=dev)
+    e2e_value, _, _ = aggregate_throughput(units=b * args.steps, seconds=e2e_s, device=dev)
+    if rank != 0:
+        return
+    line = {
+        "metric": "query-images/sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_max / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; fp32-equivalent)" if args.precision == "bf16x3" else "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": b, "query_hw": [HEIGHT, WIDTH], "ways": WAYS, "shots": SHOTS,
+                   "support_hw": [320, 320], "rois_per_image": 300, "precision": args.precision,
+                   "l2": "flushed (256 MiB memset) between timed iterations", "sharding": "episodes by rank, no collective"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "kernel": "dana::conv_gemm_kernel (tcgen05 implicit GEMM, all launches of a step)",
+                     "achieved": round(g_flops / (g_ms * 1e-3) / 1e12, 1) if g_ms > 0 else None,
+                     "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": round(g_flops / (g_ms * 1e-3) / 1e12 / peaks["tf_sustained"], 4) if g_ms > 0 else None,
+                     "traffic": None, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a step)",
+                     "launches_per_step": len(trace), "gemm_ms_per_step": round(g_ms, 3),
+                     "algorithmic_gflop_per_step": round(g_flops / 1e9, 1),
+                     "step_gflop_model": GF_PER_QUERY * b},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(sample_batch=1)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_forward_fn(batch):
+    """The oracle port of the reference forward (test infrastructure, timed here as the CPU baseline)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dana_oracle as O
+
+    import dana_b200  # noqa: F401
+    from dana_b200.synthetic import synthetic_episode, synthetic_state_dict
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = synthetic_state_dict(1996)
+    im, info, sup = synthetic_episode(1000, batch, HEIGHT, WIDTH, WAYS * SHOTS)
+    ref_nms = ref_roi = None
+    try:                                     # the reference's own compiled CPU operators, when they travelled
+        import build_ref
+        ref_c = build_ref.load()
+        if ref_c is not None:
+            ref_nms = lambda bx, sc, th: ref_c.nms(bx.contiguous(), sc.contiguous(), th)  # noqa: E731
+            ref_roi = lambda f, r, s, ph, pw, sr: ref_c.roi_align_forward(f.contiguous(), r.contiguous(), s, ph, pw, sr)  # noqa: E731
+    except Exception:  # noqa: BLE001
+        pass
+
+    def step():
+        with torch.no_grad():
+            return O.dana_forward_eval(p, im, info, sup, SHOTS, roi_align_fn=ref_roi, nms_fn=ref_nms)
+    kind = "port (oracle/dana_oracle.py; NMS + RoIAlign from the reference's compiled CPU kernels)" if ref_nms else \
+        "port (oracle/dana_oracle.py)"
+    return step, kind
+
+
+def cpu_baseline(sample_batch=1, reps=2):
+    step, kind = cpu_forward_fn(sample_batch)
+    step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": round(sample_batch / dt, 4), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "detail": kind, "sample": "%d query 600x1000 + 6 support crops per step, %d timed steps (+1 warm-up), torch CPU fp32, "
+                                      "%d threads" % (sample_batch, reps, os.cpu_count() or 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 1
+    step, kind = cpu_forward_fn(sample_batch)
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, 5))          # bounded: one 600x1000 query per step, a few seconds each
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = round(sample_batch * steps / dt, 4)
+    line = {"impl": "reference", "metric": "query-images/sec", "value": v, "unit": "images/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
+            "ms_per_step": round(1e3 * dt / steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "1 query + 6 supports per step on the host cores"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "detail": kind,
+                             "sample": "%d steps x 1 query 600x1000 (2-way 3-shot), torch CPU fp32, %d threads" % (steps, os.cpu_count() or 1)},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        a.warmup = max(a.warmup, 3)
+        run_ours(a)

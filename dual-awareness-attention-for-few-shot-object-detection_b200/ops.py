@@ -10,6 +10,17 @@ from . import _lib
 from ._lib import ConvGemmArgs, check
 
 
+# Kernel-launch accounting (bench.py's gpu_launches) and optional per-GEMM CUDA-event trace
+# (bench.py's roofline: list of (start_event, end_event, algorithmic_flops) on the launching stream).
+LAUNCHES = 0
+GEMM_TRACE = None
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -93,6 +104,15 @@ def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strid
     args.r_sx, args.r_sy, args.r_sn = [int(v) for v in r_strides]
     args.alpha = float(alpha)
     args.relu = 1 if relu else 0
+    _count(1)
+    if GEMM_TRACE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.load().dana_conv_gemm(ctypes.byref(args), _stream()), "dana_conv_gemm")
+        e1.record()
+        m = args.out_w * args.out_h * args.out_n
+        GEMM_TRACE.append((e0, e1, 2.0 * m * args.n_out * args.taps_r * args.taps_s * args.a_c))
+        return
     check(_lib.load().dana_conv_gemm(ctypes.byref(args), _stream()), "dana_conv_gemm")
 
 
@@ -171,6 +191,7 @@ def nms(boxes, scores, thresh: float):
     ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
     keep = torch.empty((n,), dtype=torch.int64, device=dev)
     count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _count(9)
     check(lib.dana_nms(_p(boxes), _p(scores), n, float(thresh), _p(keep), _p(count), _p(ws), wsb, _stream()),
           "dana_nms")
     return keep[: int(count.item())]
@@ -199,6 +220,7 @@ def proposals(fg_scores, deltas, base_anchors, im_info, feat_h, feat_w, feat_str
     rois = torch.empty((b, post_nms_top_n, 5), dtype=torch.float32, device=dev)
     sc = torch.empty((b, post_nms_top_n), dtype=torch.float32, device=dev) if want_scores else None
     cnt = torch.empty((b,), dtype=torch.int32, device=dev)
+    _count(10)
     check(_lib.load().dana_proposals(_p(fg_scores.contiguous()), _p(deltas.contiguous()),
                                      _p(base_anchors.contiguous().float()), _p(im_info.contiguous().float()), b,
                                      feat_h, feat_w, num_a, feat_stride, pre_nms_top_n, post_nms_top_n,
@@ -222,6 +244,7 @@ def roi_align_forward(inp, rois, spatial_scale, pooled_h, pooled_w, sampling_rat
     lib = _lib.load()
     wsb = lib.dana_roi_align_workspace_bytes(b, c, h, w, 0)
     ws = torch.empty((wsb,), dtype=torch.uint8, device=inp.device)
+    _count(2)
     check(lib.dana_roi_align_forward(_p(inp), _p(rois), r, b, c, h, w, pooled_h, pooled_w, float(spatial_scale),
                                      int(sampling_ratio), 0, _p(out), None, None, _p(ws), wsb, _stream()),
           "dana_roi_align_forward")
@@ -237,6 +260,7 @@ def roi_align_nhwc(feat_nhwc, rois, spatial_scale, pooled, sampling_ratio, *, wa
     dev = feat_nhwc.device
     out = torch.empty((r, pooled, pooled, c), dtype=torch.float32, device=dev) if want_f32 else None
     pair = Pair.empty((r, pooled, pooled, c), dev, split=split) if want_pair else None
+    _count(1)
     check(_lib.load().dana_roi_align_forward(_p(feat_nhwc), _p(rois), r, b, c, h, w, pooled, pooled,
                                              float(spatial_scale), int(sampling_ratio), 1, _p(out),
                                              _p(pair.hi) if pair else None,
@@ -252,6 +276,7 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch, cha
     grad = grad.contiguous().float()
     rois = rois.contiguous().float()
     gin = torch.empty((batch, channels, height, width), dtype=torch.float32, device=grad.device)
+    _count(1)
     check(_lib.load().dana_roi_align_backward(_p(grad), _p(rois), rois.shape[0], batch, channels, height, width,
                                               pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _p(gin),
                                               _stream()), "dana_roi_align_backward")
@@ -265,6 +290,7 @@ def stem(im_nchw, weight, scale, bias, split=True):
     conv_h, conv_w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     ph, pw = (conv_h - 2) // 2 + 1, (conv_w - 2) // 2 + 1
     out = Pair.empty((b, ph, pw, 64), im_nchw.device, split=split)
+    _count(1)
     check(_lib.load().dana_stem(_p(im_nchw.contiguous()), _p(weight), _p(scale), _p(bias), b, h, w, _p(out.hi),
                                 _p(out.lo), _stream()), "dana_stem")
     return out
@@ -273,6 +299,7 @@ def stem(im_nchw, weight, scale, bias, split=True):
 def avgpool(x: Pair, k: int):
     n, h, w, c = x.hi.shape
     out = torch.empty((n, h - k + 1, w - k + 1, c), dtype=torch.float32, device=x.hi.device)
+    _count(1)
     check(_lib.load().dana_avgpool(_p(x.hi), _p(x.lo), n, h, w, c, k, _p(out), _stream()), "dana_avgpool")
     return out
 
@@ -299,6 +326,7 @@ def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b
     vc = Pair.empty((maps * ns, c), dev, split=split)
     vt = Pair.zeros((sets, c, vt_pitch), dev, split=split)
     rbar = torch.empty((sets, c), **f)
+    _count(6)
     check(_lib.load().dana_support_prepare(in_hi, in_lo, in_f32, _p(pe), maps, shots, ns, c, _p(ba_w), _p(ba_b),
                                            float(gamma), _p(un_w), _p(un_b), float(unary_gamma), _p(v), _p(logit),
                                            _p(g), _p(r), _p(colmean), _p(vc.hi), _p(vc.lo), _p(vt.hi), _p(vt.lo),
@@ -311,6 +339,7 @@ def center_rows(x_f32, groups, group_rows, split=True):
     dev = x_f32.device
     out = Pair.empty((groups * group_rows, c), dev, split=split)
     sums = torch.empty((groups, c), dtype=torch.float32, device=dev) if group_rows > 256 else None
+    _count(2)
     check(_lib.load().dana_center_rows(_p(x_f32), groups, group_rows, c, _p(out.hi), _p(out.lo), _p(sums), _stream()),
           "dana_center_rows")
     return out
@@ -319,6 +348,7 @@ def center_rows(x_f32, groups, group_rows, split=True):
 def attn_softmax(logits_f32, segs, ns, split=True):
     rows, pitch = logits_f32.shape
     out = Pair.empty((rows, pitch), logits_f32.device, split=split)
+    _count(1)
     check(_lib.load().dana_attn_softmax(_p(logits_f32), rows, segs, ns, pitch, _p(out.hi), _p(out.lo), _stream()),
           "dana_attn_softmax")
     return out
@@ -330,6 +360,7 @@ def rpn_fg_prob(rpn_out_f32, num_a):
     dev = rpn_out_f32.device
     fg = torch.empty((b, h * w * num_a), dtype=torch.float32, device=dev)
     deltas = torch.empty((b, h * w * num_a, 4), dtype=torch.float32, device=dev)
+    _count(1)
     check(_lib.load().dana_rpn_fg_prob(_p(rpn_out_f32), b * h * w, num_a, pitch, _p(fg), _p(deltas), _stream()),
           "dana_rpn_fg_prob")
     return fg, deltas
@@ -338,6 +369,7 @@ def rpn_fg_prob(rpn_out_f32, num_a):
 def add_pe_split(x_f32, pe, period, out: Pair, out_pitch):
     rows = x_f32.numel() // x_f32.shape[-1]
     c = x_f32.shape[-1]
+    _count(1)
     check(_lib.load().dana_add_pe_split(_p(x_f32), _p(pe), rows, c, period, out_pitch, _p(out.hi), _p(out.lo),
                                         _stream()), "dana_add_pe_split")
     return out
@@ -345,6 +377,7 @@ def add_pe_split(x_f32, pe, period, out: Pair, out_pitch):
 
 def split_f32(x_f32, split=True):
     out = Pair.empty(tuple(x_f32.shape), x_f32.device, split=split)
+    _count(1)
     check(_lib.load().dana_split_f32(_p(x_f32.contiguous()), x_f32.numel(), _p(out.hi), _p(out.lo), _stream()),
           "dana_split_f32")
     return out
@@ -357,6 +390,7 @@ def merge_pair(x: Pair):
     rows = x.hi.numel() // c
     pitch = x.hi.stride(-2) if x.hi.dim() > 1 else c
     out = torch.empty(shape, dtype=torch.float32, device=x.hi.device)
+    _count(1)
     check(_lib.load().dana_merge_pair(_p(x.hi), _p(x.lo), rows, c, pitch, _p(out), _stream()), "dana_merge_pair")
     return out
 
@@ -366,6 +400,7 @@ def spatial_mean(x: Pair, split=True):
     dev = x.hi.device
     out = torch.empty((items, c), dtype=torch.float32, device=dev)
     pair = Pair.empty((items, c), dev, split=split)
+    _count(1)
     check(_lib.load().dana_spatial_mean(_p(x.hi), _p(x.lo), items, sp, c, _p(out), _p(pair.hi), _p(pair.lo),
                                         _stream()), "dana_spatial_mean")
     return out, pair
@@ -373,6 +408,7 @@ def spatial_mean(x: Pair, split=True):
 
 def softmax2(x_f32):
     out = torch.empty_like(x_f32)
+    _count(1)
     check(_lib.load().dana_softmax2(_p(x_f32.contiguous()), x_f32.shape[0], _p(out), _stream()), "dana_softmax2")
     return out
 
@@ -380,6 +416,7 @@ def softmax2(x_f32):
 def nhwc_pair_to_nchw(x: Pair):
     n, h, w, c = x.hi.shape
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.hi.device)
+    _count(1)
     check(_lib.load().dana_nhwc_pair_to_nchw(_p(x.hi), _p(x.lo), n, c, h * w, _p(out), _stream()),
           "dana_nhwc_pair_to_nchw")
     return out
