@@ -169,8 +169,8 @@ def run_ours(args):
     net(im_d, info_d, gt_d, nb_d, sup_d)
     torch.cuda.synchronize()
     trace, ops.GEMM_TRACE = ops.GEMM_TRACE, None
-    g_ms = sum(a.elapsed_time(c) for a, c, _ in trace)
-    g_flops = sum(f for _, _, f in trace)
+    g_ms = sum(t[0].elapsed_time(t[1]) for t in trace)
+    g_flops = sum(t[2] for t in trace)
     peaks = load_peaks()
 
     value, t_max, units = aggregate_throughput(units=b * args.steps, seconds=dev_s, device=dev)

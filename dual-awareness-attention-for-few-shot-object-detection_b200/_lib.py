@@ -26,7 +26,7 @@ class ConvGemmArgs(Structure):
         ("a_hi", c_void_p), ("a_lo", c_void_p),
         ("a_c", c_int64), ("a_w", c_int64), ("a_h", c_int64), ("a_n", c_int64),
         ("a_sx", c_int64), ("a_sy", c_int64), ("a_sn", c_int64),
-        ("taps_r", c_int32), ("taps_s", c_int32), ("pad", c_int32),
+        ("taps_r", c_int32), ("taps_s", c_int32), ("pad_y", c_int32), ("pad_x", c_int32),
         ("b_hi", c_void_p), ("b_lo", c_void_p),
         ("b_pitch", c_int64), ("b_batch_stride", c_int64),
         ("n_out", c_int32),
@@ -58,7 +58,8 @@ SIGNATURES = {
     "dana_roi_align_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_int, c_void_p, c_void_p]),
     "dana_conv_gemm": (c_int, [POINTER(ConvGemmArgs), c_void_p]),
-    "dana_stem": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dana_stem_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dana_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dana_avgpool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dana_support_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float,

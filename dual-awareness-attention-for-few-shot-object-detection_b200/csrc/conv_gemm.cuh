@@ -23,7 +23,7 @@ struct ConvGemmParams {
   CUtensorMap tm_b_hi, tm_b_lo;  // 3-D (k, co, batch), box (64, BLOCK_N, 1)
   int tiles_x, tiles_y, tiles_n, tiles_co;
   int bw, bh, bn;
-  int taps_r, taps_s, pad;
+  int taps_r, taps_s, pad_y, pad_x;
   int c_blocks;   // ceil(C_in / 64)
   int c_in;       // K extent per tap
   int n_out;      // output channels
@@ -135,10 +135,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int ka = cb * kTileK;
           const int kbk = tap * p.c_in + cb * kTileK;
-          tma_load_4d(st, &p.tm_a_hi, &full_bar[stage], ka, x0 + s - p.pad, y0 + r - p.pad, n0);
+          tma_load_4d(st, &p.tm_a_hi, &full_bar[stage], ka, x0 + s - p.pad_x, y0 + r - p.pad_y, n0);
           tma_load_3d(st + NSPLIT * kATileBytes, &p.tm_b_hi, &full_bar[stage], kbk, co_t * BLOCK_N, bcoord);
           if (NSPLIT == 2) {
-            tma_load_4d(st + kATileBytes, &p.tm_a_lo, &full_bar[stage], ka, x0 + s - p.pad, y0 + r - p.pad, n0);
+            tma_load_4d(st + kATileBytes, &p.tm_a_lo, &full_bar[stage], ka, x0 + s - p.pad_x, y0 + r - p.pad_y, n0);
             tma_load_3d(st + 2 * kATileBytes + Cfg::kBTileBytes, &p.tm_b_lo, &full_bar[stage], kbk, co_t * BLOCK_N,
                         bcoord);
           }

@@ -52,7 +52,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   if (a->out_hi == nullptr && a->out_f32 == nullptr) return DANA_EINVAL;
   if (a->n_out <= 0 || a->a_c <= 0 || a->out_w <= 0 || a->out_h <= 0 || a->out_n <= 0) return DANA_EINVAL;
   const int taps = a->taps_r * a->taps_s;
-  if (taps != 1 && taps != 9) return DANA_ENOTSUP;
+  if (taps < 1 || taps > 64) return DANA_EINVAL;
   if (taps > 1 && (a->a_c % 64) != 0) return DANA_EINVAL;
   // TMA alignment rules: 16-byte base and strides
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -76,7 +76,8 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   p.tiles_n = (a->out_n + tc.bn - 1) / tc.bn;
   p.taps_r = a->taps_r;
   p.taps_s = a->taps_s;
-  p.pad = a->pad;
+  p.pad_y = a->pad_y;
+  p.pad_x = a->pad_x;
   p.c_in = static_cast<int>(a->a_c);
   p.c_blocks = static_cast<int>((a->a_c + 63) / 64);
   p.n_out = a->n_out;

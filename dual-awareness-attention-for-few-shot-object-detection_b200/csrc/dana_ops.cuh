@@ -31,91 +31,117 @@ __device__ __forceinline__ void st_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stem: conv1 7x7/2 pad 3 (3->64, no bias) + frozen BN + ReLU + MaxPool 3x3/2 pad 0 ceil_mode
-// (lib/model/framework/resnet.py:109-113, dana.py:344).  Input NCHW fp32, output NHWC bf16 hi/lo.
-// One CTA = 8x8 pooled pixels = 17x17 conv pixels (halo recomputed), fp32 CUDA-core math.
+// Stem (lib/model/framework/resnet.py:109-113): conv1 7x7/2 pad 3 (3->64) + frozen BN + ReLU, then
+// MaxPool 3x3/2 pad 0 ceil_mode.  The 7x7 stride-2 convolution on 3 channels is rewritten as a 4x4
+// stride-1 convolution on the 2x2 space-to-depth image (12 -> 16 channels): four horizontally adjacent
+// s2d pixels are 64 contiguous bf16 = one 128-byte TMA/UMMA K-block, so conv1 runs on the tensor-core
+// implicit-GEMM kernel as a 4-tap (one per kernel row) K=256 GEMM with fused BN+ReLU.
+//   s2d[b][j_y][2 + j_x][(sy*2+sx)*3 + c] = im[b][c][2*j_y+sy][2*j_x+sx]   (0 outside, channels 12..15 = 0)
+//   rows are stored with 2 zero pixels on the left and >= 2 on the right so every 4-pixel window of an
+//   output column lies inside its own row.
 // ---------------------------------------------------------------------------------------------
-constexpr int kStemPT = 8;                      // pooled tile edge
-constexpr int kStemCT = 2 * kStemPT + 1;        // conv tile edge (17)
-constexpr int kStemIT = 2 * kStemCT + 5;        // input tile edge (39)
-constexpr int kStemInFloats = (3 * kStemIT * kStemIT + 3) / 4 * 4;  // keep the weight table 16-byte aligned
-constexpr int kStemSmem = (kStemInFloats + 147 * 64 + kStemCT * kStemCT * 65) * 4;
-
-__global__ void __launch_bounds__(256, 1)
-stem_kernel(const float* __restrict__ in, const float* __restrict__ w /*[64][3][7][7]*/,
-            const float* __restrict__ scale, const float* __restrict__ bias, int height, int width, int conv_h,
-            int conv_w, int pool_h, int pool_w, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-  extern __shared__ __align__(16) float s_stem[];
-  float* s_in = s_stem;                               // [3][39][39]
-  float* s_w = s_in + kStemInFloats;                  // [147][64]
-  float* s_c = s_w + 147 * 64;                        // [289][65]
-  const int b = blockIdx.z;
-  const int py0 = blockIdx.y * kStemPT, px0 = blockIdx.x * kStemPT;
-  const int cy0 = 2 * py0, cx0 = 2 * px0;             // first conv pixel of the tile
-  const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;     // first input pixel
-  const int tid = threadIdx.x;
-  const float* img = in + static_cast<long long>(b) * 3 * height * width;
-  for (int i = tid; i < 3 * kStemIT * kStemIT; i += 256) {
-    const int c = i / (kStemIT * kStemIT);
-    const int rem = i - c * kStemIT * kStemIT;
-    const int yy = rem / kStemIT, xx = rem - yy * kStemIT;
-    const int gy = iy0 + yy, gx = ix0 + xx;
-    s_in[i] = (gy >= 0 && gy < height && gx >= 0 && gx < width)
-                  ? __ldg(img + (static_cast<long long>(c) * height + gy) * width + gx)
-                  : 0.0f;
-  }
-  for (int i = tid; i < 147 * 64; i += 256) {
-    const int tap = i >> 6, co = i & 63;
-    s_w[i] = __ldg(w + co * 147 + tap);
-  }
-  __syncthreads();
-  const int cgp = tid & 3;   // 16-channel group
-  const int ps = tid >> 2;   // pixel slot 0..63
-  for (int p = ps; p < kStemCT * kStemCT; p += 64) {
-    const int cy = p / kStemCT, cx = p - cy * kStemCT;
-    float acc[16];
+// one thread per stored s2d pixel (incl. the zero border): 16 channels -> 32 B hi + 32 B lo
+__global__ void stem_s2d_kernel(const float* __restrict__ in, int batch, int height, int width, int h2, int w2,
+                                int wp, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  const long long total = static_cast<long long>(batch) * h2 * wp;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xp = static_cast<int>(i % wp);
+    const int jy = static_cast<int>((i / wp) % h2);
+    const int b = static_cast<int>(i / wp / h2);
+    const int jx = xp - 2;
+    float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
-    for (int c = 0; c < 3; ++c) {
-      for (int ky = 0; ky < 7; ++ky) {
-        const float* irow = s_in + (c * kStemIT + 2 * cy + ky) * kStemIT + 2 * cx;
-        const float* wrow = s_w + ((c * 7 + ky) * 7) * 64 + cgp * 16;
+    for (int k = 0; k < 16; ++k) v[k] = 0.0f;
+    if (jx >= 0 && jx < w2) {
+      const float* img = in + static_cast<long long>(b) * 3 * height * width;
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx) {
-          const float v = irow[kx];
-          const float4* w4 = reinterpret_cast<const float4*>(wrow + kx * 64);
+      for (int sy = 0; sy < 2; ++sy)
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 ww = w4[j4];
-            acc[j4 * 4 + 0] += v * ww.x;
-            acc[j4 * 4 + 1] += v * ww.y;
-            acc[j4 * 4 + 2] += v * ww.z;
-            acc[j4 * 4 + 3] += v * ww.w;
+        for (int sx = 0; sx < 2; ++sx) {
+          const int y = 2 * jy + sy, x = 2 * jx + sx;
+          if (y < height && x < width) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              v[(sy * 2 + sx) * 3 + c] = __ldg(img + (static_cast<long long>(c) * height + y) * width + x);
           }
         }
-      }
     }
-    const bool in_img = (cy0 + cy < conv_h) && (cx0 + cx < conv_w);
+    uint32_t ph[8], pl[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int co = cgp * 16 + j;
-      const float v = fmaxf(acc[j] * __ldg(scale + co) + __ldg(bias + co), 0.0f);
-      s_c[p * 65 + co] = in_img ? v : -INFINITY;  // ceil_mode windows ignore out-of-range pixels
+    for (int k = 0; k < 8; ++k) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * k], h0, l0);
+      split_bf16(v[2 * k + 1], h1, l1);
+      ph[k] = pack_bf16x2(h0, h1);
+      pl[k] = pack_bf16x2(l0, l1);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(out_hi + i * 16);
+    oh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    oh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+    if (out_lo != nullptr) {
+      uint4* ol = reinterpret_cast<uint4*>(out_lo + i * 16);
+      ol[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      ol[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
     }
   }
-  __syncthreads();
-  for (int i = tid; i < kStemPT * kStemPT * 64; i += 256) {
-    const int co = i & 63;
-    const int pp = i >> 6;
-    const int py = pp / kStemPT, px = pp - py * kStemPT;
-    if (py0 + py >= pool_h || px0 + px >= pool_w) continue;
-    float m = -INFINITY;
+}
+
+// MaxPool2d(3, stride 2, pad 0, ceil_mode) on an NHWC pair; thread per (pixel, 8-channel group)
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                    int batch, int h, int w, int c, int oh, int ow,
+                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  const int cg = c / 8;
+  const long long total = static_cast<long long>(batch) * oh * ow * cg;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    const int ox = static_cast<int>((i / cg) % ow);
+    const int oy = static_cast<int>((i / cg / ow) % oh);
+    const int b = static_cast<int>(i / cg / ow / oh);
+    float m[8];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = 2 * oy + dy;
+      if (y >= h) break;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = 2 * ox + dx;
+        if (x >= w) break;
+        const long long off = ((static_cast<long long>(b) * h + y) * w + x) * c + g * 8;
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + off));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        float v[8];
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, s_c[((2 * py + dy) * kStemCT + 2 * px + dx) * 65 + co]);
-    const long long o = ((static_cast<long long>(b) * pool_h + py0 + py) * pool_w + px0 + px) * 64 + co;
-    st_pair(out_hi, out_lo, o, m);
+        for (int e = 0; e < 4; ++e) {
+          v[2 * e] = __uint_as_float(aw[e] << 16);
+          v[2 * e + 1] = __uint_as_float(aw[e] & 0xFFFF0000u);
+        }
+        if (lo != nullptr) {
+          const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+          const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[2 * e] += __uint_as_float(lw[e] << 16);
+            v[2 * e + 1] += __uint_as_float(lw[e] & 0xFFFF0000u);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+      }
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(m[2 * e], h0, l0);
+      split_bf16(m[2 * e + 1], h1, l1);
+      ph[e] = pack_bf16x2(h0, h1);
+      pl[e] = pack_bf16x2(l0, l1);
+    }
+    const long long o = ((static_cast<long long>(b) * oh + oy) * ow + ox) * c + g * 8;
+    *reinterpret_cast<uint4*>(out_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 

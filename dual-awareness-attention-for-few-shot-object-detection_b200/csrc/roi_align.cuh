@@ -286,7 +286,8 @@ inline int roi_align_forward_run(const float* input, const float* rois, int num_
   } else if (layout == 1) {
     if (!out && !out_hi) return DANA_EINVAL;
     if (channels % 4 != 0) return DANA_ENOTSUP;
-    const int threads = (channels / 4 >= 256) ? 256 : ((channels / 4 + 31) / 32) * 32;
+    // >= 64 threads: warp 0 builds the y table, warp 1 the x table
+    const int threads = (channels / 4 >= 256) ? 256 : (((channels / 4 + 31) / 32) * 32 < 64 ? 64 : ((channels / 4 + 31) / 32) * 32);
     const int cg = threads * 4;
     static size_t configured = 0;
     if (table_bytes > 48 * 1024 && table_bytes > configured) {

@@ -83,7 +83,7 @@ class DanaEngine:
         dev, split = self.device, self.split
         sd = {k: v.detach().float() for k, v in sd.items()}
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
-        self.stem_w = f32(sd["RCNN_base.0.weight"])
+        self.stem_w = ops.pack_stem_weight(f32(sd["RCNN_base.0.weight"]), split)
         g, b, m, v = [f32(sd["RCNN_base.1." + n]) for n in ("weight", "bias", "running_mean", "running_var")]
         self.stem_scale = (g / torch.sqrt(v + BN_EPS)).contiguous()
         self.stem_bias = (b - m * self.stem_scale).contiguous()

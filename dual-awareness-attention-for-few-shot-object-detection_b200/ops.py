@@ -77,7 +77,7 @@ class Pair:
 
 # --------------------------------------------------------------------------- tensor-core GEMM / conv
 def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strides, *, out: Optional[Pair] = None,
-              out_f32=None, taps=(1, 1, 0), scale=None, bias=None, bias_sn=0, res: Optional[Pair] = None,
+              out_f32=None, taps=(1, 1, 0, 0), scale=None, bias=None, bias_sn=0, res: Optional[Pair] = None,
               res_f32=None, r_strides=(0, 0, 0), relu=False, alpha=1.0, b_pitch=None, b_batch_stride=0,
               tile=(0, 0, 0)):
     """Raw call of dana_conv_gemm; see include/dana_b200.h for the argument meaning."""
@@ -86,7 +86,7 @@ def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strid
     args.a_hi, args.a_lo = _p(a.hi), _p(a.lo)
     args.a_c, args.a_w, args.a_h, args.a_n = [int(v) for v in a_dims]
     args.a_sx, args.a_sy, args.a_sn = [int(v) for v in a_strides]
-    args.taps_r, args.taps_s, args.pad = taps
+    args.taps_r, args.taps_s, args.pad_y, args.pad_x = taps
     args.b_hi, args.b_lo = _p(w.hi), _p(w.lo)
     args.b_pitch = int(b_pitch if b_pitch is not None else w.hi.stride(-2))
     args.b_batch_stride = int(b_batch_stride)
@@ -111,7 +111,8 @@ def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strid
         check(_lib.load().dana_conv_gemm(ctypes.byref(args), _stream()), "dana_conv_gemm")
         e1.record()
         m = args.out_w * args.out_h * args.out_n
-        GEMM_TRACE.append((e0, e1, 2.0 * m * args.n_out * args.taps_r * args.taps_s * args.a_c))
+        GEMM_TRACE.append((e0, e1, 2.0 * m * args.n_out * args.taps_r * args.taps_s * args.a_c,
+                           (m, args.n_out, args.taps_r * args.taps_s * args.a_c, args.taps_r * args.taps_s)))
         return
     check(_lib.load().dana_conv_gemm(ctypes.byref(args), _stream()), "dana_conv_gemm")
 
@@ -127,13 +128,13 @@ def conv_nhwc(x: Pair, w: Pair, n_out: int, *, ksize=1, stride=1, scale=None, bi
         oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
         a_dims = (c, ow, oh, n)
         a_strides = (sx * stride, sy * stride, sn)
-        taps = (1, 1, 0)
+        taps = (1, 1, 0, 0)
     else:
         assert ksize == 3 and stride == 1
         oh, ow = h, wd
         a_dims = (c, wd, h, n)
         a_strides = (sx, sy, sn)
-        taps = (3, 3, 1)
+        taps = (3, 3, 1, 1)
     if out is None and out_f32 is None:
         out = Pair.empty((n, oh, ow, n_out), x.hi.device, split=split)
     ref = out.hi if out is not None else out_f32
@@ -284,15 +285,42 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch, cha
 
 
 # --------------------------------------------------------------------------- CUDA-core stages
-def stem(im_nchw, weight, scale, bias, split=True):
+def pack_stem_weight(w, split=True):
+    """conv1 weight [64,3,7,7] -> B operand [64, 4*64] of the space-to-depth form (load time, host side):
+    K index = d_y*64 + d_x*16 + (sy*2+sx)*3 + c  holds  w[co, c, 2*d_y+sy-1, 2*d_x+sx-1]  (0 when out of range)."""
+    co = w.shape[0]
+    packed = torch.zeros((co, 4, 4, 16), dtype=torch.float32, device=w.device)
+    for dy in range(4):
+        for dx in range(4):
+            for sy in range(2):
+                for sx in range(2):
+                    ky, kx = 2 * dy + sy - 1, 2 * dx + sx - 1
+                    if 0 <= ky < 7 and 0 <= kx < 7:
+                        q = (sy * 2 + sx) * 3
+                        packed[:, dy, dx, q:q + 3] = w[:, :, ky, kx]
+    return Pair.from_float(packed.reshape(co, 256).contiguous(), split)
+
+
+def stem(im_nchw, w_packed: Pair, scale, bias, split=True):
+    """conv1 + frozen BN + ReLU + ceil-mode max-pool (resnet.py:109-113): space-to-depth repack, 4-tap
+    tensor-core GEMM with the BN/ReLU epilogue, NHWC max-pool.  im [B,3,H,W] fp32 -> pair [B,Hp,Wp,64]."""
     b, c, h, w = im_nchw.shape
     assert c == 3
-    conv_h, conv_w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-    ph, pw = (conv_h - 2) // 2 + 1, (conv_w - 2) // 2 + 1
-    out = Pair.empty((b, ph, pw, 64), im_nchw.device, split=split)
+    dev = im_nchw.device
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    wp = w2 + 4
+    s2d = Pair.empty((b, h2, wp, 16), dev, split=split)
+    lib = _lib.load()
     _count(1)
-    check(_lib.load().dana_stem(_p(im_nchw.contiguous()), _p(weight), _p(scale), _p(bias), b, h, w, _p(out.hi),
-                                _p(out.lo), _stream()), "dana_stem")
+    check(lib.dana_stem_s2d(_p(im_nchw.contiguous()), b, h, w, _p(s2d.hi), _p(s2d.lo), _stream()), "dana_stem_s2d")
+    conv = Pair.empty((b, h2, w2, 64), dev, split=split)
+    conv_gemm(s2d, (64, w2, h2, b), (16, wp * 16, h2 * wp * 16), w_packed, 64, (w2, h2, b),
+              (64, w2 * 64, h2 * w2 * 64), out=conv, taps=(4, 1, 2, 0), scale=scale, bias=bias, relu=True)
+    ph, pw = (h2 - 2) // 2 + 1, (w2 - 2) // 2 + 1
+    out = Pair.empty((b, ph, pw, 64), dev, split=split)
+    _count(1)
+    check(lib.dana_maxpool3x3s2(_p(conv.hi), _p(conv.lo), b, h2, w2, 64, _p(out.hi), _p(out.lo), _stream()),
+          "dana_maxpool3x3s2")
     return out
 
 

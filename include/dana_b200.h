@@ -103,7 +103,8 @@ typedef struct dana_conv_gemm_args {
   const void* a_lo; /* NULL -> plain bf16 */
   int64_t a_c, a_w, a_h, a_n;       /* extents of the (strided) input view        */
   int64_t a_sx, a_sy, a_sn;         /* element strides of x, y, n (c stride is 1) */
-  int32_t taps_r, taps_s, pad;      /* 1,1,0 or 3,3,1                             */
+  int32_t taps_r, taps_s;           /* filter taps (rows, cols): 1x1, 3x3, 4x1 ... */
+  int32_t pad_y, pad_x;             /* tap (r,s) reads input (y + r - pad_y, x + s - pad_x) */
   const void* b_hi;
   const void* b_lo;
   int64_t b_pitch;        /* elements between consecutive output channels (>= taps*c_in) */
@@ -131,10 +132,13 @@ int dana_conv_gemm(const dana_conv_gemm_args* args, void* stream);
  * CUDA-core stages of the path (each replaces the torch ops named).
  * bf16 "pairs" are (hi, lo) planes with x ~= hi + lo; lo may be NULL.
  * ------------------------------------------------------------------------ */
-/* conv1 7x7/2 + frozen BN + ReLU + MaxPool 3x3/2 ceil_mode (lib/model/framework/resnet.py:109-113).
- * in [B,3,H,W] fp32 NCHW; weight [64,3,7,7]; out NHWC pair [B, Hp, Wp, 64]. */
-int dana_stem(const float* in_nchw, const float* weight, const float* scale, const float* bias, int batch, int height,
-              int width, void* out_hi, void* out_lo, void* stream);
+/* Stem, lib/model/framework/resnet.py:109-113.  conv1 7x7/2 pad 3 is run by dana_conv_gemm as a 4-tap
+ * K=256 GEMM over the 2x2 space-to-depth image written by dana_stem_s2d:
+ *   in [B,3,H,W] fp32 NCHW -> pair [B, ceil(H/2), ceil(W/2)+4, 16] (2 zero pixels left, >=2 right).
+ * dana_maxpool3x3s2: MaxPool2d(3, 2, 0, ceil_mode=True) on an NHWC pair. */
+int dana_stem_s2d(const float* in_nchw, int batch, int height, int width, void* out_hi, void* out_lo, void* stream);
+int dana_maxpool3x3s2(const void* in_hi, const void* in_lo, int batch, int h, int w, int c, void* out_hi, void* out_lo,
+                      void* stream);
 /* nn.AvgPool2d(k, stride=1) on NHWC pairs -> fp32 NHWC (lib/model/framework/dana.py:42,114). */
 int dana_avgpool(const void* in_hi, const void* in_lo, int maps, int h, int w, int c, int k, float* out, void* stream);
 /* Support side of BA + CISA (dana.py:126-147; rcnn_head :255-276 with ba_w == NULL): positional

@@ -192,7 +192,7 @@ def g_stem():
         wt = torch.randn(64, 3, 7, 7, device=DEV) * 0.05
         scale = torch.rand(64, device=DEV) + 0.5
         bias = torch.randn(64, device=DEV)
-        out = ops.stem(im, wt, scale, bias)
+        out = ops.stem(im, ops.pack_stem_weight(wt), scale, bias)
         ref = F.conv2d(im.double(), wt.double(), stride=2, padding=3)
         ref = torch.relu(ref * scale.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1))
         ref = F.max_pool2d(ref, 3, 2, 0, ceil_mode=True).permute(0, 2, 3, 1)

@@ -214,6 +214,6 @@ def test_stem_vs_oracle(ops):
         want = O.stem(im, p).permute(0, 2, 3, 1)
         g, bb, m, v = [p["RCNN_base.1." + n].cuda() for n in ("weight", "bias", "running_mean", "running_var")]
         sc = g / torch.sqrt(v + 1e-5)
-        got = ops.stem(im.cuda(), p["RCNN_base.0.weight"].cuda(), sc.contiguous(), (bb - m * sc).contiguous())
+        got = ops.stem(im.cuda(), ops.pack_stem_weight(p["RCNN_base.0.weight"].cuda()), sc.contiguous(), (bb - m * sc).contiguous())
         assert tuple(got.hi.shape) == tuple(want.shape)
         assert relerr(got.float(), want) <= 2e-5
