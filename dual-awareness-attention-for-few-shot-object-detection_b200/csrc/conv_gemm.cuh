@@ -12,7 +12,7 @@
 // Structure: persistent CTAs (one per SM), 6 warps.
 //   warp 0      TMA producer: walks (tap, 64-channel block) k-blocks through a smem ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, double-buffered accumulators
-//   warps 2..5  epilogue: tcgen05.ld -> scale/bias (folded BN), residual, ReLU -> bf16 hi/lo or fp32
+//   warps 2..9  epilogue: tcgen05.ld -> scale/bias (folded BN), residual, ReLU -> bf16 hi/lo or fp32
 #pragma once
 #include "tc_common.cuh"
 
@@ -44,7 +44,7 @@ struct ConvGemmParams {
   float* out_f32;
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
 constexpr int kTileM = 128;
 constexpr int kTileK = 64;
 constexpr int kATileBytes = kTileM * kTileK * 2;  // 16 KB per plane
@@ -57,7 +57,8 @@ struct ConvGemmCfg {
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulators
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2 * BLOCK_N * 4 /*scale,bias*/ + 256;
+  static constexpr int kXposeBytes = 8 * 4096;  // one 32x32 fp32 transposition buffer per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kXposeBytes + 2 * BLOCK_N * 4 /*scale,bias*/ + 256;
 };
 
 template <int BLOCK_N, int NSPLIT>
@@ -68,10 +69,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(kStages >= 2, "pipeline too shallow");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tiles = smem;                                   // kStages * kStageBytes
-  float* s_scale = reinterpret_cast<float*>(tiles + kStages * Cfg::kStageBytes);
+  // No alignment slack: the budget of the <256, 2> configuration is within 1 KB of the 227 KB limit.  The dynamic
+  // window starts at offset 0 of the CTA's shared memory (the kernel has no static __shared__), which is
+  // 1024-byte aligned as SWIZZLE_128B needs; checked below.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* tiles = smem_raw;                               // kStages * kStageBytes
+  float* s_xpose = reinterpret_cast<float*>(tiles + kStages * Cfg::kStageBytes);   // [8 warps][32][32]
+  float* s_scale = s_xpose + Cfg::kXposeBytes / 4;
   float* s_bias = s_scale + BLOCK_N;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
   uint64_t* full_bar = bars;                 // [kStages]
@@ -87,6 +91,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int sp_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int num_tiles = sp_tiles * p.tiles_co;
 
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) {
+    atomicExch(&g_device_error, 105);
+    __trap();
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a_hi);
     tma_prefetch_desc(&p.tm_b_hi);
@@ -100,7 +108,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], 8);
     }
     fence_mbar_init();
   }
@@ -196,150 +204,212 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;              // TMEM lane quarter this warp may read
-    const int m = q * 32 + lane;         // tile row
-    const int et = threadIdx.x - 64;     // 0..127
-    const int bw_i = m % p.bw;
-    const int bh_i = (m / p.bw) % p.bh;
-    const int bn_i = m / (p.bw * p.bh);
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter; each owns half of the tile's 32-column chunks.  A chunk goes
+    //   TMEM --tcgen05.ld--> registers (one row per lane) --scale/bias--> 32x32 fp32 smem tile (16-byte XOR
+    //   swizzle, conflict free both ways) --> registers (8 consecutive channels per lane, 4 lanes per row)
+    // so that every global access of the warp is row-contiguous: the residual read and the bf16 hi/lo (or
+    // fp32) store move 64..128 contiguous bytes per row instead of 16 bytes at 32 different rows.
+    // The residual of the next chunk is requested before the current one is processed.
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                // which half of the chunks
+    const int et = threadIdx.x - 64;                 // 0..255
+    float* tb = s_xpose + (warp - 2) * 1024;         // this warp's transposition tile
+    constexpr int kChunks = BLOCK_N / 32;
+    constexpr int kCpw = kChunks >= 2 ? kChunks / 2 : 1;   // chunks per warp
+    const int c_begin = half * kCpw;
+    const int sub = lane >> 2;                       // row within an 8-row group (phase B)
+    const int cg = (lane & 3) * 8;                   // first channel of this lane's group (phase B)
+    auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    const bool res_pair = (p.res_hi != nullptr);
+    const bool res_lo = (p.res_lo != nullptr);
+    const bool res_vec = res_pair && al16(p.res_hi) && (!res_lo || al16(p.res_lo)) && (p.sr_x % 8 == 0) &&
+                         (p.sr_y % 8 == 0) && (p.sr_n % 8 == 0);
+    const bool out_vec = (p.out_hi == nullptr || (al16(p.out_hi) && (p.out_lo == nullptr || al16(p.out_lo)) &&
+                                                  (p.so_x % 8 == 0) && (p.so_y % 8 == 0) && (p.so_n % 8 == 0))) &&
+                         (p.out_f32 == nullptr || (al16(p.out_f32) && (p.so_x % 4 == 0) && (p.so_y % 4 == 0) &&
+                                                   (p.so_n % 4 == 0))) &&
+                         (p.res_f32 == nullptr || (al16(p.res_f32) && (p.sr_x % 4 == 0) && (p.sr_y % 4 == 0) &&
+                                                   (p.sr_n % 4 == 0)));
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int co_t = t % p.tiles_co;
       const int sp = t / p.tiles_co;
-      const int x = (sp % p.tiles_x) * p.bw + bw_i;
-      const int y = ((sp / p.tiles_x) % p.tiles_y) * p.bh + bh_i;
-      const int n = (sp / (p.tiles_x * p.tiles_y)) * p.bn + bn_i;
-      const bool row_ok = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
+      const int tx0 = (sp % p.tiles_x) * p.bw;
+      const int ty0 = ((sp / p.tiles_x) % p.tiles_y) * p.bh;
+      const int tn0 = (sp / (p.tiles_x * p.tiles_y)) * p.bn;
       const int co0 = co_t * BLOCK_N;
+      // the four rows this lane serves in phase B
+      long long o_off[4], r_off[4];
+      bool row_ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = q * 32 + 8 * i + sub;
+        const int x = tx0 + m % p.bw;
+        const int y = ty0 + (m / p.bw) % p.bh;
+        const int n = tn0 + m / (p.bw * p.bh);
+        row_ok[i] = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
+        o_off[i] = static_cast<long long>(n) * p.so_n + static_cast<long long>(y) * p.so_y +
+                   static_cast<long long>(x) * p.so_x;
+        r_off[i] = static_cast<long long>(n) * p.sr_n + static_cast<long long>(y) * p.sr_y +
+                   static_cast<long long>(x) * p.sr_x;
+      }
 
-      // stage per-channel scale / bias for this tile
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < BLOCK_N; i += 128) {
+      uint4 rh[4], rl[4];
+      auto prefetch = [&](int c) {
+        const int col = co0 + c * 32 + cg;
+        if (res_vec && col + 8 <= p.n_out) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (row_ok[i]) {
+              rh[i] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + r_off[i] + col));
+              if (res_lo) rl[i] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + r_off[i] + col));
+            }
+          }
+        }
+      };
+      if (c_begin < kChunks) prefetch(c_begin);
+
+      // stage per-channel scale (x alpha) / bias for this tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < BLOCK_N; i += 256) {
         const int co = co0 + i;
-        s_scale[i] = (p.scale != nullptr && co < p.n_out) ? __ldg(p.scale + co) : 1.0f;
+        s_scale[i] = ((p.scale != nullptr && co < p.n_out) ? __ldg(p.scale + co) : 1.0f) * p.alpha;
         s_bias[i] = (p.bias != nullptr && co < p.n_out)
-                        ? __ldg(p.bias + static_cast<long long>(sp / (p.tiles_x * p.tiles_y)) * p.bn * p.bias_sn + co)
+                        ? __ldg(p.bias + static_cast<long long>(tn0) * p.bias_sn + co)
                         : 0.0f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       mbar_wait(&acc_full[acc], acc_phase, 104);
       tc_fence_after();
-      const long long o_off = static_cast<long long>(n) * p.so_n + static_cast<long long>(y) * p.so_y +
-                              static_cast<long long>(x) * p.so_x;
-      const long long r_off = static_cast<long long>(n) * p.sr_n + static_cast<long long>(y) * p.sr_y +
-                              static_cast<long long>(x) * p.sr_x;
-      const bool have_res = (p.res_hi != nullptr) || (p.res_f32 != nullptr);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+#pragma unroll
+      for (int ci = 0; ci < kCpw; ++ci) {
+        const int c = c_begin + ci;
+        if (c >= kChunks) break;
+        // ---- phase A: accumulator row -> scale/bias -> swizzled smem tile
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * BLOCK_N + c * 32);
         tmem_ld32(taddr, v);
+        uint4 ch[4], cl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ch[i] = rh[i];
+          cl[i] = rl[i];
+        }
+        if (ci + 1 < kCpw && c + 1 < kChunks) prefetch(c + 1);
         tmem_ld_wait();
-        const int cbase = co0 + c * 32;
-        if (row_ok && cbase < p.n_out) {
-          const bool full = (cbase + 32 <= p.n_out);
-          float f[32];
+        {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
+          const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+          float4* trow = reinterpret_cast<float4*>(tb + lane * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha * s_scale[c * 32 + j] + s_bias[c * 32 + j];
-          if (have_res) {
-            if (p.res_f32 != nullptr) {
-              const float* rp = p.res_f32 + r_off + cbase;
+          for (int g = 0; g < 8; ++g) {
+            const float4 sc = sc4[g], bi = bi4[g];
+            float4 o;
+            o.x = __uint_as_float(v[g * 4 + 0]) * sc.x + bi.x;
+            o.y = __uint_as_float(v[g * 4 + 1]) * sc.y + bi.y;
+            o.z = __uint_as_float(v[g * 4 + 2]) * sc.z + bi.z;
+            o.w = __uint_as_float(v[g * 4 + 3]) * sc.w + bi.w;
+            trow[g ^ (lane & 7)] = o;
+          }
+        }
+        __syncwarp();
+        // ---- phase B: 8 consecutive channels of 4 rows per lane, row-contiguous global accesses
+        const int col = co0 + c * 32 + cg;
+        const bool col_full = (col + 8 <= p.n_out);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || cbase + j < p.n_out) f[j] += __ldg(rp + j);
+        for (int i = 0; i < 4; ++i) {
+          const int r = 8 * i + sub;
+          const float4* trow = reinterpret_cast<const float4*>(tb + r * 32);
+          const float4 a = trow[(2 * (lane & 3)) ^ (r & 7)];
+          const float4 b = trow[(2 * (lane & 3) + 1) ^ (r & 7)];
+          if (!row_ok[i] || col >= p.n_out) continue;
+          float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (p.res_f32 != nullptr) {
+            const float* rp = p.res_f32 + r_off[i] + col;
+            if (col_full && out_vec) {
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+              const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp) + 1);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
             } else {
-              const __nv_bfloat16* rh = p.res_hi + r_off + cbase;
-              const bool vec = full && ((reinterpret_cast<uintptr_t>(rh) & 15) == 0);
-              if (vec) {
-                const uint4* rh4 = reinterpret_cast<const uint4*>(rh);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const uint4 w = __ldg(rh4 + g);
-                  const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+              for (int k = 0; k < 8; ++k)
+                if (col + k < p.n_out) f[k] += __ldg(rp + k);
+            }
+          } else if (res_pair) {
+            if (res_vec && col_full) {
+              const uint32_t wh[4] = {ch[i].x, ch[i].y, ch[i].z, ch[i].w};
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    f[g * 8 + e * 2] += __uint_as_float(ws[e] << 16);
-                    f[g * 8 + e * 2 + 1] += __uint_as_float(ws[e] & 0xFFFF0000u);
-                  }
+              for (int e = 0; e < 4; ++e) {
+                f[2 * e] += __uint_as_float(wh[e] << 16);
+                f[2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u);
+              }
+              if (res_lo) {
+                const uint32_t wl[4] = {cl[i].x, cl[i].y, cl[i].z, cl[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f[2 * e] += __uint_as_float(wl[e] << 16);
+                  f[2 * e + 1] += __uint_as_float(wl[e] & 0xFFFF0000u);
                 }
-                if (p.res_lo != nullptr) {
-                  const uint4* rl4 = reinterpret_cast<const uint4*>(p.res_lo + r_off + cbase);
+              }
+            } else {
 #pragma unroll
-                  for (int g = 0; g < 4; ++g) {
-                    const uint4 w = __ldg(rl4 + g);
-                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      f[g * 8 + e * 2] += __uint_as_float(ws[e] << 16);
-                      f[g * 8 + e * 2 + 1] += __uint_as_float(ws[e] & 0xFFFF0000u);
-                    }
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if (full || cbase + j < p.n_out) {
-                    f[j] += __bfloat162float(rh[j]);
-                    if (p.res_lo != nullptr) f[j] += __bfloat162float(p.res_lo[r_off + cbase + j]);
-                  }
+              for (int k = 0; k < 8; ++k) {
+                if (col + k < p.n_out) {
+                  f[k] += __bfloat162float(p.res_hi[r_off[i] + col + k]);
+                  if (res_lo) f[k] += __bfloat162float(p.res_lo[r_off[i] + col + k]);
                 }
               }
             }
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
           }
           if (p.out_f32 != nullptr) {
-            float* op = p.out_f32 + o_off + cbase;
-            if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-              float4* o4 = reinterpret_cast<float4*>(op);
-#pragma unroll
-              for (int g = 0; g < 8; ++g) o4[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+            float* op = p.out_f32 + o_off[i] + col;
+            if (col_full && out_vec) {
+              reinterpret_cast<float4*>(op)[0] = make_float4(f[0], f[1], f[2], f[3]);
+              reinterpret_cast<float4*>(op)[1] = make_float4(f[4], f[5], f[6], f[7]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || cbase + j < p.n_out) op[j] = f[j];
+              for (int k = 0; k < 8; ++k)
+                if (col + k < p.n_out) op[k] = f[k];
             }
           }
           if (p.out_hi != nullptr) {
-            __nv_bfloat16* oh = p.out_hi + o_off + cbase;
-            __nv_bfloat16* ol = (p.out_lo != nullptr) ? p.out_lo + o_off + cbase : nullptr;
-            uint32_t ph[16], pl[16];
+            uint32_t ph[4], pl[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int e = 0; e < 4; ++e) {
               __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(f[2 * j], h0, l0);
-              split_bf16(f[2 * j + 1], h1, l1);
-              ph[j] = pack_bf16x2(h0, h1);
-              pl[j] = pack_bf16x2(l0, l1);
+              split_bf16(f[2 * e], h0, l0);
+              split_bf16(f[2 * e + 1], h1, l1);
+              ph[e] = pack_bf16x2(h0, h1);
+              pl[e] = pack_bf16x2(l0, l1);
             }
-            if (full && ((reinterpret_cast<uintptr_t>(oh) & 15) == 0)) {
-              uint4* o4 = reinterpret_cast<uint4*>(oh);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) o4[g] = make_uint4(ph[g * 4], ph[g * 4 + 1], ph[g * 4 + 2], ph[g * 4 + 3]);
-              if (ol != nullptr) {
-                uint4* l4 = reinterpret_cast<uint4*>(ol);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) l4[g] = make_uint4(pl[g * 4], pl[g * 4 + 1], pl[g * 4 + 2], pl[g * 4 + 3]);
-              }
+            __nv_bfloat16* oh = p.out_hi + o_off[i] + col;
+            __nv_bfloat16* ol = (p.out_lo != nullptr) ? p.out_lo + o_off[i] + col : nullptr;
+            if (col_full && out_vec) {
+              *reinterpret_cast<uint4*>(oh) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              if (ol != nullptr) *reinterpret_cast<uint4*>(ol) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (full || cbase + j < p.n_out) {
-                  const uint32_t wh = ph[j >> 1], wl = pl[j >> 1];
-                  oh[j] = __ushort_as_bfloat16(static_cast<unsigned short>((j & 1) ? (wh >> 16) : (wh & 0xFFFF)));
+              for (int k = 0; k < 8; ++k) {
+                if (col + k < p.n_out) {
+                  const uint32_t wh = ph[k >> 1], wl = pl[k >> 1];
+                  oh[k] = __ushort_as_bfloat16(static_cast<unsigned short>((k & 1) ? (wh >> 16) : (wh & 0xFFFF)));
                   if (ol != nullptr)
-                    ol[j] = __ushort_as_bfloat16(static_cast<unsigned short>((j & 1) ? (wl >> 16) : (wl & 0xFFFF)));
+                    ol[k] = __ushort_as_bfloat16(static_cast<unsigned short>((k & 1) ? (wl >> 16) : (wl & 0xFFFF)));
                 }
               }
             }
           }
         }
+        __syncwarp();   // the tile is rewritten by the next chunk's phase A
       }
       // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
       tc_fence_before();

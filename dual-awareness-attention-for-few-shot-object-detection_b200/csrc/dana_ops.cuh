@@ -197,7 +197,7 @@ __global__ void support_pe_logit_kernel(const __nv_bfloat16* __restrict__ in_hi,
   }
 }
 
-// block per map: p = softmax_n(logit); wsum[c] = sum_n p_n v[n][c]; colmean[c] = mean_n v[n][c]
+// grid (maps, c/32), block 256: p = softmax_n(logit); wsum[c] = sum_n p_n v[n][c]; colmean[c] = mean_n v[n][c]
 __global__ void __launch_bounds__(256)
 support_softmax_wsum_kernel(const float* __restrict__ v, const float* __restrict__ logit, int ns, int c,
                             float* __restrict__ wsum, float* __restrict__ colmean) {
@@ -225,16 +225,31 @@ support_softmax_wsum_kernel(const float* __restrict__ v, const float* __restrict
   sum = 0.0f;
   for (int i = 0; i < (blockDim.x >> 5); ++i) sum += s_red[i];
   const float inv = 1.0f / sum;
+  __syncthreads();
+  // this CTA's 32-channel slab: lane = channel (128-byte coalesced rows), 8 warps stride the positions
+  __shared__ float s_a[8][33], s_m[8][33];
+  const int ch = blockIdx.y * 32 + lane;
   const float* vm = v + static_cast<long long>(m) * ns * c;
-  for (int ch = tid; ch < c; ch += blockDim.x) {
-    float a = 0.0f, mean = 0.0f;
-    for (int n = 0; n < ns; ++n) {
+  float a = 0.0f, mean = 0.0f;
+  if (ch < c) {
+    for (int n = warp; n < ns; n += 8) {
       const float x = vm[static_cast<long long>(n) * c + ch];
       a += (s_p[n] * inv) * x;
       mean += x;
     }
-    if (wsum) wsum[static_cast<long long>(m) * c + ch] = a;
-    if (colmean) colmean[static_cast<long long>(m) * c + ch] = mean / static_cast<float>(ns);
+  }
+  s_a[warp][lane] = a;
+  s_m[warp][lane] = mean;
+  __syncthreads();
+  if (warp == 0 && ch < c) {
+    float ta = 0.0f, tm = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ta += s_a[i][lane];
+      tm += s_m[i][lane];
+    }
+    if (wsum) wsum[static_cast<long long>(m) * c + ch] = ta;
+    if (colmean) colmean[static_cast<long long>(m) * c + ch] = tm / static_cast<float>(ns);
   }
 }
 
