@@ -32,18 +32,41 @@ inline TileChoice choose_tile(int w, int h, int n, bool batched_b) {
   return best;
 }
 
-template <int BLOCK_N, int NSPLIT>
-inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+template <int BLOCK_N, int NSPLIT, bool FAST>
+inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT>;
   static bool configured = false;
   if (!configured) {
-    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT>,
+    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, FAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  conv_gemm_kernel<BLOCK_N, NSPLIT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  conv_gemm_kernel<BLOCK_N, NSPLIT, FAST><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   DANA_LAUNCH_CHECK();
   return DANA_OK;
+}
+
+// The fast epilogue needs: bf16 pair output only, full 32-column chunks, 16-byte aligned pointers and
+// strides that are multiples of 8 elements (so every 8-channel group is one aligned 16-byte access).
+inline bool fast_epilogue_ok(const ConvGemmParams& p, int nsplit) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (p.out_f32 != nullptr || p.res_f32 != nullptr || p.out_hi == nullptr) return false;
+  if ((p.n_out % 32) != 0) return false;
+  if (!al16(p.out_hi) || (p.so_x % 8) || (p.so_y % 8) || (p.so_n % 8)) return false;
+  if (nsplit == 2 && (p.out_lo == nullptr || !al16(p.out_lo))) return false;
+  if (nsplit == 1 && p.out_lo != nullptr) return false;
+  if (p.res_hi != nullptr) {
+    if (!al16(p.res_hi) || (p.sr_x % 8) || (p.sr_y % 8) || (p.sr_n % 8)) return false;
+    if (nsplit == 2 && (p.res_lo == nullptr || !al16(p.res_lo))) return false;
+    if (nsplit == 1 && p.res_lo != nullptr) return false;
+  }
+  return true;
+}
+
+template <int BLOCK_N, int NSPLIT>
+inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+  if (fast_epilogue_ok(p, NSPLIT)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, true>(p, grid, stream);
+  return launch_conv_gemm_v<BLOCK_N, NSPLIT, false>(p, grid, stream);
 }
 
 inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream) {
