@@ -7,6 +7,8 @@
 // The arithmetic order of the decode mirrors the reference expression by expression with explicit
 // round-to-nearest intrinsics (torch CPU evaluates mul and add as separate fp32 ops, never FMA).
 #pragma once
+#include <cub/device/device_radix_sort.cuh>
+
 #include "nms.cuh"
 
 namespace dana {
@@ -14,7 +16,8 @@ namespace dana {
 // grid over B*HWA anchors.  boxes_all [B][HWA] float4, idx_all [B][HWA] int (0..HWA-1)
 __global__ void proposals_decode_kernel(const float4* __restrict__ deltas, const float4* __restrict__ base_anchors,
                                         const float* __restrict__ im_info, int batch, int feat_w, int num_a,
-                                        int hwa, int feat_stride, float4* __restrict__ boxes_all,
+                                        int hwa, int feat_stride, const float* __restrict__ fg_scores,
+                                        float4* __restrict__ boxes_all, unsigned long long* __restrict__ keys,
                                         int* __restrict__ idx_all) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<long long>(batch) * hwa) return;
@@ -50,52 +53,130 @@ __global__ void proposals_decode_kernel(const float4* __restrict__ deltas, const
   y2 = fminf(fmaxf(y2, 0.0f), ymax);
   boxes_all[gid] = make_float4(x1, y1, x2, y2);
   idx_all[gid] = i;
+  // One global ascending radix sort replaces B per-image sorts: key = (image << 32) | ~orderable(score).
+  // orderable() is the usual monotone float->uint map, so within an image the order is descending score;
+  // the sort is stable, so ties keep ascending anchor index (the documented tie rule).
+  const unsigned int bits = __float_as_uint(fg_scores[gid]);
+  const unsigned int ord = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  keys[gid] = (static_cast<unsigned long long>(b) << 32) | static_cast<unsigned long long>(~ord);
 }
 
-__global__ void proposals_segs_kernel(int* segs, int batch, int hwa) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= batch) segs[i] = i * hwa;
-}
-
-// sorted_boxes [B][n_pre] = boxes_all[b][order[b][r]]
-__global__ void proposals_gather_kernel(const float4* __restrict__ boxes_all, const int* __restrict__ order, int batch,
-                                        int hwa, int n_pre, float4* __restrict__ sorted_boxes) {
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= static_cast<long long>(batch) * n_pre) return;
-  const int b = static_cast<int>(gid / n_pre);
-  const int r = static_cast<int>(gid - static_cast<long long>(b) * n_pre);
-  sorted_boxes[gid] = boxes_all[static_cast<long long>(b) * hwa + order[static_cast<long long>(b) * hwa + r]];
-}
-
-// rois [B][post][5]; one CTA per image
-__global__ void proposals_write_kernel(const float4* __restrict__ sorted_boxes, const float* __restrict__ sorted_scores,
-                                       const int* __restrict__ kept_ranks, const int* __restrict__ kept_count,
-                                       int n_pre, int hwa, int post, float* __restrict__ rois,
-                                       float* __restrict__ roi_scores, int* __restrict__ roi_counts) {
+// Greedy NMS against the kept set, one CTA (256 threads) per image, early exit at max_keep.
+// Sorted candidates are taken 64 at a time: (1) each candidate is tested against every box kept so far
+// (4 threads per candidate, kept boxes in shared memory), (2) the 64x64 IoU bits inside the chunk are built
+// with warp ballots, (3) one thread resolves the chunk serially in registers.  Same fp32 arithmetic and
+// ">=" rule as nms.cuh (bit-exact keep set); work is O(examined x kept) instead of O(n^2).
+// Writes rois [B][post][5] (zero padded), optional scores / counts.
+__global__ void __launch_bounds__(256)
+proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __restrict__ order,
+                           const unsigned long long* __restrict__ keys_sorted, int hwa, int n_pre, int post,
+                           float thresh, float* __restrict__ rois, float* __restrict__ roi_scores,
+                           int* __restrict__ roi_counts) {
+  extern __shared__ float4 s_keep_box[];            // [post]
+  float* s_keep_area = reinterpret_cast<float*>(s_keep_box + post);   // [post]
+  __shared__ float4 s_cand[64];
+  __shared__ float s_cand_area[64];
+  __shared__ unsigned long long s_diag[64];
+  __shared__ unsigned int s_dead[64];
+  __shared__ unsigned long long s_keepbits;
+  __shared__ int s_nkept;
   const int b = blockIdx.x;
-  const int cnt = min(kept_count[b], post);
-  for (int k = threadIdx.x; k < post; k += blockDim.x) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long seg = static_cast<long long>(b) * hwa;
+  if (tid == 0) s_nkept = 0;
+  __syncthreads();
+  for (int base = 0; base < n_pre; base += 64) {
+    const int nkept = s_nkept;
+    const int valid = min(64, n_pre - base);
+    if (tid < 64) {
+      float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid < valid) bx = boxes_all[seg + order[seg + base + tid]];
+      s_cand[tid] = bx;
+      s_cand_area[tid] = box_area_rn(bx);
+      s_dead[tid] = 0;
+    }
+    __syncthreads();
+    // (1) against the kept set: candidate = tid / 4, four threads stride the kept list
+    {
+      const int cj = tid >> 2, part = tid & 3;
+      const float4 cb = s_cand[cj];
+      const float ca = s_cand_area[cj];
+      bool dead = false;
+      for (int k = part; k < nkept && !dead; k += 4) dead = iou_suppresses(s_keep_box[k], s_keep_area[k], cb, ca, thresh);
+      if (dead) s_dead[cj] = 1;   // benign race: all writers store 1
+    }
+    // (2) IoU bits inside the chunk: warp w handles rows 8w..8w+7
+    {
+      const float4 c0 = s_cand[lane], c1 = s_cand[lane + 32];
+      const float a0 = s_cand_area[lane], a1 = s_cand_area[lane + 32];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int ri = warp * 8 + r;
+        const float4 rb = s_cand[ri];
+        const float ra = s_cand_area[ri];
+        const bool p0 = (ri < valid) && (lane < valid) && (lane > ri) && iou_suppresses(rb, ra, c0, a0, thresh);
+        const bool p1 = (ri < valid) && (lane + 32 < valid) && (lane + 32 > ri) && iou_suppresses(rb, ra, c1, a1, thresh);
+        const unsigned lo = __ballot_sync(0xffffffffu, p0);
+        const unsigned hi = __ballot_sync(0xffffffffu, p1);
+        if (lane == 0) s_diag[ri] = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
+      }
+    }
+    __syncthreads();
+    // (3) serial resolution of the chunk
+    if (tid == 0) {
+      unsigned long long removed = 0;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) removed |= static_cast<unsigned long long>(s_dead[j] != 0) << j;
+      unsigned long long keep = 0;
+      int room = post - nkept;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const bool alive = (j < valid) && !((removed >> j) & 1ull) && room > 0;
+        if (alive) {
+          keep |= (1ull << j);
+          removed |= s_diag[j];
+          --room;
+        }
+      }
+      s_keepbits = keep;
+    }
+    __syncthreads();
+    const unsigned long long keep = s_keepbits;
+    if (tid < 64 && ((keep >> tid) & 1ull)) {
+      const int pos = nkept + __popcll(keep & ((1ull << tid) - 1ull));
+      const float4 bx = s_cand[tid];
+      s_keep_box[pos] = bx;
+      s_keep_area[pos] = s_cand_area[tid];
+      float* row = rois + (static_cast<long long>(b) * post + pos) * 5;
+      row[0] = static_cast<float>(b);
+      row[1] = bx.x;
+      row[2] = bx.y;
+      row[3] = bx.z;
+      row[4] = bx.w;
+      if (roi_scores) {
+        // recover the score from the sorted key (low 32 bits hold ~orderable(score))
+        const unsigned int ord = ~static_cast<unsigned int>(keys_sorted[seg + base + tid] & 0xFFFFFFFFull);
+        const unsigned int bits = (ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord;
+        roi_scores[static_cast<long long>(b) * post + pos] = __uint_as_float(bits);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_nkept = nkept + __popcll(keep);
+    __syncthreads();
+    if (s_nkept >= post) break;
+  }
+  const int cnt = s_nkept;
+  for (int k = cnt + tid; k < post; k += 256) {   // zero padding (proposal_layer.py:137,188-190)
     float* row = rois + (static_cast<long long>(b) * post + k) * 5;
     row[0] = static_cast<float>(b);
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sc = 0.f;
-    if (k < cnt) {
-      const int r = kept_ranks[static_cast<long long>(b) * n_pre + k];
-      bx = sorted_boxes[static_cast<long long>(b) * n_pre + r];
-      sc = sorted_scores[static_cast<long long>(b) * hwa + r];
-    }
-    row[1] = bx.x;
-    row[2] = bx.y;
-    row[3] = bx.z;
-    row[4] = bx.w;
-    if (roi_scores) roi_scores[static_cast<long long>(b) * post + k] = sc;
+    row[1] = row[2] = row[3] = row[4] = 0.0f;
+    if (roi_scores) roi_scores[static_cast<long long>(b) * post + k] = 0.0f;
   }
-  if (threadIdx.x == 0 && roi_counts) roi_counts[b] = cnt;
+  if (tid == 0 && roi_counts) roi_counts[b] = cnt;
 }
 
 struct ProposalsWorkspace {
-  int64_t off_boxes_all, off_idx_all, off_keys_out, off_order, off_segs, off_sorted, off_mask, off_kept, off_count,
-      off_cub;
+  int64_t off_boxes_all, off_idx_all, off_keys, off_keys_out, off_order, off_cub;
   int64_t cub_bytes, total;
   int n_pre;
 };
@@ -108,11 +189,16 @@ inline int proposals_n_pre(int batch, int hwa, int pre_nms_top_n) {
   return hwa;
 }
 
+inline int proposals_key_bits(int batch) {
+  int bits = 1;
+  while ((1 << bits) < batch) ++bits;
+  return 32 + bits;
+}
+
 inline ProposalsWorkspace proposals_workspace_layout(int batch, int hwa, int pre_nms_top_n) {
   ProposalsWorkspace w;
   w.n_pre = proposals_n_pre(batch, hwa, pre_nms_top_n);
   const int64_t tot = static_cast<int64_t>(batch) * hwa;
-  const int64_t nw = (w.n_pre + 63) / 64;
   int64_t o = 0;
   auto take = [&](int64_t bytes) {
     const int64_t r = o;
@@ -121,18 +207,13 @@ inline ProposalsWorkspace proposals_workspace_layout(int batch, int hwa, int pre
   };
   w.off_boxes_all = take(16 * tot);
   w.off_idx_all = take(4 * tot);
-  w.off_keys_out = take(4 * tot);
+  w.off_keys = take(8 * tot);
+  w.off_keys_out = take(8 * tot);
   w.off_order = take(4 * tot);
-  w.off_segs = take(4LL * (batch + 1));
-  w.off_sorted = take(16LL * batch * w.n_pre);
-  w.off_mask = take(8LL * batch * nw * w.n_pre);
-  w.off_kept = take(4LL * batch * w.n_pre);
-  w.off_count = take(4LL * batch);
   size_t cub_bytes = 0;
-  cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, cub_bytes, static_cast<const float*>(nullptr),
-                                                     static_cast<float*>(nullptr), static_cast<const int*>(nullptr),
-                                                     static_cast<int*>(nullptr), static_cast<int>(tot), batch,
-                                                     static_cast<const int*>(nullptr), static_cast<const int*>(nullptr));
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<const unsigned long long*>(nullptr),
+                                  static_cast<unsigned long long*>(nullptr), static_cast<const int*>(nullptr),
+                                  static_cast<int*>(nullptr), static_cast<int>(tot), 0, proposals_key_bits(batch));
   w.cub_bytes = static_cast<int64_t>(cub_bytes);
   w.off_cub = take(w.cub_bytes + 256);
   w.total = o;
@@ -150,41 +231,31 @@ inline int proposals_run(const float* fg_scores, const float* deltas, const floa
   const int hwa = feat_h * feat_w * num_a;
   const ProposalsWorkspace w = proposals_workspace_layout(batch, hwa, pre_nms_top_n);
   if (workspace_bytes < w.total) return DANA_EINVAL;
-  if (4LL * w.n_pre > 200 * 1024) return DANA_ENOTSUP;
+  const size_t keep_smem = static_cast<size_t>(post_nms_top_n) * 20;
+  if (keep_smem > 200 * 1024) return DANA_ENOTSUP;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float4* boxes_all = reinterpret_cast<float4*>(ws + w.off_boxes_all);
   int* idx_all = reinterpret_cast<int*>(ws + w.off_idx_all);
-  float* keys_out = reinterpret_cast<float*>(ws + w.off_keys_out);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + w.off_keys);
+  unsigned long long* keys_out = reinterpret_cast<unsigned long long*>(ws + w.off_keys_out);
   int* order = reinterpret_cast<int*>(ws + w.off_order);
-  int* segs = reinterpret_cast<int*>(ws + w.off_segs);
-  float4* sorted = reinterpret_cast<float4*>(ws + w.off_sorted);
-  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + w.off_mask);
-  int* kept = reinterpret_cast<int*>(ws + w.off_kept);
-  int* kcount = reinterpret_cast<int*>(ws + w.off_count);
   const long long tot = static_cast<long long>(batch) * hwa;
   const int tb = 256;
   proposals_decode_kernel<<<static_cast<int>((tot + tb - 1) / tb), tb, 0, stream>>>(
       reinterpret_cast<const float4*>(deltas), reinterpret_cast<const float4*>(base_anchors), im_info, batch, feat_w,
-      num_a, hwa, feat_stride, boxes_all, idx_all);
-  proposals_segs_kernel<<<1, 256, 0, stream>>>(segs, batch, hwa);
+      num_a, hwa, feat_stride, fg_scores, boxes_all, keys, idx_all);
   size_t cub_bytes = static_cast<size_t>(w.cub_bytes);
-  DANA_CUDA_CHECK(cub::DeviceSegmentedRadixSort::SortPairsDescending(ws + w.off_cub, cub_bytes, fg_scores, keys_out,
-                                                                     idx_all, order, static_cast<int>(tot), batch, segs,
-                                                                     segs + 1, 0, 32, stream));
-  const long long tg = static_cast<long long>(batch) * w.n_pre;
-  proposals_gather_kernel<<<static_cast<int>((tg + tb - 1) / tb), tb, 0, stream>>>(boxes_all, order, batch, hwa,
-                                                                                     w.n_pre, sorted);
-  const int nblk = (w.n_pre + 63) / 64;
-  const long long mstride = static_cast<long long>(nblk) * w.n_pre;
-  nms_mask_kernel<<<dim3(nblk, nblk, batch), 256, 0, stream>>>(sorted, nullptr, w.n_pre, nms_thresh, mask, mstride);
-  static bool configured = false;
-  if (!configured) {
-    DANA_CUDA_CHECK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+  DANA_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys, keys_out, idx_all, order,
+                                                  static_cast<int>(tot), 0, proposals_key_bits(batch), stream));
+  static size_t configured = 0;
+  if (keep_smem > 40 * 1024 && keep_smem > configured) {
+    DANA_CUDA_CHECK(cudaFuncSetAttribute(proposals_nms_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(keep_smem)));
+    configured = keep_smem;
   }
-  nms_scan_kernel<<<batch, 256, 4 * w.n_pre, stream>>>(mask, mstride, nullptr, w.n_pre, post_nms_top_n, kept, kcount);
-  proposals_write_kernel<<<batch, 256, 0, stream>>>(sorted, keys_out, kept, kcount, w.n_pre, hwa, post_nms_top_n, rois,
-                                                    roi_scores, roi_counts);
+  proposals_nms_write_kernel<<<batch, 256, keep_smem, stream>>>(boxes_all, order, keys_out, hwa, w.n_pre,
+                                                                post_nms_top_n, nms_thresh, rois, roi_scores,
+                                                                roi_counts);
   DANA_LAUNCH_CHECK();
   return DANA_OK;
 }

@@ -1,0 +1,58 @@
+"""RoIAlign microbenchmark at the BASELINE.json shape (map [B,1024,38,63], 300 RoIs per image): the
+reference-layout operator (NCHW fp32 -> [R,C,7,7] fp32, dana_roi_align_forward layout 0) and the
+pipeline variant (NHWC -> bf16 pair).  Algorithmic bytes: 4*R*C*49 + 4*C*h*w*B + 20*R.
+  ncu --set full --clock-control none --import-source on -k regex:roi_align_fwd -c 2 -o gpurun_out/roi python tools/roi_bench.py --iters 1
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import dana_b200  # noqa: E402,F401
+from dana_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--batch", type=int, default=4)
+a = ap.parse_args()
+b, c, h, w = a.batch, 1024, 38, 63
+rs = np.random.RandomState(0)
+feat = torch.randn(b, c, h, w, device="cuda")
+r = 300 * b
+# proposal-like boxes: mixture of scales, clipped to the image
+cx, cy = rs.uniform(0, 1000, r), rs.uniform(0, 600, r)
+bw, bh = np.exp(rs.uniform(np.log(16), np.log(600), r)), np.exp(rs.uniform(np.log(16), np.log(500), r))
+rois = np.stack([np.repeat(np.arange(b), 300), np.clip(cx - bw / 2, 0, 999), np.clip(cy - bh / 2, 0, 599),
+                 np.clip(cx + bw / 2, 0, 999), np.clip(cy + bh / 2, 0, 599)], 1).astype(np.float32)
+rois = torch.from_numpy(rois).cuda()
+nhwc = feat.permute(0, 2, 3, 1).contiguous()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+alg_bytes = 4.0 * r * c * 49 + 4.0 * c * h * w * b + 20.0 * r
+
+
+def timeit(fn):
+    for _ in range(2):
+        fn()
+    tot = 0.0
+    for _ in range(a.iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / a.iters
+
+
+ms = timeit(lambda: ops.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0))
+print("roi_align NCHW fp32 (reference layout, incl. NCHW->NHWC staging): %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
+      (ms, alg_bytes / ms / 1e6, alg_bytes / 1e6))
+ms = timeit(lambda: ops.roi_align_nhwc(nhwc, rois, 1.0 / 16, 7, 0, want_f32=False, want_pair=True))
+pb = 2 * 2.0 * r * c * 49 + 4.0 * c * h * w * b
+print("roi_align NHWC -> bf16 hi/lo pair (pipeline):                      %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
+      (ms, pb / ms / 1e6, pb / 1e6))
