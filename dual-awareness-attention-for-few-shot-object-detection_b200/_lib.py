@@ -55,6 +55,8 @@ SIGNATURES = {
     "dana_roi_align_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "dana_roi_align_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dana_roi_align_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_roi_align_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_int, c_void_p, c_void_p]),
     "dana_conv_gemm": (c_int, [POINTER(ConvGemmArgs), c_void_p]),

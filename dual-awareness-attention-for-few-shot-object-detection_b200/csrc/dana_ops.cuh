@@ -148,21 +148,35 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ hi, const 
 // ---------------------------------------------------------------------------------------------
 // AvgPool2d(k, stride 1) on NHWC bf16 pairs -> fp32 NHWC (dana.py:42,114: 20x20 -> 7x7, k = 14)
 // ---------------------------------------------------------------------------------------------
-__global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                    int maps, int h, int w, int c, int k, float* __restrict__ out) {
+// grid (maps, c/32), block (32, 8): the map's 32-channel slab is staged in shared memory once, then pooled
+// separably (row sums over k columns, then k row-sum rows) -- h*w*(1 + ...) loads instead of oh*ow*k*k.
+__global__ void __launch_bounds__(256)
+avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int maps, int h, int w,
+                    int c, int k, float* __restrict__ out) {
+  extern __shared__ float s_pool[];
   const int oh = h - k + 1, ow = w - k + 1;
-  const long long total = static_cast<long long>(maps) * oh * ow * c;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(i % c);
-    const int ox = static_cast<int>((i / c) % ow);
-    const int oy = static_cast<int>((i / c / ow) % oh);
-    const int m = static_cast<int>(i / c / ow / oh);
+  float* s_in = s_pool;                 // [h*w][32]
+  float* s_rs = s_pool + h * w * 32;    // [h][ow][32]
+  const int m = blockIdx.x;
+  const int ch = blockIdx.y * 32 + threadIdx.x;
+  const bool ok = ch < c;
+  const long long base = static_cast<long long>(m) * h * w * c + ch;
+  for (int p = threadIdx.y; p < h * w; p += blockDim.y)
+    s_in[p * 32 + threadIdx.x] = ok ? ld_pair(hi, lo, base + static_cast<long long>(p) * c) : 0.0f;
+  __syncthreads();
+  for (int i = threadIdx.y; i < h * ow; i += blockDim.y) {
+    const int y = i / ow, ox = i - y * ow;
     float s = 0.0f;
-    for (int dy = 0; dy < k; ++dy)
-      for (int dx = 0; dx < k; ++dx)
-        s += ld_pair(hi, lo, ((static_cast<long long>(m) * h + oy + dy) * w + ox + dx) * c + ch);
-    out[i] = s / static_cast<float>(k * k);
+    for (int dx = 0; dx < k; ++dx) s += s_in[(y * w + ox + dx) * 32 + threadIdx.x];
+    s_rs[i * 32 + threadIdx.x] = s;
+  }
+  __syncthreads();
+  const float inv = 1.0f / static_cast<float>(k * k);
+  for (int i = threadIdx.y; i < oh * ow; i += blockDim.y) {
+    const int oy = i / ow, ox = i - oy * ow;
+    float s = 0.0f;
+    for (int dy = 0; dy < k; ++dy) s += s_rs[((oy + dy) * ow + ox) * 32 + threadIdx.x];
+    if (ok) out[(static_cast<long long>(m) * oh * ow + i) * c + ch] = s * inv;
   }
 }
 

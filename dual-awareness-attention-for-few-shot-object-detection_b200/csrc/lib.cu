@@ -74,6 +74,13 @@ int dana_roi_align_forward(const float* input, const float* rois, int num_rois, 
                                static_cast<cudaStream_t>(stream));
 }
 
+int dana_roi_align_head(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels, int height,
+                        int width, float spatial_scale, int sampling_ratio, float* out, void* out_hi, void* out_lo,
+                        const float* pe, void* qpe_hi, void* qpe_lo, void* stream) {
+  return roi_align_head_run(feat_nhwc, rois, num_rois, batch, channels, height, width, spatial_scale, sampling_ratio,
+                            out, out_hi, out_lo, pe, qpe_hi, qpe_lo, static_cast<cudaStream_t>(stream));
+}
+
 int dana_roi_align_backward(const float* grad_out, const float* rois, int num_rois, int batch, int channels,
                             int height, int width, int pooled_h, int pooled_w, float spatial_scale,
                             int sampling_ratio, float* grad_input, void* stream) {

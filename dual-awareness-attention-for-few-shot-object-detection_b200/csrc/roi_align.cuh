@@ -205,6 +205,142 @@ roi_align_fwd_kernel(const float* __restrict__ feat /*NHWC*/, const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipeline RoIAlign (NHWC fp32 map -> [R][7][7][C]): same separable math as above, tuned for issue rate.
+//   * compact weight tables: per bin only the <= 16 taps that are non-zero, plus their first index
+//   * 8 channels per thread (two 16-byte loads per tap), pointers advanced by increments
+//   * optional fused outputs: fp32, bf16 hi/lo pair, and pair of (value + positional encoding[bin])
+//     (the query side of the head attention, dana.py:259) -- removes a 470 MB round trip per step.
+// grid (num_rois, C / (8 * blockDim.x)), block = min(128, C / 8) threads (>= 64).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRoiTaps = 16;
+
+__device__ __forceinline__ void build_axis_compact(float* w /*[kRoiTaps]*/, int* lo_out, int* n_out, int p, int size,
+                                                   float start, float bin, int grid) {
+#pragma unroll
+  for (int i = 0; i < kRoiTaps; ++i) w[i] = 0.0f;
+  int lo = -1, hi = -1;
+  for (int i = 0; i < grid; ++i) {
+    const float v = sample_coord(start, bin, p, i, grid);
+    int l, h;
+    float wl, wh;
+    if (!axis_taps(v, size, l, h, wl, wh)) continue;
+    if (lo < 0) lo = l;          // sample coordinates are non-decreasing in i: the first valid tap is the lowest
+    if (l - lo < kRoiTaps) w[l - lo] += wl;
+    if (h - lo < kRoiTaps) w[h - lo] += wh;
+    hi = h;
+  }
+  *lo_out = lo < 0 ? 0 : lo;
+  *n_out = lo < 0 ? 0 : min(hi - lo + 1, kRoiTaps);
+}
+
+__device__ __forceinline__ void store8_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, const float (&f)[8]) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * e] - __uint_as_float(ph[e] << 16),
+                                                    f[2 * e + 1] - __uint_as_float(ph[e] & 0xFFFF0000u));
+    pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  if (lo != nullptr) *reinterpret_cast<uint4*>(lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+__global__ void __launch_bounds__(128)
+roi_align_head_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restrict__ rois, int channels, int height,
+                      int width, float spatial_scale, int sampling_ratio, float* __restrict__ out,
+                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                      const float* __restrict__ pe, __nv_bfloat16* __restrict__ qpe_hi,
+                      __nv_bfloat16* __restrict__ qpe_lo) {
+  __shared__ float s_wy[7][kRoiTaps], s_wx[7][kRoiTaps];
+  __shared__ int s_ylo[7], s_ny[7], s_xlo[7], s_nx[7];
+  __shared__ RoiGeom s_g;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) s_g = roi_geometry(rois + static_cast<long long>(r) * 5, spatial_scale, 7, 7, sampling_ratio);
+  __syncthreads();
+  const RoiGeom g = s_g;
+  if (tid < 7) build_axis_compact(s_wy[tid], &s_ylo[tid], &s_ny[tid], tid, height, g.start_h, g.bin_h, g.grid_h);
+  if (tid >= 32 && tid < 39)
+    build_axis_compact(s_wx[tid - 32], &s_xlo[tid - 32], &s_nx[tid - 32], tid - 32, width, g.start_w, g.bin_w, g.grid_w);
+  __syncthreads();
+  const int c0 = (blockIdx.y * blockDim.x + tid) * 8;
+  if (c0 >= channels) return;
+  const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
+  const float* fbase = feat + static_cast<long long>(g.batch_ind) * height * width * channels + c0;
+  const long long row_pitch = static_cast<long long>(width) * channels;
+  for (int ph = 0; ph < 7; ++ph) {
+    float acc[7][8];
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw)
+#pragma unroll
+      for (int v = 0; v < 8; ++v) acc[pw][v] = 0.0f;
+    const int ny = s_ny[ph];
+    const float* rowp = fbase + static_cast<long long>(s_ylo[ph]) * row_pitch;
+    for (int ky = 0; ky < ny; ++ky, rowp += row_pitch) {
+      const float wy = s_wy[ph][ky];
+      if (wy == 0.0f) continue;
+#pragma unroll
+      for (int pw = 0; pw < 7; ++pw) {
+        const int nx = s_nx[pw];
+        const float* px = rowp + static_cast<long long>(s_xlo[pw]) * channels;
+        float rs[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) rs[v] = 0.0f;
+        for (int kx = 0; kx < nx; ++kx, px += channels) {
+          const float wx = s_wx[pw][kx];
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(px));
+          const float4 f1 = __ldg(reinterpret_cast<const float4*>(px) + 1);
+          rs[0] += wx * f0.x; rs[1] += wx * f0.y; rs[2] += wx * f0.z; rs[3] += wx * f0.w;
+          rs[4] += wx * f1.x; rs[5] += wx * f1.y; rs[6] += wx * f1.z; rs[7] += wx * f1.w;
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[pw][v] += wy * rs[v];
+      }
+    }
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw) {
+      float o[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) o[v] = acc[pw][v] * inv_count;
+      const int bin = ph * 7 + pw;
+      const long long off = (static_cast<long long>(r) * 49 + bin) * channels + c0;
+      if (out != nullptr) {
+        reinterpret_cast<float4*>(out + off)[0] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(out + off)[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (out_hi != nullptr) store8_pair(out_hi, out_lo, off, o);
+      if (qpe_hi != nullptr) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(bin) * channels + c0));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(bin) * channels + c0) + 1);
+        float qv[8] = {o[0] + p0.x, o[1] + p0.y, o[2] + p0.z, o[3] + p0.w, o[4] + p1.x, o[5] + p1.y, o[6] + p1.z, o[7] + p1.w};
+        store8_pair(qpe_hi, qpe_lo, off, qv);
+      }
+    }
+  }
+}
+
+inline int roi_align_head_run(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels,
+                              int height, int width, float spatial_scale, int sampling_ratio, float* out, void* out_hi,
+                              void* out_lo, const float* pe, void* qpe_hi, void* qpe_lo, cudaStream_t stream) {
+  if (num_rois == 0) return DANA_OK;
+  if (!feat_nhwc || !rois || num_rois < 0 || batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return DANA_EINVAL;
+  if (!out && !out_hi && !qpe_hi) return DANA_EINVAL;
+  if (qpe_hi && !pe) return DANA_EINVAL;
+  if (channels % 8 != 0) return DANA_ENOTSUP;
+  // compact tables hold 16 taps per bin: bins of at most 14 feature pixels
+  if (sampling_ratio <= 0 && (height > 7 * 14 || width > 7 * 14)) return DANA_ENOTSUP;
+  int threads = channels / 8 >= 128 ? 128 : ((channels / 8 + 31) / 32) * 32;
+  if (threads < 64) threads = 64;
+  const int groups = (channels / 8 + threads - 1) / threads;
+  roi_align_head_kernel<<<dim3(num_rois, groups), threads, 0, stream>>>(
+      feat_nhwc, rois, channels, height, width, spatial_scale, sampling_ratio, out, static_cast<__nv_bfloat16*>(out_hi),
+      static_cast<__nv_bfloat16*>(out_lo), pe, static_cast<__nv_bfloat16*>(qpe_hi), static_cast<__nv_bfloat16*>(qpe_lo));
+  DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
 // NCHW -> NHWC transpose of one feature map batch: [B][C][HW] -> [B][HW][C], 32x32 tiles
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int channels, int hw) {
   __shared__ float tile[32][33];

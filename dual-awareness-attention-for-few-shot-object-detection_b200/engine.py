@@ -277,12 +277,21 @@ class DanaEngine:
         # ---- RoIAlign on the query feature (dana.py:183)
         base_f32 = ops.merge_pair(Pair(corr.hi[..., :1024], None if corr.lo is None else corr.lo[..., :1024]))
         r = b * post_nms_top_n
-        pooled_f32, pooled = ops.roi_align_nhwc(base_f32, rois.view(-1, 5), 1.0 / 16.0, pooling_size, 0, split=split)
-        if "pooled" in want:
+        bins = pooling_size * pooling_size
+        need_f32 = "pooled" in want
+        if pooling_size == 7:   # fused: pooled pair (layer4 input) + positional-encoded query pair (dana.py:259)
+            pooled_f32, pooled, qpe4 = ops.roi_align_head(base_f32, rois.view(-1, 5), 1.0 / 16.0, 0, pe=self.pe(bins),
+                                                          want_f32=need_f32, want_pair=True, want_qpe=True, split=split)
+            qpe = qpe4.view(r * bins, 1024)
+        else:
+            pooled_f32, pooled = ops.roi_align_nhwc(base_f32, rois.view(-1, 5), 1.0 / 16.0, pooling_size, 0, split=split)
+            qpe = None
+        if need_f32:
             extra["pooled"] = pooled_f32.permute(0, 3, 1, 2)
         if teacher and "pooled" in teacher:
             pooled_f32 = teacher["pooled"].permute(0, 2, 3, 1).contiguous()
             pooled = ops.split_f32(pooled_f32, split)
+            qpe = None
 
         # ---- head: box regression (dana.py:246,387-389)
         top = self.layer4(pooled)
@@ -293,7 +302,6 @@ class DanaEngine:
             extra["fc7"] = fc7_f32
 
         # ---- head: per-RoI CISA (dana.py:247-290); support projections hoisted out of the RoI loop
-        bins = pooling_size * pooling_size
         sp_k = sh - pooling_size + 1
         s_pooled = ops.avgpool(sup, sp_k)                                 # dana.py:114  [maps,7,7,C] fp32
         if "support_pooled" in want:
@@ -303,8 +311,9 @@ class DanaEngine:
                                                  un_b=self.rcnn_un_b, unary_gamma=self.unary_gamma, vt_pitch=pitch_h,
                                                  split=split)
         kc_h = ops.linear(vc_h, self.rcnn_k_w, 256, split=split)
-        qpe = Pair.empty((r * bins, c), dev, split)
-        ops.add_pe_split(pooled_f32, self.pe(bins), bins, qpe, c)         # :259
+        if qpe is None:
+            qpe = Pair.empty((r * bins, c), dev, split)
+            ops.add_pe_split(pooled_f32, self.pe(bins), bins, qpe, c)     # :259
         q_h = torch.empty((r * bins, 256), dtype=torch.float32, device=dev)
         ops.linear(qpe, self.rcnn_q_w, 256, out_f32=q_h)                  # :266
         qc_h = ops.center_rows(q_h, r, bins, split=split)                 # :267

@@ -270,6 +270,27 @@ def roi_align_nhwc(feat_nhwc, rois, spatial_scale, pooled, sampling_ratio, *, wa
     return out, pair
 
 
+def roi_align_head(feat_nhwc, rois, spatial_scale, sampling_ratio, *, pe=None, want_f32=False, want_pair=True,
+                   want_qpe=False, split=True):
+    """Head RoIAlign (7x7): NHWC fp32 map [B,H,W,C] -> [R,7,7,C] as fp32 / bf16 pair / pair of value + pe[bin]
+    (dana.py:183 and the positional-encoded query of :259 in one pass).  Returns (f32, pair, qpe_pair)."""
+    _need_cuda(feat_nhwc, rois)
+    b, h, w, c = feat_nhwc.shape
+    r = rois.shape[0]
+    dev = feat_nhwc.device
+    out = torch.empty((r, 7, 7, c), dtype=torch.float32, device=dev) if want_f32 else None
+    pair = Pair.empty((r, 7, 7, c), dev, split=split) if want_pair else None
+    qpe = Pair.empty((r, 7, 7, c), dev, split=split) if want_qpe else None
+    _count(1)
+    check(_lib.load().dana_roi_align_head(_p(feat_nhwc), _p(rois), r, b, c, h, w, float(spatial_scale),
+                                          int(sampling_ratio), _p(out), _p(pair.hi) if pair else None,
+                                          _p(pair.lo) if (pair and pair.lo is not None) else None, _p(pe),
+                                          _p(qpe.hi) if qpe else None,
+                                          _p(qpe.lo) if (qpe and qpe.lo is not None) else None, _stream()),
+          "dana_roi_align_head")
+    return out, pair, qpe
+
+
 def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch, channels, height, width,
                        sampling_ratio):
     """model._C.roi_align_backward (csrc/ROIAlign.h:29-45)."""

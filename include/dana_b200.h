@@ -79,6 +79,12 @@ int dana_roi_align_forward(const float* input, const float* rois, int num_rois, 
                            int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int layout,
                            float* out, void* out_hi, void* out_lo, void* workspace, int64_t workspace_bytes,
                            void* stream);
+/* Head variant of the forward (7x7 bins): NHWC fp32 map -> [R,7,7,C] written as any of fp32 (out), bf16 pair
+ * (out_hi/out_lo) and bf16 pair of value + pe[bin][c] (qpe_*; the positional-encoded query of rcnn_head,
+ * lib/model/framework/dana.py:259).  pe is fp32 [49, C]. */
+int dana_roi_align_head(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels, int height,
+                        int width, float spatial_scale, int sampling_ratio, float* out, void* out_hi, void* out_lo,
+                        const float* pe, void* qpe_hi, void* qpe_lo, void* stream);
 /* grad_input [B,C,H,W] fp32 is ZEROED by the call and then accumulated (NCHW only). */
 int dana_roi_align_backward(const float* grad_out, const float* rois, int num_rois, int batch, int channels,
                             int height, int width, int pooled_h, int pooled_w, float spatial_scale,

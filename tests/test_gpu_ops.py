@@ -217,3 +217,26 @@ def test_stem_vs_oracle(ops):
         got = ops.stem(im.cuda(), ops.pack_stem_weight(p["RCNN_base.0.weight"].cuda()), sc.contiguous(), (bb - m * sc).contiguous())
         assert tuple(got.hi.shape) == tuple(want.shape)
         assert relerr(got.float(), want) <= 2e-5
+
+
+def test_roi_align_head_fused_outputs(ops):
+    """dana_roi_align_head: pooled fp32 / bf16 pair / pair of pooled + positional encoding, vs the oracle."""
+    rs = np.random.RandomState(77)
+    feat = rs.standard_normal((2, 64, 38, 63)).astype(np.float32)
+    r = 200
+    x1, y1 = rs.uniform(-30, 980, r), rs.uniform(-30, 590, r)
+    rois = np.stack([rs.randint(0, 2, r).astype(np.float64), x1, y1, x1 + rs.uniform(0.3, 700, r),
+                     y1 + rs.uniform(0.3, 500, r)], 1).astype(np.float32)
+    rois[0, 1:] = [0, 0, 999, 599]
+    rois[1, 1:] = [500, 300, 400, 200]
+    rois[2, 1:] = [1500, 900, 1600, 950]
+    rois[3, 1:] = [10.2, 10.7, 10.9, 11.1]
+    want = O.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0)                       # [R,C,7,7]
+    pe = O.positional_encoding(49, 64)
+    nhwc = torch.from_numpy(feat).cuda().permute(0, 2, 3, 1).contiguous()
+    f32, pair, qpe = ops.roi_align_head(nhwc, torch.from_numpy(rois).cuda(), 1.0 / 16, 0, pe=pe.cuda().contiguous(),
+                                        want_f32=True, want_pair=True, want_qpe=True)
+    assert relerr(f32.permute(0, 3, 1, 2), want) <= 1e-5
+    assert relerr(pair.float().permute(0, 3, 1, 2), want) <= 2e-5
+    want_q = want.reshape(r, 64, 49).transpose(1, 2) + pe.unsqueeze(0)             # [R,49,C]
+    assert relerr(qpe.float().reshape(r, 49, 64), want_q) <= 2e-5

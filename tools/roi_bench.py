@@ -56,3 +56,11 @@ ms = timeit(lambda: ops.roi_align_nhwc(nhwc, rois, 1.0 / 16, 7, 0, want_f32=Fals
 pb = 2 * 2.0 * r * c * 49 + 4.0 * c * h * w * b
 print("roi_align NHWC -> bf16 hi/lo pair (pipeline):                      %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
       (ms, pb / ms / 1e6, pb / 1e6))
+pe = torch.randn(49, c, device="cuda")
+ms = timeit(lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, pe=pe, want_f32=False, want_pair=True, want_qpe=True))
+pb2 = 4 * 2.0 * r * c * 49 + 4.0 * c * h * w * b
+print("roi_align_head NHWC -> pooled pair + (pooled+PE) pair:              %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
+      (ms, pb2 / ms / 1e6, pb2 / 1e6))
+ms = timeit(lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, want_f32=True, want_pair=False, want_qpe=False))
+print("roi_align_head NHWC -> fp32 [R,7,7,C]:                              %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
+      (ms, alg_bytes / ms / 1e6, alg_bytes / 1e6))
