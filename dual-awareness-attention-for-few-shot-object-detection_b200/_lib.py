@@ -38,6 +38,7 @@ class ConvGemmArgs(Structure):
         ("res_hi", c_void_p), ("res_lo", c_void_p), ("res_f32", c_void_p),
         ("r_sx", c_int64), ("r_sy", c_int64), ("r_sn", c_int64),
         ("alpha", c_float), ("relu", c_int32),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64), ("sk_epoch", c_int32),
     ]
 
 
@@ -59,6 +60,7 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_roi_align_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_int, c_void_p, c_void_p]),
+    "dana_conv_gemm_workspace_bytes": (c_int64, []),
     "dana_conv_gemm": (c_int, [POINTER(ConvGemmArgs), c_void_p]),
     "dana_stem_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dana_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

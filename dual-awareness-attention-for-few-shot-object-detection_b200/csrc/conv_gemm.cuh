@@ -42,6 +42,10 @@ struct ConvGemmParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   float* out_f32;
+  // stream-K (see the kernel comment): per-CTA fp32 partial-accumulator slots and ready flags
+  float* sk_partials;   // [grid][128 * BLOCK_N]
+  int* sk_flags;        // [grid]
+  int sk_epoch;         // value a flag takes when this launch's partial is published; 0 = stream-K off
 };
 
 constexpr int kGemmThreads = 320;
@@ -63,7 +67,36 @@ struct ConvGemmCfg {
 
 // FAST epilogue: host-verified n_out % 32 == 0, bf16 pair output (no fp32 output / residual), every
 // pointer 16-byte aligned and every stride a multiple of 8 elements -> no per-element predicates.
-template <int BLOCK_N, int NSPLIT, bool FAST>
+// Work distribution.  Classic persistent scheduling hands out whole 128 x BLOCK_N tiles; with 150 tiles on 148
+// SMs that is two rounds at 51 % utilisation, with 75 tiles half the SMs idle.  With stream-K (sk_epoch != 0) the
+// linearised (tile, k-block) iteration space is cut into gridDim.x equal contiguous ranges instead.  A CTA whose
+// range ends inside a tile dumps its raw fp32 accumulators into its workspace slot and raises its flag; the CTA
+// that owns the tile's last k-block adds the slots of the (lower-numbered) CTAs that covered the tile's head and
+// runs the normal epilogue.  Every CTA publishes at most one partial, waits only on lower-numbered CTAs, and
+// all CTAs are co-resident (grid <= SM count), so the wait cannot deadlock.
+struct SkRange {
+  long long it, it_end;
+  int num_kb;
+  // Next segment of this CTA (tile index, k-block range [kb0, kb1)), walking the range BACKWARDS: the tail
+  // segment (a tile this CTA only starts) is computed and published first, the head segment (a tile whose
+  // beginning a lower CTA computes) is finished last, so by the time a partial is needed it has long been
+  // written -- in the forward order every CTA would wait for its predecessor's whole range (a serial chain).
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (it >= it_end) return false;
+    tile = static_cast<int>((it_end - 1) / num_kb);
+    const long long tile_start = static_cast<long long>(tile) * num_kb;
+    kb1 = static_cast<int>(it_end - tile_start);
+    kb0 = (tile_start >= it) ? 0 : static_cast<int>(it - tile_start);
+    it_end = tile_start + kb0;
+    return true;
+  }
+};
+
+// CM: thread-block cluster size along M.  The CM CTAs of a cluster work on CM consecutive M-tiles of the same
+// N-tile; each loads 1/CM of the weight (B) tile and TMA-multicasts it to all of them, which divides the L2->SM
+// weight traffic by CM (the compute-bound layers are L2-bandwidth bound at 128x256 tiles).  A smem slot is
+// released cluster-wide: every CTA's MMA commit arrives on the `empty` barrier of all CM CTAs.
+template <int BLOCK_N, int NSPLIT, bool FAST, int CM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT>;
@@ -91,7 +124,28 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
   const int num_kb = p.taps_r * p.taps_s * p.c_blocks;
   const int sp_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int num_tiles = sp_tiles * p.tiles_co;
+  // work item w -> (N-tile, group of CM consecutive M-tiles); this CTA takes M-tile group*CM + rank, which may
+  // lie past the end (phantom tile: TMA zero-fills, the epilogue masks every row) so that all CTAs of a cluster
+  // run the same pipeline schedule
+  const int cm_rank = (CM > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CM;
+  const int num_clusters = gridDim.x / CM;
+  const int num_work = ((sp_tiles + CM - 1) / CM) * p.tiles_co;
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CM) - 1u);
+  const bool stream_k = (CM == 1) && (p.sk_epoch != 0);
+  const long long total_it = static_cast<long long>(num_work) * num_kb;
+  auto my_range = [&]() {
+    SkRange r;
+    r.num_kb = num_kb;
+    if (stream_k) {
+      r.it = total_it * blockIdx.x / gridDim.x;
+      r.it_end = total_it * (blockIdx.x + 1) / gridDim.x;
+    } else {
+      r.it = 0;
+      r.it_end = 0;
+    }
+    return r;
+  };
 
   if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) {
     atomicExch(&g_device_error, 105);
@@ -106,7 +160,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CM);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -120,6 +174,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -128,14 +183,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int co_t = t % p.tiles_co;
-        const int sp = t / p.tiles_co;
+      SkRange rng = my_range();
+      int wk = cluster_id - num_clusters, kb_lo = 0, kb_hi = num_kb;
+      while (stream_k ? rng.next(wk, kb_lo, kb_hi) : ((wk += num_clusters) < num_work)) {
+        const int co_t = wk % p.tiles_co;
+        const int sp = (wk / p.tiles_co) * CM + cm_rank;
         const int x0 = (sp % p.tiles_x) * p.bw;
         const int y0 = ((sp / p.tiles_x) % p.tiles_y) * p.bh;
         const int n0 = (sp / (p.tiles_x * p.tiles_y)) * p.bn;
         const int bcoord = p.b_batched ? n0 : 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           const int tap = kb / p.c_blocks;
           const int cb = kb - tap * p.c_blocks;
           const int r = tap / p.taps_s;
@@ -146,11 +203,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const int ka = cb * kTileK;
           const int kbk = tap * p.c_in + cb * kTileK;
           tma_load_4d(st, &p.tm_a_hi, &full_bar[stage], ka, x0 + s - p.pad_x, y0 + r - p.pad_y, n0);
-          tma_load_3d(st + NSPLIT * kATileBytes, &p.tm_b_hi, &full_bar[stage], kbk, co_t * BLOCK_N, bcoord);
+          if (CM == 1) {
+            tma_load_3d(st + NSPLIT * kATileBytes, &p.tm_b_hi, &full_bar[stage], kbk, co_t * BLOCK_N, bcoord);
+          } else {
+            tma_load_3d_mc(st + NSPLIT * kATileBytes + cm_rank * (Cfg::kBTileBytes / CM), &p.tm_b_hi, &full_bar[stage],
+                           kbk, co_t * BLOCK_N + cm_rank * (BLOCK_N / CM), 0, kMcMask);
+          }
           if (NSPLIT == 2) {
             tma_load_4d(st + kATileBytes, &p.tm_a_lo, &full_bar[stage], ka, x0 + s - p.pad_x, y0 + r - p.pad_y, n0);
-            tma_load_3d(st + 2 * kATileBytes + Cfg::kBTileBytes, &p.tm_b_lo, &full_bar[stage], kbk, co_t * BLOCK_N,
-                        bcoord);
+            if (CM == 1) {
+              tma_load_3d(st + 2 * kATileBytes + Cfg::kBTileBytes, &p.tm_b_lo, &full_bar[stage], kbk, co_t * BLOCK_N,
+                          bcoord);
+            } else {
+              tma_load_3d_mc(st + 2 * kATileBytes + Cfg::kBTileBytes + cm_rank * (Cfg::kBTileBytes / CM), &p.tm_b_lo,
+                             &full_bar[stage], kbk, co_t * BLOCK_N + cm_rank * (BLOCK_N / CM), 0, kMcMask);
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -167,11 +234,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      SkRange rng = my_range();
+      int wk = cluster_id - num_clusters, kb_lo = 0, kb_hi = num_kb;
+      while (stream_k ? rng.next(wk, kb_lo, kb_hi) : ((wk += num_clusters) < num_work)) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1, 102);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase, 103);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(tiles + stage * Cfg::kStageBytes);
@@ -185,14 +254,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               const uint64_t dal = umma_desc_sw128(a_hi + kATileBytes + koff);
               const uint64_t dbl = umma_desc_sw128(b_hi + Cfg::kBTileBytes + koff);
               // small cross terms first, leading term last
-              umma_bf16(d_addr, dal, db, idesc, (kb | k) != 0);
+              umma_bf16(d_addr, dal, db, idesc, ((kb - kb_lo) | k) != 0);
               umma_bf16(d_addr, da, dbl, idesc, 1);
               umma_bf16(d_addr, da, db, idesc, 1);
             } else {
-              umma_bf16(d_addr, da, db, idesc, (kb | k) != 0);
+              umma_bf16(d_addr, da, db, idesc, ((kb - kb_lo) | k) != 0);
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (CM == 1) {
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          } else {
+            umma_commit_mc(&empty_bar[stage], kMcMask);  // ... in every CTA of the cluster
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -235,9 +308,66 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                                                    (p.sr_n % 4 == 0)));
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int co_t = t % p.tiles_co;
-      const int sp = t / p.tiles_co;
+    SkRange rng = my_range();
+    int wk = cluster_id - num_clusters, kb_lo = 0, kb_hi = num_kb;
+    while (stream_k ? rng.next(wk, kb_lo, kb_hi) : ((wk += num_clusters) < num_work)) {
+      if (stream_k && kb_hi < num_kb) {
+        // ---- this CTA's range ends inside the tile: publish the raw accumulators and move on
+        mbar_wait(&acc_full[acc], acc_phase, 104);
+        tc_fence_after();
+        float* slot = p.sk_partials + static_cast<long long>(blockIdx.x) * (128 * BLOCK_N);
+#pragma unroll
+        for (int ci = 0; ci < kCpw; ++ci) {
+          const int c = c_begin + ci;
+          if (c >= kChunks) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + c * 32), v);
+          tmem_ld_wait();
+          float* dst = slot + (c * 4 + q) * 1024 + lane;   // [chunk][quarter][column j][lane]: coalesced per j
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[j * 32] = __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          __threadfence();
+          atomicExch(p.sk_flags + blockIdx.x, p.sk_epoch);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
+      // contributors to the head of this tile (stream-K, range started inside the tile): CTAs below this one
+      int sk_first = blockIdx.x, sk_last = blockIdx.x;   // [sk_first, sk_last) = contributing CTA ids
+      if (stream_k && kb_lo > 0) {
+        const long long tile_start = static_cast<long long>(wk) * num_kb;
+        int cprev = static_cast<int>(blockIdx.x) - 1;
+        while (cprev >= 0) {
+          const long long b0 = total_it * cprev / gridDim.x, b1 = total_it * (cprev + 1) / gridDim.x;
+          if (b1 <= tile_start) break;
+          sk_first = cprev;
+          if (b0 <= tile_start) break;
+          --cprev;
+        }
+        for (int cc = sk_first + static_cast<int>(lane); cc < sk_last; cc += 32) {
+          const long long t0 = clock64();
+          while (atomicAdd(p.sk_flags + cc, 0) != p.sk_epoch) {
+            if (clock64() - t0 > 8000000000LL) {
+              atomicExch(&g_device_error, 106);
+              __trap();
+            }
+          }
+        }
+        __syncwarp();
+        __threadfence();
+      }
+      const int co_t = wk % p.tiles_co;
+      const int sp = (wk / p.tiles_co) * CM + cm_rank;
       const int tx0 = (sp % p.tiles_x) * p.bw;
       const int ty0 = ((sp / p.tiles_x) % p.tiles_y) * p.bh;
       const int tn0 = (sp / (p.tiles_x * p.tiles_y)) * p.bn;
@@ -303,6 +433,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         if (ci + 1 < kCpw && c + 1 < kChunks) prefetch(c + 1);
         tmem_ld_wait();
+        for (int cc = sk_first; cc < sk_last; ++cc) {   // stream-K: add the partial sums of the tile's head
+          const float* src = p.sk_partials + static_cast<long long>(cc) * (128 * BLOCK_N) + (c * 4 + q) * 1024 + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(src + j * 32));
+        }
         {
           const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
           const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c * 32);
@@ -471,6 +606,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }

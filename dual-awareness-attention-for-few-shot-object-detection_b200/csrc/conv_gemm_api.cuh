@@ -32,16 +32,33 @@ inline TileChoice choose_tile(int w, int h, int n, bool batched_b) {
   return best;
 }
 
-template <int BLOCK_N, int NSPLIT, bool FAST>
+template <int BLOCK_N, int NSPLIT, bool FAST, int CM>
 inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT>;
   static bool configured = false;
   if (!configured) {
-    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, FAST>,
+    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, FAST, CM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  conv_gemm_kernel<BLOCK_N, NSPLIT, FAST><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  if (CM == 1) {
+    conv_gemm_kernel<BLOCK_N, NSPLIT, FAST, CM><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CM;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DANA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, NSPLIT, FAST, CM>, p));
+  }
   DANA_LAUNCH_CHECK();
   return DANA_OK;
 }
@@ -63,10 +80,10 @@ inline bool fast_epilogue_ok(const ConvGemmParams& p, int nsplit) {
   return true;
 }
 
-template <int BLOCK_N, int NSPLIT>
+template <int BLOCK_N, int NSPLIT, int CM>
 inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stream) {
-  if (fast_epilogue_ok(p, NSPLIT)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, true>(p, grid, stream);
-  return launch_conv_gemm_v<BLOCK_N, NSPLIT, false>(p, grid, stream);
+  if (fast_epilogue_ok(p, NSPLIT)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, true, CM>(p, grid, stream);
+  return launch_conv_gemm_v<BLOCK_N, NSPLIT, false, CM>(p, grid, stream);
 }
 
 inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream) {
@@ -127,25 +144,12 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);
   p.out_f32 = a->out_f32;
 
-  // BLOCK_N heuristic: waves(tiles) * columns * per-column cost (narrow tiles are smem-read bound)
+  // BLOCK_N: the widest tile that the output fills (wide tiles read A once per 256 columns and keep the MMA off the
+  // shared-memory read limit); wave quantisation is handled by stream-K below, not by shrinking tiles
   const long long sp_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
   const int sms = sm_count();
-  int block_n = 64;
+  int block_n = a->n_out > 128 ? 256 : (a->n_out > 64 ? 128 : 64);
   {
-    double best = -1.0;
-    const int cand[3] = {256, 128, 64};
-    const double percol[3] = {0.5, 0.64, 0.80};
-    for (int i = 0; i < 3; ++i) {
-      const int bn_ = cand[i];
-      if (bn_ > 64 && a->n_out <= bn_ / 2) continue;
-      const long long tiles = sp_tiles * ((a->n_out + bn_ - 1) / bn_);
-      const long long waves = (tiles + sms - 1) / sms;
-      const double cost = static_cast<double>(waves) * (bn_ * percol[i] + 24.0);
-      if (best < 0 || cost < best) {
-        best = cost;
-        block_n = bn_;
-      }
-    }
     const char* env = getenv("DANA_BLOCK_N");
     if (env != nullptr) {
       const int v = atoi(env);
@@ -153,6 +157,16 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     }
   }
   p.tiles_co = (a->n_out + block_n - 1) / block_n;
+  // cluster of 2 CTAs along M sharing (multicasting) the weight tile: only where weights are shared across
+  // tiles (not the per-image attention operands), the K loop is long enough to matter and tiles are 256 wide
+  int cm = 1;
+  {
+    const long long k_total_ = static_cast<long long>(taps) * a->a_c;
+    // measured on B200 (tools/gemm_bench.py): no gain -- the big layers lose to wave quantisation, not to L2
+    // bandwidth -- so the multicast path is opt-in (DANA_CLUSTER=2) and stream-K below is the default remedy
+    const char* env = getenv("DANA_CLUSTER");
+    if (env != nullptr && atoi(env) == 2 && block_n == 256 && !batched && k_total_ >= 256 && sp_tiles >= 2) cm = 2;
+  }
 
   // tensor maps
   const int nsplit = (a->a_lo != nullptr) ? 2 : 1;
@@ -177,7 +191,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     const uint64_t bs = batched ? static_cast<uint64_t>(a->b_batch_stride)
                                 : static_cast<uint64_t>(a->b_pitch) * static_cast<uint64_t>(a->n_out);
     const uint64_t str[2] = {static_cast<uint64_t>(a->b_pitch) * 2, ((bs * 2 + 15) / 16) * 16};
-    const uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+    const uint32_t box[3] = {64, static_cast<uint32_t>(block_n / cm), 1};
     int rc = encode_bf16_map(&p.tm_b_hi, a->b_hi, 3, dims, str, box);
     if (rc != DANA_OK) return rc;
     if (nsplit == 2) {
@@ -186,16 +200,40 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     }
   }
 
-  const long long num_tiles = sp_tiles * p.tiles_co;
-  const int grid = static_cast<int>(num_tiles < sms ? num_tiles : sms);
-  if (nsplit == 1) {
-    if (block_n == 256) return launch_conv_gemm<256, 1>(p, grid, stream);
-    if (block_n == 128) return launch_conv_gemm<128, 1>(p, grid, stream);
-    return launch_conv_gemm<64, 1>(p, grid, stream);
+  const long long num_work = ((sp_tiles + cm - 1) / cm) * p.tiles_co;
+  const long long max_clusters = sms / cm;
+  int grid = static_cast<int>((num_work < max_clusters ? num_work : max_clusters) * cm);
+  // stream-K when whole-tile scheduling would leave SMs idle (partial last round or fewer tiles than SMs)
+  p.sk_epoch = 0;
+  {
+    const long long num_kb = static_cast<long long>(taps) * p.c_blocks;
+    const long long total_it = num_work * num_kb;
+    const long long rounds = (num_work + sms - 1) / sms;
+    const double eff = static_cast<double>(num_work) / static_cast<double>(rounds * sms);
+    const int64_t need = 4096 + static_cast<int64_t>(sms) * 128 * block_n * 4;
+    const char* env = getenv("DANA_STREAMK");
+    const bool allowed = (env == nullptr) || atoi(env) != 0;
+    // cost model (microseconds): a k-block costs ~0.8 us in x3 / ~0.27 us in bf16 at BLOCK_N = 256; stream-K pays
+    // ~4 us for publishing / collecting partial tiles
+    const double kb_us = (nsplit == 2 ? 0.8 : 0.27) * block_n / 256.0;
+    const double plain_us = static_cast<double>(rounds * num_kb) * kb_us;
+    const double sk_us = static_cast<double>((total_it + sms - 1) / sms) * kb_us + 4.0;
+    if (allowed && cm == 1 && a->workspace != nullptr && a->workspace_bytes >= need && a->sk_epoch != 0 && eff < 0.9 &&
+        sk_us < 0.85 * plain_us && total_it >= sms && sms <= 1024) {
+      p.sk_epoch = a->sk_epoch;
+      p.sk_flags = static_cast<int*>(a->workspace);
+      p.sk_partials = reinterpret_cast<float*>(static_cast<uint8_t*>(a->workspace) + 4096);
+      grid = sms;
+    }
   }
-  if (block_n == 256) return launch_conv_gemm<256, 2>(p, grid, stream);
-  if (block_n == 128) return launch_conv_gemm<128, 2>(p, grid, stream);
-  return launch_conv_gemm<64, 2>(p, grid, stream);
+  if (nsplit == 1) {
+    if (block_n == 256) return cm == 2 ? launch_conv_gemm<256, 1, 2>(p, grid, stream) : launch_conv_gemm<256, 1, 1>(p, grid, stream);
+    if (block_n == 128) return launch_conv_gemm<128, 1, 1>(p, grid, stream);
+    return launch_conv_gemm<64, 1, 1>(p, grid, stream);
+  }
+  if (block_n == 256) return cm == 2 ? launch_conv_gemm<256, 2, 2>(p, grid, stream) : launch_conv_gemm<256, 2, 1>(p, grid, stream);
+  if (block_n == 128) return launch_conv_gemm<128, 2, 1>(p, grid, stream);
+  return launch_conv_gemm<64, 2, 1>(p, grid, stream);
 }
 
 }  // namespace dana

@@ -88,6 +88,8 @@ int dana_roi_align_backward(const float* grad_out, const float* rois, int num_ro
                                 spatial_scale, sampling_ratio, grad_input, static_cast<cudaStream_t>(stream));
 }
 
+int64_t dana_conv_gemm_workspace_bytes(void) { return 4096 + static_cast<int64_t>(sm_count()) * 128 * 256 * 4; }
+
 int dana_conv_gemm(const dana_conv_gemm_args* args, void* stream) {
   return conv_gemm_dispatch(args, static_cast<cudaStream_t>(stream));
 }

@@ -21,6 +21,24 @@ def _count(n):
     LAUNCHES += n
 
 
+# stream-K scratch of the GEMM kernel: one zero-initialised buffer per device (single-stream use), and a
+# launch counter that serves as the epoch of the ready flags
+_SK_WS = {}
+_SK_EPOCH = 0
+
+
+def _sk_workspace(device):
+    global _SK_EPOCH
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _SK_WS.get(key)
+    if ws is None:
+        nbytes = _lib.load().dana_conv_gemm_workspace_bytes()
+        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        _SK_WS[key] = ws
+    _SK_EPOCH = _SK_EPOCH % 0x7FFFFFF0 + 1
+    return ws, _SK_EPOCH
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -104,6 +122,8 @@ def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strid
     args.r_sx, args.r_sy, args.r_sn = [int(v) for v in r_strides]
     args.alpha = float(alpha)
     args.relu = 1 if relu else 0
+    ws, epoch = _sk_workspace(a.hi.device)
+    args.workspace, args.workspace_bytes, args.sk_epoch = _p(ws), ws.numel(), epoch
     _count(1)
     if GEMM_TRACE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

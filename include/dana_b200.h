@@ -131,7 +131,14 @@ typedef struct dana_conv_gemm_args {
   int64_t r_sx, r_sy, r_sn;
   float alpha;
   int32_t relu;
+  /* Optional stream-K scratch (dana_conv_gemm_workspace_bytes() bytes, zero-initialised once, private to one
+   * stream).  sk_epoch must be non-zero and different for consecutive launches that share the workspace;
+   * workspace == NULL or sk_epoch == 0 selects whole-tile scheduling. */
+  void* workspace;
+  int64_t workspace_bytes;
+  int32_t sk_epoch;
 } dana_conv_gemm_args;
+int64_t dana_conv_gemm_workspace_bytes(void);
 int dana_conv_gemm(const dana_conv_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------
