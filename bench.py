@@ -175,6 +175,10 @@ def run_ours(args):
 
     value, t_max, units = aggregate_throughput(units=b * args.steps, seconds=dev_s, device=dev)
     e2e_value, _, _ = aggregate_throughput(units=b * args.steps, seconds=e2e_s, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {

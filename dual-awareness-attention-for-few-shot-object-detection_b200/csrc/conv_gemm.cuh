@@ -593,6 +593,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }  // !FAST
         __syncwarp();   // the tile is rewritten by the next chunk's phase A
       }
+      if (sk_first < sk_last) {
+        // every epilogue warp has folded the partial sums in: hand the contributors' flags back (zero), so the
+        // next launch -- or the next replay of a captured graph -- starts from a clean workspace
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et < sk_last - sk_first) atomicExch(p.sk_flags + sk_first + et, 0);
+      }
       // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
       tc_fence_before();
       __syncwarp();

@@ -219,11 +219,13 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     const double plain_us = static_cast<double>(rounds * num_kb) * kb_us;
     const double sk_us = static_cast<double>((total_it + sms - 1) / sms) * kb_us + 4.0;
     if (allowed && cm == 1 && a->workspace != nullptr && a->workspace_bytes >= need && a->sk_epoch != 0 && eff < 0.9 &&
-        sk_us < 0.85 * plain_us && total_it >= sms && sms <= 1024) {
-      p.sk_epoch = a->sk_epoch;
+        sk_us < 0.85 * plain_us && total_it >= sms && sms <= 1024 && num_work * 4 >= 16) {
+      p.sk_epoch = 1;   // flags are reset by the consumer, a constant "ready" value is enough
       p.sk_flags = static_cast<int*>(a->workspace);
       p.sk_partials = reinterpret_cast<float*>(static_cast<uint8_t*>(a->workspace) + 4096);
-      grid = sms;
+      // at most ~4 CTAs per tile: collecting many partial tiles costs more than it balances
+      const long long cap = num_work * 4;
+      grid = static_cast<int>(cap < sms ? cap : sms);
     }
   }
   if (nsplit == 1) {

@@ -288,25 +288,12 @@ roi_align_head_kernel(const float* __restrict__ feat /*NHWC*/, const float* __re
         float rs[8];
 #pragma unroll
         for (int v = 0; v < 8; ++v) rs[v] = 0.0f;
-        // four taps per trip, loads issued back to back (8 x 16 B in flight per thread); taps past nx carry
-        // weight 0 and re-read the last valid pixel, so no per-tap branch is needed
-        for (int k4 = 0; k4 < nx; k4 += 4) {
-          float4 f0[4], f1[4];
-          float wx[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int kx = k4 + j;
-            const int kc = kx < nx ? kx : nx - 1;
-            const float4* q4 = reinterpret_cast<const float4*>(px + static_cast<long long>(kc) * channels);
-            f0[j] = __ldg(q4);
-            f1[j] = __ldg(q4 + 1);
-            wx[j] = kx < nx ? s_wx[pw][kx] : 0.0f;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            rs[0] += wx[j] * f0[j].x; rs[1] += wx[j] * f0[j].y; rs[2] += wx[j] * f0[j].z; rs[3] += wx[j] * f0[j].w;
-            rs[4] += wx[j] * f1[j].x; rs[5] += wx[j] * f1[j].y; rs[6] += wx[j] * f1[j].z; rs[7] += wx[j] * f1[j].w;
-          }
+        for (int kx = 0; kx < nx; ++kx, px += channels) {
+          const float wx = s_wx[pw][kx];
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(px));
+          const float4 f1 = __ldg(reinterpret_cast<const float4*>(px) + 1);
+          rs[0] += wx * f0.x; rs[1] += wx * f0.y; rs[2] += wx * f0.z; rs[3] += wx * f0.w;
+          rs[4] += wx * f1.x; rs[5] += wx * f1.y; rs[6] += wx * f1.z; rs[7] += wx * f1.w;
         }
 #pragma unroll
         for (int v = 0; v < 8; ++v) acc[pw][v] += wy * rs[v];
