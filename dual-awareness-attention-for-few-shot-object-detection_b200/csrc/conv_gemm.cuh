@@ -23,6 +23,7 @@ struct ConvGemmParams {
   CUtensorMap tm_b_hi, tm_b_lo;  // 3-D (k, co, batch), box (64, BLOCK_N, 1)
   int tiles_x, tiles_y, tiles_n, tiles_co;
   int bw, bh, bn;
+  int lbw, lbh;   // log2(bw), log2(bh): the tile extents are powers of two
   int taps_r, taps_s, pad_y, pad_x;
   int c_blocks;   // ceil(C_in / 64)
   int c_in;       // K extent per tap
@@ -130,7 +131,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int cm_rank = (CM > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / CM;
   const int num_clusters = gridDim.x / CM;
-  const int num_work = ((sp_tiles + CM - 1) / CM) * p.tiles_co;
+  const int m_groups = (sp_tiles + CM - 1) / CM;
+  const int num_work = m_groups * p.tiles_co;
   constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CM) - 1u);
   const bool stream_k = (CM == 1) && (p.sk_epoch != 0);
   const long long total_it = static_cast<long long>(num_work) * num_kb;
@@ -186,8 +188,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       SkRange rng = my_range();
       int wk = cluster_id - num_clusters, kb_lo = 0, kb_hi = num_kb;
       while (stream_k ? rng.next(wk, kb_lo, kb_hi) : ((wk += num_clusters) < num_work)) {
-        const int co_t = wk % p.tiles_co;
-        const int sp = (wk / p.tiles_co) * CM + cm_rank;
+        const int co_t = wk / m_groups;   // N-tile is the slow index: a CTA keeps its weights / scale / bias
+        const int sp = (wk % m_groups) * CM + cm_rank;
         const int x0 = (sp % p.tiles_x) * p.bw;
         const int y0 = ((sp / p.tiles_x) % p.tiles_y) * p.bh;
         const int n0 = (sp / (p.tiles_x * p.tiles_y)) * p.bn;
@@ -308,6 +310,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                                                    (p.sr_n % 4 == 0)));
     int acc = 0;
     uint32_t acc_phase = 0;
+    int staged_co = -1, staged_n = -1;
     SkRange rng = my_range();
     int wk = cluster_id - num_clusters, kb_lo = 0, kb_hi = num_kb;
     while (stream_k ? rng.next(wk, kb_lo, kb_hi) : ((wk += num_clusters) < num_work)) {
@@ -366,11 +369,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         __syncwarp();
         __threadfence();
       }
-      const int co_t = wk % p.tiles_co;
-      const int sp = (wk / p.tiles_co) * CM + cm_rank;
-      const int tx0 = (sp % p.tiles_x) * p.bw;
-      const int ty0 = ((sp / p.tiles_x) % p.tiles_y) * p.bh;
-      const int tn0 = (sp / (p.tiles_x * p.tiles_y)) * p.bn;
+      // tile coordinates: integer divisions by runtime values are ~25 instructions each, so lane 0 does them
+      // once and the warp shares the results
+      int co_t = 0, tx0 = 0, ty0 = 0, tn0 = 0;
+      if (lane == 0) {
+        co_t = wk / m_groups;   // N-tile is the slow index: a CTA keeps its weights / scale / bias
+        const int sp = (wk - co_t * m_groups) * CM + cm_rank;
+        const int txy = p.tiles_x * p.tiles_y;
+        const int tn = sp / txy;
+        const int rem = sp - tn * txy;
+        const int ty = rem / p.tiles_x;
+        tx0 = (rem - ty * p.tiles_x) * p.bw;
+        ty0 = ty * p.bh;
+        tn0 = tn * p.bn;
+      }
+      co_t = __shfl_sync(0xffffffffu, co_t, 0);
+      tx0 = __shfl_sync(0xffffffffu, tx0, 0);
+      ty0 = __shfl_sync(0xffffffffu, ty0, 0);
+      tn0 = __shfl_sync(0xffffffffu, tn0, 0);
       const int co0 = co_t * BLOCK_N;
       // the four rows this lane serves in phase B
       long long o_off[4], r_off[4];
@@ -378,9 +394,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = q * 32 + 8 * i + sub;
-        const int x = tx0 + m % p.bw;
-        const int y = ty0 + (m / p.bw) % p.bh;
-        const int n = tn0 + m / (p.bw * p.bh);
+        const int x = tx0 + (m & (p.bw - 1));
+        const int y = ty0 + ((m >> p.lbw) & (p.bh - 1));
+        const int n = tn0 + (m >> (p.lbw + p.lbh));
         row_ok[i] = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
         o_off[i] = static_cast<long long>(n) * p.so_n + static_cast<long long>(y) * p.so_y +
                    static_cast<long long>(x) * p.so_x;
@@ -388,8 +404,34 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                    static_cast<long long>(x) * p.sr_x;
       }
 
+      // FAST path: per-row base pointers (first chunk of this warp, this lane's 8-channel group); chunk ci is
+      // then a compile-time offset of ci*32 elements, the lo plane a uniform delta
+      const __nv_bfloat16* rhp[4];
+      __nv_bfloat16* ohp[4];
+      const long long d_res = (FAST && res_pair && NSPLIT == 2) ? (p.res_lo - p.res_hi) : 0;
+      const long long d_out = (FAST && NSPLIT == 2) ? (p.out_lo - p.out_hi) : 0;
+      if constexpr (FAST) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rhp[i] = res_pair ? p.res_hi + r_off[i] + co0 + c_begin * 32 + cg : nullptr;
+          ohp[i] = p.out_hi + o_off[i] + co0 + c_begin * 32 + cg;
+        }
+      }
       uint4 rh[4], rl[4];
       auto prefetch = [&](int c) {
+        if constexpr (FAST) {
+          if (res_pair) {
+            const int ofs = (c - c_begin) * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (row_ok[i]) {
+                rh[i] = __ldg(reinterpret_cast<const uint4*>(rhp[i] + ofs));
+                if (NSPLIT == 2) rl[i] = __ldg(reinterpret_cast<const uint4*>(rhp[i] + d_res + ofs));
+              }
+            }
+          }
+          return;
+        }
         const int col = co0 + c * 32 + cg;
         if (res_vec && col + 8 <= p.n_out) {
 #pragma unroll
@@ -403,16 +445,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       };
       if (c_begin < kChunks) prefetch(c_begin);
 
-      // stage per-channel scale (x alpha) / bias for this tile
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = et; i < BLOCK_N; i += 256) {
-        const int co = co0 + i;
-        s_scale[i] = ((p.scale != nullptr && co < p.n_out) ? __ldg(p.scale + co) : 1.0f) * p.alpha;
-        s_bias[i] = (p.bias != nullptr && co < p.n_out)
-                        ? __ldg(p.bias + static_cast<long long>(tn0) * p.bias_sn + co)
-                        : 0.0f;
+      // stage per-channel scale (x alpha) / bias -- only when the N-tile (or, with per-image bias, the image)
+      // changes, which with N-major tile order is once or twice per CTA
+      if (co_t != staged_co || (p.bias_sn != 0 && tn0 != staged_n)) {
+        staged_co = co_t;
+        staged_n = tn0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < BLOCK_N; i += 256) {
+          const int co = co0 + i;
+          s_scale[i] = ((p.scale != nullptr && co < p.n_out) ? __ldg(p.scale + co) : 1.0f) * p.alpha;
+          s_bias[i] = (p.bias != nullptr && co < p.n_out)
+                          ? __ldg(p.bias + static_cast<long long>(tn0) * p.bias_sn + co)
+                          : 0.0f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       mbar_wait(&acc_full[acc], acc_phase, 104);
       tc_fence_after();
@@ -439,24 +486,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(src + j * 32));
         }
         {
-          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
-          const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c * 32);
-          float4* trow = reinterpret_cast<float4*>(tb + lane * 32);
+          // raw accumulators into the swizzled tile; scale / bias are applied in phase B, where a lane needs
+          // only the 8 values of its own channel group
+          uint4* trow = reinterpret_cast<uint4*>(tb + lane * 32);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 sc = sc4[g], bi = bi4[g];
-            float4 o;
-            o.x = __uint_as_float(v[g * 4 + 0]) * sc.x + bi.x;
-            o.y = __uint_as_float(v[g * 4 + 1]) * sc.y + bi.y;
-            o.z = __uint_as_float(v[g * 4 + 2]) * sc.z + bi.z;
-            o.w = __uint_as_float(v[g * 4 + 3]) * sc.w + bi.w;
-            trow[g ^ (lane & 7)] = o;
-          }
+          for (int g = 0; g < 8; ++g) trow[g ^ (lane & 7)] = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
         }
         __syncwarp();
         // ---- phase B: 8 consecutive channels of 4 rows per lane, row-contiguous global accesses
         const int col = co0 + c * 32 + cg;
         const bool col_full = (col + 8 <= p.n_out);
+        const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c * 32 + cg);
+        const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + c * 32 + cg + 4);
+        const float4 bi0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cg);
+        const float4 bi1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cg + 4);
         if constexpr (FAST) {
           const float floor_v = p.relu ? 0.0f : -INFINITY;
 #pragma unroll
@@ -465,7 +508,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const float4* trow = reinterpret_cast<const float4*>(tb + r * 32);
             const float4 a = trow[(2 * (lane & 3)) ^ (r & 7)];
             const float4 b = trow[(2 * (lane & 3) + 1) ^ (r & 7)];
-            float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            float f[8] = {a.x * sc0.x + bi0.x, a.y * sc0.y + bi0.y, a.z * sc0.z + bi0.z, a.w * sc0.w + bi0.w,
+                          b.x * sc1.x + bi1.x, b.y * sc1.y + bi1.y, b.z * sc1.z + bi1.z, b.w * sc1.w + bi1.w};
             if (res_pair) {
               const uint32_t wh[4] = {ch[i].x, ch[i].y, ch[i].z, ch[i].w};
 #pragma unroll
@@ -495,9 +539,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               }
             }
             if (row_ok[i]) {
-              *reinterpret_cast<uint4*>(p.out_hi + o_off[i] + col) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              if (NSPLIT == 2)
-                *reinterpret_cast<uint4*>(p.out_lo + o_off[i] + col) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              *reinterpret_cast<uint4*>(ohp[i] + ci * 32) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              if (NSPLIT == 2) *reinterpret_cast<uint4*>(ohp[i] + d_out + ci * 32) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
           }
         } else {
@@ -508,7 +551,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const float4 a = trow[(2 * (lane & 3)) ^ (r & 7)];
           const float4 b = trow[(2 * (lane & 3) + 1) ^ (r & 7)];
           if (!row_ok[i] || col >= p.n_out) continue;
-          float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          float f[8] = {a.x * sc0.x + bi0.x, a.y * sc0.y + bi0.y, a.z * sc0.z + bi0.z, a.w * sc0.w + bi0.w,
+                          b.x * sc1.x + bi1.x, b.y * sc1.y + bi1.y, b.z * sc1.z + bi1.z, b.w * sc1.w + bi1.w};
           if (p.res_f32 != nullptr) {
             const float* rp = p.res_f32 + r_off[i] + col;
             if (col_full && out_vec) {

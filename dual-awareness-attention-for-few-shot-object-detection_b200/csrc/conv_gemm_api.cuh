@@ -111,6 +111,10 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   p.bw = tc.bw;
   p.bh = tc.bh;
   p.bn = tc.bn;
+  auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  if ((tc.bw & (tc.bw - 1)) || (tc.bh & (tc.bh - 1))) return DANA_EINVAL;   // power-of-two tile extents
+  p.lbw = ilog2(tc.bw);
+  p.lbh = ilog2(tc.bh);
   p.tiles_x = (a->out_w + tc.bw - 1) / tc.bw;
   p.tiles_y = (a->out_h + tc.bh - 1) / tc.bh;
   p.tiles_n = (a->out_n + tc.bn - 1) / tc.bn;

@@ -27,6 +27,9 @@ SHAPES = [
     ("l4.conv2 3x3 512->512", 1200, 4, 4, 512, 512, 3, 1, False),
     ("l4.conv3 1x1 512->2048 +res", 1200, 4, 4, 512, 2048, 1, 1, True),
     ("l4.conv1 1x1 2048->512", 1200, 4, 4, 2048, 512, 1, 1, False),
+    ("exp 1x1 64->256 no res", 4, 150, 250, 64, 256, 1, 1, False),
+    ("exp 1x1 256->256 +res", 4, 150, 250, 256, 256, 1, 1, True),
+    ("exp 1x1 64->64 +res", 4, 150, 250, 64, 64, 1, 1, True),
 ]
 
 ap = argparse.ArgumentParser()
