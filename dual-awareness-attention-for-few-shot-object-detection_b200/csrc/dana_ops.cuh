@@ -380,23 +380,48 @@ __global__ void center_apply_kernel(const float* __restrict__ in, const float* _
 // 1/sqrt(d) in the GEMM epilogue), `segs` segments of `ns` columns per row -> P bf16 pair, pad = 0.
 // warp per row.
 // ---------------------------------------------------------------------------------------------
-__global__ void attn_softmax_kernel(const float* __restrict__ s, long long rows, int segs, int ns, int pitch,
-                                    __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// One warp per (row, segment): the segment lives in registers (<= 16 values per lane, ns <= 512), one expf per
+// element, warp-shuffle max / sum, coalesced lane-strided loads and bf16 stores.
+__global__ void __launch_bounds__(256)
+attn_softmax_kernel(const float* __restrict__ s, long long rows, int segs, int ns, int pitch,
+                    __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+  const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float* sr = s + row * pitch;
-  for (int k = 0; k < segs; ++k) {
-    const float* sk = sr + k * ns;
-    float mx = -INFINITY;
-    for (int j = lane; j < ns; j += 32) mx = fmaxf(mx, sk[j]);
-    mx = warp_max(mx);
-    float sum = 0.0f;
-    for (int j = lane; j < ns; j += 32) sum += expf(sk[j] - mx);
-    sum = warp_sum(sum);
-    for (int j = lane; j < ns; j += 32) st_pair(p_hi, p_lo, row * pitch + k * ns + j, expf(sk[j] - mx) / sum);
+  if (wid >= rows * segs) return;
+  const long long row = wid / segs;
+  const int k = static_cast<int>(wid - row * segs);
+  const long long base = row * pitch + static_cast<long long>(k) * ns;
+  float v[16];
+  float mx = -INFINITY;
+  const int nt = (ns + 31) >> 5;   // live register slots (uniform)
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (t < nt) {
+      const int j = lane + 32 * t;
+      v[t] = (j < ns) ? s[base + j] : -INFINITY;
+      mx = fmaxf(mx, v[t]);
+    }
   }
-  for (int j = segs * ns + lane; j < pitch; j += 32) st_pair(p_hi, p_lo, row * pitch + j, 0.0f);
+  mx = warp_max(mx);
+  float sum = 0.0f;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (t < nt) {
+      v[t] = (lane + 32 * t < ns) ? expf(v[t] - mx) : 0.0f;
+      sum += v[t];
+    }
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (t < nt) {
+      const int j = lane + 32 * t;
+      if (j < ns) st_pair(p_hi, p_lo, base + j, v[t] * inv);
+    }
+  }
+  if (k == segs - 1)   // zero the row's pad columns
+    for (int j = segs * ns + lane; j < pitch; j += 32) st_pair(p_hi, p_lo, row * pitch + j, 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------
