@@ -39,6 +39,7 @@ class ConvGemmArgs(Structure):
         ("r_sx", c_int64), ("r_sy", c_int64), ("r_sn", c_int64),
         ("alpha", c_float), ("relu", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_int64), ("sk_epoch", c_int32),
+        ("softmax_ns", c_int32), ("softmax_pitch", c_int32),
     ]
 
 
@@ -68,7 +69,7 @@ SIGNATURES = {
     "dana_support_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "dana_center_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_attn_softmax": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dana_rpn_fg_prob": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),

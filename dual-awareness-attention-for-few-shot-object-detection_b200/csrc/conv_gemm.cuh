@@ -47,6 +47,7 @@ struct ConvGemmParams {
   float* sk_partials;   // [grid][128 * BLOCK_N]
   int* sk_flags;        // [grid]
   int sk_epoch;         // value a flag takes when this launch's partial is published; 0 = stream-K off
+  int sm_ns, sm_pitch;  // SOFTMAX epilogue: keys per segment, column pitch of a segment in the output
 };
 
 constexpr int kGemmThreads = 320;
@@ -97,9 +98,15 @@ struct SkRange {
 // N-tile; each loads 1/CM of the weight (B) tile and TMA-multicasts it to all of them, which divides the L2->SM
 // weight traffic by CM (the compute-bound layers are L2-bandwidth bound at 128x256 tiles).  A smem slot is
 // released cluster-wide: every CTA's MMA commit arrives on the `empty` barrier of all CM CTAs.
-template <int BLOCK_N, int NSPLIT, bool FAST, int CM>
+// EPI: 0 generic epilogue, 1 FAST, 2 SOFTMAX -- the attention-logits contraction with the row softmax fused in
+// (dana.py:142-143,273-274): N-tile t is shot t's segment of sm_ns keys (sm_ns <= BLOCK_N), the epilogue takes
+// max / sum over the segment straight from TMEM and writes the normalised probabilities as a bf16 pair at
+// column t*sm_pitch (pad columns zeroed); the fp32 logits never leave the SM.
+template <int BLOCK_N, int NSPLIT, int EPI, int CM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  constexpr bool FAST = (EPI == 1);
+  constexpr bool SOFTMAX = (EPI == 2);
   using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT>;
   constexpr int kStages = Cfg::kStages;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
@@ -206,7 +213,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const int kbk = tap * p.c_in + cb * kTileK;
           tma_load_4d(st, &p.tm_a_hi, &full_bar[stage], ka, x0 + s - p.pad_x, y0 + r - p.pad_y, n0);
           if (CM == 1) {
-            tma_load_3d(st + NSPLIT * kATileBytes, &p.tm_b_hi, &full_bar[stage], kbk, co_t * BLOCK_N, bcoord);
+            tma_load_3d(st + NSPLIT * kATileBytes, &p.tm_b_hi, &full_bar[stage], kbk, SOFTMAX ? co_t * p.sm_ns : co_t * BLOCK_N, bcoord);
           } else {
             tma_load_3d_mc(st + NSPLIT * kATileBytes + cm_rank * (Cfg::kBTileBytes / CM), &p.tm_b_hi, &full_bar[stage],
                            kbk, co_t * BLOCK_N + cm_rank * (BLOCK_N / CM), 0, kMcMask);
@@ -214,8 +221,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (NSPLIT == 2) {
             tma_load_4d(st + kATileBytes, &p.tm_a_lo, &full_bar[stage], ka, x0 + s - p.pad_x, y0 + r - p.pad_y, n0);
             if (CM == 1) {
-              tma_load_3d(st + 2 * kATileBytes + Cfg::kBTileBytes, &p.tm_b_lo, &full_bar[stage], kbk, co_t * BLOCK_N,
-                          bcoord);
+              tma_load_3d(st + 2 * kATileBytes + Cfg::kBTileBytes, &p.tm_b_lo, &full_bar[stage], kbk,
+                          SOFTMAX ? co_t * p.sm_ns : co_t * BLOCK_N, bcoord);
             } else {
               tma_load_3d_mc(st + 2 * kATileBytes + Cfg::kBTileBytes + cm_rank * (Cfg::kBTileBytes / CM), &p.tm_b_lo,
                              &full_bar[stage], kbk, co_t * BLOCK_N + cm_rank * (BLOCK_N / CM), 0, kMcMask);
@@ -463,6 +470,83 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
       mbar_wait(&acc_full[acc], acc_phase, 104);
       tc_fence_after();
+      if constexpr (SOFTMAX) {
+        const int ns = p.sm_ns;
+        const int used = (ns + 31) >> 5;                       // chunks that hold keys
+        const uint32_t trow0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+        // row statistics (lane = row): two passes over the segment in TMEM
+        float mx = -INFINITY;
+        for (int c = 0; c < used; ++c) {
+          uint32_t v[32];
+          tmem_ld32(trow0 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < ns) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
+        float sum = 0.0f;
+        for (int c = 0; c < used; ++c) {
+          uint32_t v[32];
+          tmem_ld32(trow0 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < ns) sum += expf((__uint_as_float(v[j]) - mx) * p.alpha);
+        }
+        const float inv = 1.0f / sum;
+        const long long seg_col = static_cast<long long>(co_t) * p.sm_pitch;
+#pragma unroll
+        for (int ci = 0; ci < kCpw; ++ci) {
+          const int c = c_begin + ci;
+          if (c >= kChunks || c * 32 >= p.sm_pitch) break;
+          uint32_t v[32];
+          tmem_ld32(trow0 + c * 32, v);
+          tmem_ld_wait();
+          float4* trow = reinterpret_cast<float4*>(tb + lane * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 o;
+            o.x = (c * 32 + g * 4 + 0 < ns) ? expf((__uint_as_float(v[g * 4 + 0]) - mx) * p.alpha) * inv : 0.0f;
+            o.y = (c * 32 + g * 4 + 1 < ns) ? expf((__uint_as_float(v[g * 4 + 1]) - mx) * p.alpha) * inv : 0.0f;
+            o.z = (c * 32 + g * 4 + 2 < ns) ? expf((__uint_as_float(v[g * 4 + 2]) - mx) * p.alpha) * inv : 0.0f;
+            o.w = (c * 32 + g * 4 + 3 < ns) ? expf((__uint_as_float(v[g * 4 + 3]) - mx) * p.alpha) * inv : 0.0f;
+            trow[g ^ (lane & 7)] = o;
+          }
+          __syncwarp();
+          const int col = c * 32 + cg;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + sub;
+            const float4* tr = reinterpret_cast<const float4*>(tb + r * 32);
+            const float4 a = tr[(2 * (lane & 3)) ^ (r & 7)];
+            const float4 b = tr[(2 * (lane & 3) + 1) ^ (r & 7)];
+            if (row_ok[i] && col < p.sm_pitch) {
+              const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+              uint32_t ph[4], pl[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * e] - __uint_as_float(ph[e] << 16),
+                                                                f[2 * e + 1] - __uint_as_float(ph[e] & 0xFFFF0000u));
+                pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              *reinterpret_cast<uint4*>(p.out_hi + o_off[i] + seg_col + col) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              if (NSPLIT == 2)
+                *reinterpret_cast<uint4*>(p.out_lo + o_off[i] + seg_col + col) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
 #pragma unroll
       for (int ci = 0; ci < kCpw; ++ci) {
         const int c = c_begin + ci;

@@ -32,17 +32,17 @@ inline TileChoice choose_tile(int w, int h, int n, bool batched_b) {
   return best;
 }
 
-template <int BLOCK_N, int NSPLIT, bool FAST, int CM>
+template <int BLOCK_N, int NSPLIT, int EPI, int CM>
 inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT>;
   static bool configured = false;
   if (!configured) {
-    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, FAST, CM>,
+    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   if (CM == 1) {
-    conv_gemm_kernel<BLOCK_N, NSPLIT, FAST, CM><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+    conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -57,7 +57,7 @@ inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t st
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DANA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, NSPLIT, FAST, CM>, p));
+    DANA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM>, p));
   }
   DANA_LAUNCH_CHECK();
   return DANA_OK;
@@ -82,8 +82,12 @@ inline bool fast_epilogue_ok(const ConvGemmParams& p, int nsplit) {
 
 template <int BLOCK_N, int NSPLIT, int CM>
 inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stream) {
-  if (fast_epilogue_ok(p, NSPLIT)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, true, CM>(p, grid, stream);
-  return launch_conv_gemm_v<BLOCK_N, NSPLIT, false, CM>(p, grid, stream);
+  if (p.sm_ns > 0) {
+    if constexpr (CM == 1 && BLOCK_N != 128) return launch_conv_gemm_v<BLOCK_N, NSPLIT, 2, 1>(p, grid, stream);
+    return DANA_ENOTSUP;
+  }
+  if (fast_epilogue_ok(p, NSPLIT)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, 1, CM>(p, grid, stream);
+  return launch_conv_gemm_v<BLOCK_N, NSPLIT, 0, CM>(p, grid, stream);
 }
 
 inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream) {
@@ -101,6 +105,15 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   if ((a->a_sx % 8) || (a->a_sy % 8) || (a->a_sn % 8) || (a->b_pitch % 8) || (a->b_batch_stride % 8))
     return DANA_EINVAL;
   const bool batched = a->b_batch_stride != 0;
+  const bool softmax = a->softmax_ns > 0;
+  if (softmax) {
+    auto al16b = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (a->softmax_ns > 256 || a->softmax_pitch < a->softmax_ns || (a->softmax_pitch % 8) != 0) return DANA_EINVAL;
+    if (a->out_hi == nullptr || a->out_f32 != nullptr || a->scale || a->bias || a->res_hi || a->res_f32) return DANA_EINVAL;
+    if (!al16b(a->out_hi) || (a->out_lo && !al16b(a->out_lo)) || (a->o_sx % 8) || (a->o_sy % 8) || (a->o_sn % 8))
+      return DANA_EINVAL;
+    if ((a->a_lo != nullptr) != (a->out_lo != nullptr)) return DANA_EINVAL;
+  }
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -153,14 +166,17 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   const long long sp_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
   const int sms = sm_count();
   int block_n = a->n_out > 128 ? 256 : (a->n_out > 64 ? 128 : 64);
+  if (softmax) block_n = a->softmax_ns <= 64 ? 64 : 256;   // one N-tile per shot segment
   {
     const char* env = getenv("DANA_BLOCK_N");
-    if (env != nullptr) {
+    if (env != nullptr && !softmax) {
       const int v = atoi(env);
       if (v == 64 || v == 128 || v == 256) block_n = v;
     }
   }
-  p.tiles_co = (a->n_out + block_n - 1) / block_n;
+  p.tiles_co = softmax ? (a->n_out + a->softmax_ns - 1) / a->softmax_ns : (a->n_out + block_n - 1) / block_n;
+  p.sm_ns = softmax ? a->softmax_ns : 0;
+  p.sm_pitch = softmax ? a->softmax_pitch : 0;
   // cluster of 2 CTAs along M sharing (multicasting) the weight tile: only where weights are shared across
   // tiles (not the per-image attention operands), the K loop is long enough to matter and tiles are 256 wide
   int cm = 1;
@@ -222,7 +238,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     const double kb_us = (nsplit == 2 ? 0.8 : 0.27) * block_n / 256.0;
     const double plain_us = static_cast<double>(rounds * num_kb) * kb_us;
     const double sk_us = static_cast<double>((total_it + sms - 1) / sms) * kb_us + 4.0;
-    if (allowed && cm == 1 && a->workspace != nullptr && a->workspace_bytes >= need && a->sk_epoch != 0 && eff < 0.9 &&
+    if (allowed && !softmax && cm == 1 && a->workspace != nullptr && a->workspace_bytes >= need && a->sk_epoch != 0 && eff < 0.9 &&
         sk_us < 0.85 * plain_us && total_it >= sms && sms <= 1024 && num_work * 4 >= 16) {
       p.sk_epoch = 1;   // flags are reset by the consumer, a constant "ready" value is enough
       p.sk_flags = static_cast<int*>(a->workspace);

@@ -294,7 +294,7 @@ __global__ void support_enhance_logit_kernel(float* __restrict__ v, const float*
 // vt layout: vt[(map / shots)][ch][ (map % shots) * ns + n ] with row pitch vt_pitch
 // grid: (ceil(ns/32), ceil(c/32), maps), block (32, 8)
 __global__ void support_finalize_kernel(const float* __restrict__ v, const float* __restrict__ colmean, int ns, int c,
-                                        int shots, long long vt_pitch, __nv_bfloat16* __restrict__ vc_hi,
+                                        int shots, int seg_pitch, long long vt_pitch, __nv_bfloat16* __restrict__ vc_hi,
                                         __nv_bfloat16* __restrict__ vc_lo, __nv_bfloat16* __restrict__ vt_hi,
                                         __nv_bfloat16* __restrict__ vt_lo) {
   __shared__ float tile[32][33];
@@ -316,7 +316,7 @@ __global__ void support_finalize_kernel(const float* __restrict__ v, const float
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int ch = c0 + i, n = n0 + threadIdx.x;
     if (ch < c && n < ns) {
-      const long long o = (static_cast<long long>(set) * c + ch) * vt_pitch + static_cast<long long>(slot) * ns + n;
+      const long long o = (static_cast<long long>(set) * c + ch) * vt_pitch + static_cast<long long>(slot) * seg_pitch + n;
       st_pair(vt_hi, vt_lo, o, tile[threadIdx.x][i]);
     }
   }

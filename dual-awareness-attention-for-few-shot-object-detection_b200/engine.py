@@ -152,21 +152,39 @@ class DanaEngine:
         return x
 
     # ------------------------------------------------------------------ attention
+    @staticmethod
+    def seg_pitch(ns):
+        """Column pitch of one shot's key segment in P / V^T: 8-aligned where the fused softmax epilogue is used."""
+        return (ns + 7) // 8 * 8 if ns <= 256 else ns
+
     def _attention(self, qc: Pair, kc_all: Pair, vt_all: Pair, rbar_all, set_index, sets, batch, ns, out: Pair):
         """CISA contractions for one support set (dana.py:142-150 / :273-281).
         qc [batch*rows, 256] centred queries; kc_all [batch*sets*K*ns, 256]; vt_all [batch*sets, C, pitch];
-        rbar_all [batch*sets, C].  Writes the attended feature into `out` [batch*rows, C] (any row pitch)."""
+        rbar_all [batch*sets, C].  Writes the attended feature into `out` [batch*rows, C] (any row pitch).
+        ns <= 256: the logits GEMM carries the softmax in its epilogue (no fp32 logits in HBM);
+        larger segments: logits GEMM -> attn_softmax kernel."""
         k = self.n_shot
         d = qc.hi.shape[1]
         c = vt_all.hi.shape[1]
         pitch = vt_all.hi.shape[2]
+        sp = self.seg_pitch(ns)
         kn = k * ns
         rows_total = qc.hi.shape[0]
         kc = kc_all[set_index * kn:]
-        logits = torch.empty((rows_total, pitch), dtype=torch.float32, device=self.device)
-        ops.linear(qc, kc, kn, alpha=1.0 / math.sqrt(d), out_f32=logits, batch=batch, b_batch_stride=sets * kn * d)
-        p = ops.attn_softmax(logits, k, ns, split=self.split)
-        p_view = Pair(p.hi[:, :kn], None if p.lo is None else p.lo[:, :kn])
+        if ns <= 256:
+            p = Pair.empty((rows_total, pitch), self.device, self.split)
+            if pitch > k * sp:                       # row-pitch padding beyond the last segment must be finite
+                p.hi[:, k * sp:].zero_()
+                if p.lo is not None:
+                    p.lo[:, k * sp:].zero_()
+            ops.linear(qc, kc, kn, alpha=1.0 / math.sqrt(d), out=p, batch=batch, b_batch_stride=sets * kn * d,
+                       softmax_ns=ns, softmax_pitch=sp)
+        else:
+            logits = torch.empty((rows_total, pitch), dtype=torch.float32, device=self.device)
+            ops.linear(qc, kc, kn, alpha=1.0 / math.sqrt(d), out_f32=logits, batch=batch, b_batch_stride=sets * kn * d)
+            p = ops.attn_softmax(logits, k, ns, split=self.split)
+        kk = k * sp
+        p_view = Pair(p.hi[:, :kk], None if p.lo is None else p.lo[:, :kk])
         vt = vt_all[set_index:]
         vt2 = Pair(vt.hi.view(-1, pitch), None if vt.lo is None else vt.lo.view(-1, pitch))
         ops.linear(p_view, vt2, c, alpha=1.0 / k, bias=rbar_all[set_index:], bias_sn=sets * c, out=out, batch=batch,
@@ -182,10 +200,11 @@ class DanaEngine:
         maps, sh, sw, c = sup.hi.shape
         ns, nq = sh * sw, qh * qw
         # support side, all sets*K maps at once (:126-147)
-        pitch = (k * ns + 7) // 8 * 8
+        pitch = (k * self.seg_pitch(ns) + 7) // 8 * 8
         vc, vt, rbar = ops.support_prepare(sup.view(maps, ns, c), self.pe(ns), k, ba_w=self.ba_w, ba_b=self.ba_b,
                                            gamma=self.channel_gamma, un_w=self.rpn_un_w, un_b=self.rpn_un_b,
-                                           unary_gamma=self.unary_gamma, vt_pitch=pitch, split=split)
+                                           unary_gamma=self.unary_gamma, vt_pitch=pitch, seg_pitch=self.seg_pitch(ns),
+                                           split=split)
         kc = ops.linear(vc, self.rpn_k_w, 256, split=split)
         # query side (:118,124-125)
         x2d = Pair(corr.hi.view(b * nq, 2048)[:, :1024], None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, :1024])
@@ -306,10 +325,10 @@ class DanaEngine:
         s_pooled = ops.avgpool(sup, sp_k)                                 # dana.py:114  [maps,7,7,C] fp32
         if "support_pooled" in want:
             extra["support_pooled"] = s_pooled.permute(0, 3, 1, 2)
-        pitch_h = (k * bins + 7) // 8 * 8
+        pitch_h = (k * self.seg_pitch(bins) + 7) // 8 * 8
         vc_h, vt_h, rbar_h = ops.support_prepare(s_pooled.view(maps, bins, c), self.pe(bins), k, un_w=self.rcnn_un_w,
                                                  un_b=self.rcnn_un_b, unary_gamma=self.unary_gamma, vt_pitch=pitch_h,
-                                                 split=split)
+                                                 seg_pitch=self.seg_pitch(bins), split=split)
         kc_h = ops.linear(vc_h, self.rcnn_k_w, 256, split=split)
         if qpe is None:
             qpe = Pair.empty((r * bins, c), dev, split)

@@ -97,7 +97,7 @@ class Pair:
 def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strides, *, out: Optional[Pair] = None,
               out_f32=None, taps=(1, 1, 0, 0), scale=None, bias=None, bias_sn=0, res: Optional[Pair] = None,
               res_f32=None, r_strides=(0, 0, 0), relu=False, alpha=1.0, b_pitch=None, b_batch_stride=0,
-              tile=(0, 0, 0)):
+              tile=(0, 0, 0), softmax_ns=0, softmax_pitch=0):
     """Raw call of dana_conv_gemm; see include/dana_b200.h for the argument meaning."""
     _need_cuda(a.hi, w.hi)
     args = ConvGemmArgs()
@@ -124,6 +124,7 @@ def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strid
     args.relu = 1 if relu else 0
     ws, epoch = _sk_workspace(a.hi.device)
     args.workspace, args.workspace_bytes, args.sk_epoch = _p(ws), ws.numel(), epoch
+    args.softmax_ns, args.softmax_pitch = int(softmax_ns), int(softmax_pitch)
     _count(1)
     if GEMM_TRACE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -175,7 +176,8 @@ def conv_nhwc(x: Pair, w: Pair, n_out: int, *, ksize=1, stride=1, scale=None, bi
 
 
 def linear(x: Pair, w: Pair, n_out: int, *, bias=None, scale=None, relu=False, alpha=1.0, out: Optional[Pair] = None,
-           out_f32=None, split=True, batch=1, b_batch_stride=0, bias_sn=0, res_f32=None):
+           out_f32=None, split=True, batch=1, b_batch_stride=0, bias_sn=0, res_f32=None, softmax_ns=0,
+           softmax_pitch=0):
     """y = alpha * x @ w.T (* scale) + bias on a row-major pair x [batch*rows, K] (nn.Linear / torch.bmm,
     dana.py:124,140,142,147).  With batch > 1 the rows are split evenly and w / bias may differ per batch."""
     rows_total, k = x.hi.shape
@@ -193,7 +195,7 @@ def linear(x: Pair, w: Pair, n_out: int, *, bias=None, scale=None, relu=False, a
     conv_gemm(x, (k, rows, 1, batch), (pitch, pitch * rows, pitch * rows), w, n_out, (rows, 1, batch),
               (opitch, opitch * rows, opitch * rows), out=out, out_f32=out_f32, scale=scale, bias=bias,
               bias_sn=bias_sn, relu=relu, alpha=alpha, b_batch_stride=b_batch_stride, res_f32=res_f32,
-              r_strides=r_strides)
+              r_strides=r_strides, softmax_ns=softmax_ns, softmax_pitch=softmax_pitch)
     return out if out is not None else out_f32
 
 
@@ -374,7 +376,7 @@ def avgpool(x: Pair, k: int):
 
 
 def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b, unary_gamma=0.1, vt_pitch,
-                    split=True):
+                    seg_pitch=None, split=True):
     """Support side of BA+CISA.  x: Pair or fp32 tensor [maps, ns, c].  Returns (vc pair [maps*ns, c],
     vt pair [sets, c, vt_pitch], rbar fp32 [sets, c])."""
     if isinstance(x, Pair):
@@ -399,7 +401,8 @@ def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b
     check(_lib.load().dana_support_prepare(in_hi, in_lo, in_f32, _p(pe), maps, shots, ns, c, _p(ba_w), _p(ba_b),
                                            float(gamma), _p(un_w), _p(un_b), float(unary_gamma), _p(v), _p(logit),
                                            _p(g), _p(r), _p(colmean), _p(vc.hi), _p(vc.lo), _p(vt.hi), _p(vt.lo),
-                                           int(vt_pitch), _p(rbar), _stream()), "dana_support_prepare")
+                                           int(vt_pitch), int(seg_pitch if seg_pitch is not None else ns), _p(rbar),
+                                           _stream()), "dana_support_prepare")
     return vc, vt, rbar
 
 

@@ -137,6 +137,11 @@ typedef struct dana_conv_gemm_args {
   void* workspace;
   int64_t workspace_bytes;
   int32_t sk_epoch;
+  /* Fused attention softmax (dana.py:142-143): when softmax_ns > 0 the n_out columns are consecutive segments of
+   * softmax_ns keys (one per shot, softmax_ns <= 256); the epilogue writes softmax_j(alpha * acc) of every segment
+   * as a bf16 pair at column segment * softmax_pitch (softmax_pitch % 8 == 0, pad columns zeroed). */
+  int32_t softmax_ns;
+  int32_t softmax_pitch;
 } dana_conv_gemm_args;
 int64_t dana_conv_gemm_workspace_bytes(void);
 int dana_conv_gemm(const dana_conv_gemm_args* args, void* stream);
@@ -156,12 +161,13 @@ int dana_maxpool3x3s2(const void* in_hi, const void* in_lo, int batch, int h, in
 int dana_avgpool(const void* in_hi, const void* in_lo, int maps, int h, int w, int c, int k, float* out, void* stream);
 /* Support side of BA + CISA (dana.py:126-147; rcnn_head :255-276 with ba_w == NULL): positional
  * encoding, background-attenuation gate, unary term r, mean-centred k-projection input (vc) and the
- * transposed values vt[set][c][shot*ns + n] (row pitch vt_pitch) for the P.V contraction. */
+ * transposed values vt[set][c][shot*seg_pitch + n] (row pitch vt_pitch, seg_pitch >= ns) for the P.V
+ * contraction. */
 int dana_support_prepare(const void* in_hi, const void* in_lo, const float* in_f32, const float* pe, int maps,
                          int shots, int ns, int c, const float* ba_w, const float* ba_b, float gamma,
                          const float* un_w, const float* un_b, float unary_gamma, float* v, float* logit, float* g,
                          float* r, float* colmean, void* vc_hi, void* vc_lo, void* vt_hi, void* vt_lo,
-                         int64_t vt_pitch, float* rbar, void* stream);
+                         int64_t vt_pitch, int seg_pitch, float* rbar, void* stream);
 /* x - x.mean(1, keepdim=True) over groups of rows (dana.py:125,141,267,272) -> pair. */
 int dana_center_rows(const float* in, int groups, int group_rows, int c, void* out_hi, void* out_lo, float* sums,
                      void* stream);
