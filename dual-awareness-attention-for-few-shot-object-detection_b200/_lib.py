@@ -54,6 +54,9 @@ SIGNATURES = {
     "dana_proposals_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "dana_proposals": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dana_detections_workspace_bytes": (c_int64, [c_int, c_int]),
+    "dana_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float,
+                                c_float, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dana_roi_align_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "dana_roi_align_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

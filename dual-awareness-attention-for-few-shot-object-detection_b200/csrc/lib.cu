@@ -60,6 +60,18 @@ int dana_proposals(const float* fg_scores, const float* deltas, const float* bas
                        workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int64_t dana_detections_workspace_bytes(int batch, int rois_per_image) {
+  if (batch <= 0 || rois_per_image <= 0) return 256;
+  return proposals_workspace_layout(batch, rois_per_image, 0).total;
+}
+
+int dana_detections(const float* rois, const float* cls_prob, const float* bbox_pred, const float* im_info, int batch,
+                    int rois_per_image, const float* stds, const float* means, float score_thresh, float nms_thresh,
+                    float* dets, int32_t* counts, void* workspace, int64_t workspace_bytes, void* stream) {
+  return detections_run(rois, cls_prob, bbox_pred, im_info, batch, rois_per_image, stds, means, score_thresh,
+                        nms_thresh, dets, counts, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int64_t dana_roi_align_workspace_bytes(int batch, int channels, int height, int width, int layout) {
   if (layout != 0) return 256;
   return 4LL * batch * channels * height * width + 256;

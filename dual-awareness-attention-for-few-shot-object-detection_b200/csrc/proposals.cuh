@@ -70,8 +70,8 @@ __global__ void proposals_decode_kernel(const float4* __restrict__ deltas, const
 __global__ void __launch_bounds__(256)
 proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __restrict__ order,
                            const unsigned long long* __restrict__ keys_sorted, int hwa, int n_pre, int post,
-                           float thresh, float* __restrict__ rois, float* __restrict__ roi_scores,
-                           int* __restrict__ roi_counts) {
+                           float thresh, float min_score, int det_format, float* __restrict__ rois,
+                           float* __restrict__ roi_scores, int* __restrict__ roi_counts) {
   extern __shared__ float4 s_keep_box[];            // [post]
   float* s_keep_area = reinterpret_cast<float*>(s_keep_box + post);   // [post]
   __shared__ float4 s_cand[64];
@@ -93,7 +93,14 @@ proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __re
       if (tid < valid) bx = boxes_all[seg + order[seg + base + tid]];
       s_cand[tid] = bx;
       s_cand_area[tid] = box_area_rn(bx);
-      s_dead[tid] = 0;
+      // candidates at or below the score floor never enter (detections: score > thresh, inference.py:130)
+      unsigned int dead0 = 0;
+      if (tid < valid && min_score > -INFINITY) {
+        const unsigned int ord = ~static_cast<unsigned int>(keys_sorted[seg + base + tid] & 0xFFFFFFFFull);
+        const unsigned int bits = (ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord;
+        dead0 = !(__uint_as_float(bits) > min_score);
+      }
+      s_dead[tid] = dead0;
     }
     __syncthreads();
     // (1) against the kept set: candidate = tid / 4, four threads stride the kept list
@@ -148,17 +155,23 @@ proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __re
       s_keep_box[pos] = bx;
       s_keep_area[pos] = s_cand_area[tid];
       float* row = rois + (static_cast<long long>(b) * post + pos) * 5;
-      row[0] = static_cast<float>(b);
-      row[1] = bx.x;
-      row[2] = bx.y;
-      row[3] = bx.z;
-      row[4] = bx.w;
-      if (roi_scores) {
-        // recover the score from the sorted key (low 32 bits hold ~orderable(score))
-        const unsigned int ord = ~static_cast<unsigned int>(keys_sorted[seg + base + tid] & 0xFFFFFFFFull);
-        const unsigned int bits = (ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord;
-        roi_scores[static_cast<long long>(b) * post + pos] = __uint_as_float(bits);
+      // recover the score from the sorted key (low 32 bits hold ~orderable(score))
+      const unsigned int ord = ~static_cast<unsigned int>(keys_sorted[seg + base + tid] & 0xFFFFFFFFull);
+      const unsigned int bits = (ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord;
+      if (det_format) {           // (x1, y1, x2, y2, score), utils.py:312-317
+        row[0] = bx.x;
+        row[1] = bx.y;
+        row[2] = bx.z;
+        row[3] = bx.w;
+        row[4] = __uint_as_float(bits);
+      } else {                    // (image, x1, y1, x2, y2), proposal_layer.py:186-188
+        row[0] = static_cast<float>(b);
+        row[1] = bx.x;
+        row[2] = bx.y;
+        row[3] = bx.z;
+        row[4] = bx.w;
       }
+      if (roi_scores) roi_scores[static_cast<long long>(b) * post + pos] = __uint_as_float(bits);
     }
     __syncthreads();
     if (tid == 0) s_nkept = nkept + __popcll(keep);
@@ -168,7 +181,7 @@ proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __re
   const int cnt = s_nkept;
   for (int k = cnt + tid; k < post; k += 256) {   // zero padding (proposal_layer.py:137,188-190)
     float* row = rois + (static_cast<long long>(b) * post + k) * 5;
-    row[0] = static_cast<float>(b);
+    row[0] = det_format ? 0.0f : static_cast<float>(b);
     row[1] = row[2] = row[3] = row[4] = 0.0f;
     if (roi_scores) roi_scores[static_cast<long long>(b) * post + k] = 0.0f;
   }
@@ -254,8 +267,84 @@ inline int proposals_run(const float* fg_scores, const float* deltas, const floa
     configured = keep_smem;
   }
   proposals_nms_write_kernel<<<batch, 256, keep_smem, stream>>>(boxes_all, order, keys_out, hwa, w.n_pre,
-                                                                post_nms_top_n, nms_thresh, rois, roi_scores,
-                                                                roi_counts);
+                                                                post_nms_top_n, nms_thresh, -INFINITY, 0, rois,
+                                                                roi_scores, roi_counts);
+  DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Detections after the forward pass (inference.py:108-142, utils.py:312-317):
+// de-normalise the head's deltas (x STDS + MEANS), decode against the rois, clip to the image, divide by the
+// image scale, keep fg score > score_thresh, sort by score, NMS(nms_thresh).  Same decode arithmetic, key
+// sort and greedy NMS kernel as the proposal layer.  dets [B][R][5] = (x1, y1, x2, y2, score), zero padded.
+// ---------------------------------------------------------------------------------------------
+__global__ void detections_decode_kernel(const float* __restrict__ rois, const float* __restrict__ cls_prob,
+                                         const float4* __restrict__ bbox_pred, const float* __restrict__ im_info,
+                                         int batch, int r, float4 stds, float4 means, float4* __restrict__ boxes_all,
+                                         unsigned long long* __restrict__ keys, int* __restrict__ idx_all) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= batch * r) return;
+  const int b = gid / r;
+  const float* roi = rois + static_cast<long long>(gid) * 5;
+  const float4 dn = bbox_pred[gid];
+  const float4 d = make_float4(__fadd_rn(__fmul_rn(dn.x, stds.x), means.x), __fadd_rn(__fmul_rn(dn.y, stds.y), means.y),
+                               __fadd_rn(__fmul_rn(dn.z, stds.z), means.z), __fadd_rn(__fmul_rn(dn.w, stds.w), means.w));
+  const float w = __fadd_rn(__fsub_rn(roi[3], roi[1]), 1.0f);
+  const float h = __fadd_rn(__fsub_rn(roi[4], roi[2]), 1.0f);
+  const float cx = __fadd_rn(roi[1], __fmul_rn(0.5f, w));
+  const float cy = __fadd_rn(roi[2], __fmul_rn(0.5f, h));
+  const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx);
+  const float pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
+  const float pw = __fmul_rn(expf(d.z), w);
+  const float ph = __fmul_rn(expf(d.w), h);
+  const float xmax = __fsub_rn(__ldg(im_info + b * 3 + 1), 1.0f);
+  const float ymax = __fsub_rn(__ldg(im_info + b * 3 + 0), 1.0f);
+  const float scale = __ldg(im_info + b * 3 + 2);
+  const float x1 = __fdiv_rn(fminf(fmaxf(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), 0.0f), xmax), scale);
+  const float y1 = __fdiv_rn(fminf(fmaxf(__fsub_rn(pcy, __fmul_rn(0.5f, ph)), 0.0f), ymax), scale);
+  const float x2 = __fdiv_rn(fminf(fmaxf(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 0.0f), xmax), scale);
+  const float y2 = __fdiv_rn(fminf(fmaxf(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 0.0f), ymax), scale);
+  boxes_all[gid] = make_float4(x1, y1, x2, y2);
+  idx_all[gid] = gid - b * r;
+  const unsigned int bits = __float_as_uint(cls_prob[static_cast<long long>(gid) * 2 + 1]);
+  const unsigned int ord = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  keys[gid] = (static_cast<unsigned long long>(b) << 32) | static_cast<unsigned long long>(~ord);
+}
+
+inline int detections_run(const float* rois, const float* cls_prob, const float* bbox_pred, const float* im_info,
+                          int batch, int r, const float* stds, const float* means, float score_thresh,
+                          float nms_thresh, float* dets, int32_t* counts, void* workspace, int64_t workspace_bytes,
+                          cudaStream_t stream) {
+  if (!rois || !cls_prob || !bbox_pred || !im_info || !dets || !workspace || !stds || !means) return DANA_EINVAL;
+  if (batch <= 0 || r <= 0) return DANA_EINVAL;
+  if (reinterpret_cast<uintptr_t>(bbox_pred) & 15) return DANA_EINVAL;
+  const ProposalsWorkspace w = proposals_workspace_layout(batch, r, 0);
+  if (workspace_bytes < w.total) return DANA_EINVAL;
+  const size_t keep_smem = static_cast<size_t>(r) * 20;
+  if (keep_smem > 200 * 1024) return DANA_ENOTSUP;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float4* boxes_all = reinterpret_cast<float4*>(ws + w.off_boxes_all);
+  int* idx_all = reinterpret_cast<int*>(ws + w.off_idx_all);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + w.off_keys);
+  unsigned long long* keys_out = reinterpret_cast<unsigned long long*>(ws + w.off_keys_out);
+  int* order = reinterpret_cast<int*>(ws + w.off_order);
+  const int tot = batch * r;
+  detections_decode_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(
+      rois, cls_prob, reinterpret_cast<const float4*>(bbox_pred), im_info, batch, r,
+      make_float4(stds[0], stds[1], stds[2], stds[3]), make_float4(means[0], means[1], means[2], means[3]), boxes_all,
+      keys, idx_all);
+  size_t cub_bytes = static_cast<size_t>(w.cub_bytes);
+  DANA_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys, keys_out, idx_all, order, tot, 0,
+                                                  proposals_key_bits(batch), stream));
+  static size_t configured = 0;
+  if (keep_smem > 40 * 1024 && keep_smem > configured) {
+    DANA_CUDA_CHECK(cudaFuncSetAttribute(proposals_nms_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(keep_smem)));
+    configured = keep_smem;
+  }
+  proposals_nms_write_kernel<<<batch, 256, keep_smem, stream>>>(boxes_all, order, keys_out, r, r, r, nms_thresh,
+                                                                score_thresh, 1, dets, nullptr, counts);
   DANA_LAUNCH_CHECK();
   return DANA_OK;
 }

@@ -234,14 +234,22 @@ class DanaEngine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
+    def encode_supports(self, support_ims):
+        """Support-feature cache: at test time the support crops of a class are fixed
+        (inference_loader.py:61-71), so their trunk features can be computed once and passed to forward() as
+        `support_feats` instead of re-running RCNN_base on them for every query (38 GF per 3-shot query).
+        support_ims [B, sets*K, 3, Hs, Ws] -> NHWC pair [B*sets*K, hs, ws, 1024]."""
+        return self.trunk(support_ims.reshape(-1, *support_ims.shape[2:]).float().contiguous())
+
+    @torch.no_grad()
     def forward(self, im_data, im_info, support_ims, pre_nms_top_n=6000, post_nms_top_n=300, nms_thresh=0.7,
-                pooling_size=7, want=None, teacher=None):
+                pooling_size=7, want=None, teacher=None, support_feats=None):
         """Eval forward.  im_data [B,3,H,W] fp32, im_info [B,3], support_ims [B, sets*K, 3, Hs, Ws].
         Returns (rois [B,post,5], cls_prob [sets*B*post, 2], bbox_pred [B*post, 4]); with `want` (a set of
         stage names) also a dict of intermediates exported in the reference's layouts."""
         dev, split, k = self.device, self.split, self.n_shot
         b = im_data.shape[0]
-        n_sup = support_ims.shape[1]
+        n_sup = support_ims.shape[1] if support_feats is None else support_feats.hi.shape[0] // b
         assert n_sup % k == 0, "support_ims must hold sets*n_shot crops per image"
         sets = n_sup // k
         want = want or ()
@@ -251,7 +259,7 @@ class DanaEngine:
         qh, qw = self._trunk_hw(im_data.shape[2], im_data.shape[3])
         corr = Pair.empty((b, qh, qw, 2048), dev, split)             # [base | dense]: removes the cat (:154)
         base = self.trunk(im_data.float().contiguous(), out=corr[..., :1024])
-        sup = self.trunk(support_ims.reshape(-1, *support_ims.shape[2:]).float().contiguous())
+        sup = support_feats if support_feats is not None else self.encode_supports(support_ims)
         maps, sh, sw, c = sup.hi.shape
         ns = sh * sw
         nq = qh * qw

@@ -64,6 +64,18 @@ int dana_proposals(const float* fg_scores, const float* deltas, const float* bas
                    void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Detections after the forward pass -- replaces the torch ops of inference.py:108-142 and NMS() of
+ * utils.py:312-317: box_deltas * STDS + MEANS (host arrays of 4 floats), bbox_transform_inv against the rois,
+ * clip_boxes, / im_info scale, fg score > score_thresh, sort by score, nms(nms_thresh).
+ * rois [B,R,5], cls_prob [B*R,2] (column 1 = fg), bbox_pred [B*R,4], im_info [B,3].
+ * dets [B,R,5] fp32 out: (x1, y1, x2, y2, score) in kept order, zero padded; counts [B] int32 out.
+ * ------------------------------------------------------------------------ */
+int64_t dana_detections_workspace_bytes(int batch, int rois_per_image);
+int dana_detections(const float* rois, const float* cls_prob, const float* bbox_pred, const float* im_info, int batch,
+                    int rois_per_image, const float* stds, const float* means, float score_thresh, float nms_thresh,
+                    float* dets, int32_t* counts, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * RoIAlign -- replaces model._C.roi_align_forward / roi_align_backward
  * (lib/model/csrc/vision.cpp:9-10, csrc/ROIAlign.h:11-45; sampling rules of
  * csrc/cpu/ROIAlign_cpu.cpp:18-219: no rounding, no half-pixel shift, adaptive

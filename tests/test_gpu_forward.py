@@ -144,3 +144,13 @@ def test_module_boundary_eval_forward():
     assert roi_set_match(out[0], torch.from_numpy(g["rois"])) >= 0.97
     with pytest.raises(NotImplementedError):
         net.train()(im.cuda(), info.cuda(), torch.zeros(1, 1, 5).cuda(), torch.zeros(1).cuda(), sup.cuda())
+
+
+def test_support_feature_cache_matches_full_forward(small_case):
+    """encode_supports() once + forward(support_feats=...) == forward on the raw crops (bitwise: same kernels)."""
+    p, im, info, sup, eng = small_case
+    a = eng.forward(im.cuda(), info.cuda(), sup.cuda())
+    cache = eng.encode_supports(sup.cuda())
+    b = eng.forward(im.cuda(), info.cuda(), None, support_feats=cache)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
