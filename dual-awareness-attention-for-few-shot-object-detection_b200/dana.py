@@ -58,7 +58,7 @@ class _RPNParams(nn.Module):
 class DAnARCNN(nn.Module):
     def __init__(self, classes, attention_type, rpn_reduce_dim=256, rcnn_reduce_dim=256, gamma=0.1,
                  semantic_enhance=False, num_layers=50, pretrained=False, num_way=2, num_shot=5, pos_encoding=True,
-                 precision="bf16x3"):
+                 precision="bf16x3", use_cuda_graph=False):
         super().__init__()
         if attention_type != "concat":
             raise NotImplementedError("only attention_type='concat' (the shipped configuration, utils.py:119) is built")
@@ -79,6 +79,9 @@ class DAnARCNN(nn.Module):
         # the reference ignores num_layers and always builds resnet50 (dana.py:337); 101 is the stated extension
         self.num_layers = num_layers if num_layers in RES_LAYERS else 50
         self.precision = precision
+        # capture the eval forward into a CUDA graph per input shape (falls back to eager launches if capture fails)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
         dim_in = 1024
 
         def lin(i, o, std=0.01):
@@ -188,9 +191,25 @@ class DAnARCNN(nn.Module):
                                       "backward; dana.py:100-108,166-215) is not built yet -- call .eval()")
         if cfg.POOLING_MODE != "align":
             raise NotImplementedError("POOLING_MODE %r is not built (shipped configs use 'align')" % cfg.POOLING_MODE)
-        rois, cls_prob, bbox_pred = self.engine().forward(
-            im_data, im_info.data, support_ims, pre_nms_top_n=cfg.TEST.RPN_PRE_NMS_TOP_N,
-            post_nms_top_n=cfg.TEST.RPN_POST_NMS_TOP_N, nms_thresh=cfg.TEST.RPN_NMS_THRESH,
-            pooling_size=cfg.POOLING_SIZE)
+        eng = self.engine()
+        kw = dict(pre_nms_top_n=cfg.TEST.RPN_PRE_NMS_TOP_N, post_nms_top_n=cfg.TEST.RPN_POST_NMS_TOP_N,
+                  nms_thresh=cfg.TEST.RPN_NMS_THRESH, pooling_size=cfg.POOLING_SIZE)
+        rois = None
+        if self.use_cuda_graph:
+            key = (id(eng), tuple(im_data.shape), tuple(support_ims.shape), tuple(sorted(kw.items())))
+            g = self._graphs.get(key)
+            if g is None:
+                try:
+                    from .engine import GraphedForward
+                    g = GraphedForward(eng, im_data, im_info.data, support_ims, **kw)
+                except Exception as e:  # noqa: BLE001  -- capture is an optimisation, never a requirement
+                    import warnings
+                    warnings.warn("dana_b200: CUDA graph capture failed (%r); running eagerly" % (e,))
+                    g = False
+                self._graphs[key] = g
+            if g:
+                rois, cls_prob, bbox_pred = g(im_data, im_info.data, support_ims)
+        if rois is None:
+            rois, cls_prob, bbox_pred = eng.forward(im_data, im_info.data, support_ims, **kw)
         # eval: losses are python 0 and rois_label is None (dana.py:173-179,216-220)
         return rois, cls_prob, bbox_pred, 0, 0, 0, 0, None
