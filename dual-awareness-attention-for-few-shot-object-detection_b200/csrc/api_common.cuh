@@ -42,10 +42,10 @@ inline EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// bf16 tensor map, 128-byte swizzle, zero fill out of bounds.
+// bf16 tensor map, 128-byte (or 64-byte) swizzle matching the box's inner extent, zero fill out of bounds.
 // dims[0] is the contiguous dimension; strides_bytes has rank-1 entries (dims 1..rank-1).
 inline int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box) {
+                           const uint64_t* strides_bytes, const uint32_t* box, bool swizzle64 = false) {
   EncodeTiledFn fn = get_encode_tiled();
   if (fn == nullptr) return DANA_ECUDA;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -57,7 +57,8 @@ inline int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint
   }
   for (int i = 0; i < rank - 1; ++i) s[i] = strides_bytes[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), d, s, b,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     t_last_cuda_error = 100000 + static_cast<int>(r);

@@ -25,7 +25,7 @@ struct ConvGemmParams {
   int bw, bh, bn;
   int lbw, lbh;   // log2(bw), log2(bh): the tile extents are powers of two
   int taps_r, taps_s, pad_y, pad_x;
-  int c_blocks;   // ceil(C_in / 64)
+  int c_blocks;   // ceil(C_in / K-tile)
   int c_in;       // K extent per tap
   int n_out;      // output channels
   int out_w, out_h, out_n;
@@ -52,11 +52,14 @@ struct ConvGemmParams {
 
 constexpr int kGemmThreads = 320;
 constexpr int kTileM = 128;
-constexpr int kTileK = 64;
-constexpr int kATileBytes = kTileM * kTileK * 2;  // 16 KB per plane
-
-template <int BLOCK_N, int NSPLIT>
+// KT = K extent of one pipeline stage: 64 bf16 (128-byte swizzle rows) by default.  The split mode at BLOCK_N = 256
+// has two planes per operand, i.e. only two 96 KB stages; its long-K launches use KT = 32 (64-byte swizzle rows,
+// four 48 KB stages), which covers the TMA latency better (measured: RPN 3x3 conv 0.406 -> 0.357 ms).  Narrow tiles
+// already have >= 3 stages and lose with the halved boxes (twice the TMA / barrier traffic), so they stay at 64.
+template <int BLOCK_N, int NSPLIT, int KT = 64>
 struct ConvGemmCfg {
+  static constexpr int kTileK = KT;
+  static constexpr int kATileBytes = kTileM * kTileK * 2;   // per plane
   static constexpr int kBTileBytes = BLOCK_N * kTileK * 2;
   static constexpr int kStageBytes = NSPLIT * (kATileBytes + kBTileBytes);
   static constexpr int kBudget = 200 * 1024;
@@ -102,12 +105,14 @@ struct SkRange {
 // (dana.py:142-143,273-274): N-tile t is shot t's segment of sm_ns keys (sm_ns <= BLOCK_N), the epilogue takes
 // max / sum over the segment straight from TMEM and writes the normalised probabilities as a bf16 pair at
 // column t*sm_pitch (pad columns zeroed); the fp32 logits never leave the SM.
-template <int BLOCK_N, int NSPLIT, int EPI, int CM>
+template <int BLOCK_N, int NSPLIT, int EPI, int CM, int KT = 64>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr bool FAST = (EPI == 1);
   constexpr bool SOFTMAX = (EPI == 2);
-  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT>;
+  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT>;
+  constexpr int kTileK = Cfg::kTileK;
+  constexpr int kATileBytes = Cfg::kATileBytes;
   constexpr int kStages = Cfg::kStages;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(kStages >= 2, "pipeline too shallow");
@@ -256,12 +261,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint32_t b_hi = a_hi + NSPLIT * kATileBytes;
 #pragma unroll
           for (int k = 0; k < kTileK / 16; ++k) {
-            const uint32_t koff = k * 32;  // 16 bf16 = 32 B inside the 128-B swizzle row
-            const uint64_t da = umma_desc_sw128(a_hi + koff);
-            const uint64_t db = umma_desc_sw128(b_hi + koff);
+            const uint32_t koff = k * 32;  // 16 bf16 = 32 B inside the swizzled row
+            const uint64_t da = (kTileK == 64) ? umma_desc_sw128(a_hi + koff) : umma_desc_sw64(a_hi + koff);
+            const uint64_t db = (kTileK == 64) ? umma_desc_sw128(b_hi + koff) : umma_desc_sw64(b_hi + koff);
             if (NSPLIT == 2) {
-              const uint64_t dal = umma_desc_sw128(a_hi + kATileBytes + koff);
-              const uint64_t dbl = umma_desc_sw128(b_hi + Cfg::kBTileBytes + koff);
+              const uint64_t dal = (kTileK == 64) ? umma_desc_sw128(a_hi + kATileBytes + koff)
+                                                  : umma_desc_sw64(a_hi + kATileBytes + koff);
+              const uint64_t dbl = (kTileK == 64) ? umma_desc_sw128(b_hi + Cfg::kBTileBytes + koff)
+                                                  : umma_desc_sw64(b_hi + Cfg::kBTileBytes + koff);
               // small cross terms first, leading term last
               umma_bf16(d_addr, dal, db, idesc, ((kb - kb_lo) | k) != 0);
               umma_bf16(d_addr, da, dbl, idesc, 1);

@@ -32,17 +32,17 @@ inline TileChoice choose_tile(int w, int h, int n, bool batched_b) {
   return best;
 }
 
-template <int BLOCK_N, int NSPLIT, int EPI, int CM>
+template <int BLOCK_N, int NSPLIT, int EPI, int CM, int KT = 64>
 inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT>;
+  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT>;
   static bool configured = false;
   if (!configured) {
-    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM>,
+    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM, KT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   if (CM == 1) {
-    conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+    conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM, KT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -57,7 +57,7 @@ inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t st
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DANA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM>, p));
+    DANA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM, KT>, p));
   }
   DANA_LAUNCH_CHECK();
   return DANA_OK;
@@ -80,8 +80,12 @@ inline bool fast_epilogue_ok(const ConvGemmParams& p, int nsplit) {
   return true;
 }
 
-template <int BLOCK_N, int NSPLIT, int CM>
+template <int BLOCK_N, int NSPLIT, int CM, int KT = 64>
 inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+  if constexpr (KT == 32) {   // only the plain-epilogue, non-cluster variants are instantiated at KT = 32
+    if (fast_epilogue_ok(p, NSPLIT)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, 1, 1, 32>(p, grid, stream);
+    return launch_conv_gemm_v<BLOCK_N, NSPLIT, 0, 1, 32>(p, grid, stream);
+  }
   if (p.sm_ns > 0) {
     if constexpr (CM == 1 && BLOCK_N != 128) return launch_conv_gemm_v<BLOCK_N, NSPLIT, 2, 1>(p, grid, stream);
     return DANA_ENOTSUP;
@@ -136,7 +140,6 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   p.pad_y = a->pad_y;
   p.pad_x = a->pad_x;
   p.c_in = static_cast<int>(a->a_c);
-  p.c_blocks = static_cast<int>((a->a_c + 63) / 64);
   p.n_out = a->n_out;
   p.out_w = a->out_w;
   p.out_h = a->out_h;
@@ -188,19 +191,31 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     if (env != nullptr && atoi(env) == 2 && block_n == 256 && !batched && k_total_ >= 256 && sp_tiles >= 2) cm = 2;
   }
 
-  // tensor maps
+  // K extent of a pipeline stage (see ConvGemmCfg): 32 for the long-K / wide-N launches of the split mode
   const int nsplit = (a->a_lo != nullptr) ? 2 : 1;
+  int ktile = 64;
+  {
+    const long long k_total_ = static_cast<long long>(taps) * a->a_c;
+    if (nsplit == 2 && block_n == 256 && cm == 1 && !softmax && (a->a_c % 32) == 0 && k_total_ >= 256 &&
+        (a->n_out >= 512 || k_total_ >= 2048))
+      ktile = 32;
+    const char* env = getenv("DANA_KTILE");
+    if (env != nullptr && nsplit == 2 && block_n == 256 && cm == 1 && !softmax && (a->a_c % 32) == 0)
+      ktile = atoi(env) == 32 ? 32 : 64;
+  }
+  p.c_blocks = static_cast<int>((a->a_c + ktile - 1) / ktile);
+  // tensor maps
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(a->a_c), static_cast<uint64_t>(a->a_w),
                               static_cast<uint64_t>(a->a_h), static_cast<uint64_t>(a->a_n)};
     const uint64_t str[3] = {static_cast<uint64_t>(a->a_sx) * 2, static_cast<uint64_t>(a->a_sy) * 2,
                              static_cast<uint64_t>(a->a_sn) * 2};
-    const uint32_t box[4] = {64, static_cast<uint32_t>(tc.bw), static_cast<uint32_t>(tc.bh),
+    const uint32_t box[4] = {static_cast<uint32_t>(ktile), static_cast<uint32_t>(tc.bw), static_cast<uint32_t>(tc.bh),
                              static_cast<uint32_t>(tc.bn)};
-    int rc = encode_bf16_map(&p.tm_a_hi, a->a_hi, 4, dims, str, box);
+    int rc = encode_bf16_map(&p.tm_a_hi, a->a_hi, 4, dims, str, box, ktile == 32);
     if (rc != DANA_OK) return rc;
     if (nsplit == 2) {
-      rc = encode_bf16_map(&p.tm_a_lo, a->a_lo, 4, dims, str, box);
+      rc = encode_bf16_map(&p.tm_a_lo, a->a_lo, 4, dims, str, box, ktile == 32);
       if (rc != DANA_OK) return rc;
     }
   }
@@ -211,11 +226,11 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     const uint64_t bs = batched ? static_cast<uint64_t>(a->b_batch_stride)
                                 : static_cast<uint64_t>(a->b_pitch) * static_cast<uint64_t>(a->n_out);
     const uint64_t str[2] = {static_cast<uint64_t>(a->b_pitch) * 2, ((bs * 2 + 15) / 16) * 16};
-    const uint32_t box[3] = {64, static_cast<uint32_t>(block_n / cm), 1};
-    int rc = encode_bf16_map(&p.tm_b_hi, a->b_hi, 3, dims, str, box);
+    const uint32_t box[3] = {static_cast<uint32_t>(ktile), static_cast<uint32_t>(block_n / cm), 1};
+    int rc = encode_bf16_map(&p.tm_b_hi, a->b_hi, 3, dims, str, box, ktile == 32);
     if (rc != DANA_OK) return rc;
     if (nsplit == 2) {
-      rc = encode_bf16_map(&p.tm_b_lo, a->b_lo, 3, dims, str, box);
+      rc = encode_bf16_map(&p.tm_b_lo, a->b_lo, 3, dims, str, box, ktile == 32);
       if (rc != DANA_OK) return rc;
     }
   }
@@ -235,7 +250,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     const bool allowed = (env == nullptr) || atoi(env) != 0;
     // cost model (microseconds): a k-block costs ~0.8 us in x3 / ~0.27 us in bf16 at BLOCK_N = 256; stream-K pays
     // ~4 us for publishing / collecting partial tiles
-    const double kb_us = (nsplit == 2 ? 0.8 : 0.27) * block_n / 256.0;
+    const double kb_us = (nsplit == 2 ? 0.8 : 0.27) * block_n / 256.0 * ktile / 64.0;
     const double plain_us = static_cast<double>(rounds * num_kb) * kb_us;
     const double sk_us = static_cast<double>((total_it + sms - 1) / sms) * kb_us + 4.0;
     if (allowed && !softmax && cm == 1 && a->workspace != nullptr && a->workspace_bytes >= need && a->sk_epoch != 0 && eff < 0.9 &&
@@ -253,6 +268,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     if (block_n == 128) return launch_conv_gemm<128, 1, 1>(p, grid, stream);
     return launch_conv_gemm<64, 1, 1>(p, grid, stream);
   }
+  if (block_n == 256 && ktile == 32) return launch_conv_gemm<256, 2, 1, 32>(p, grid, stream);
   if (block_n == 256) return cm == 2 ? launch_conv_gemm<256, 2, 2>(p, grid, stream) : launch_conv_gemm<256, 2, 1>(p, grid, stream);
   if (block_n == 128) return launch_conv_gemm<128, 2, 1>(p, grid, stream);
   return launch_conv_gemm<64, 2, 1>(p, grid, stream);

@@ -188,6 +188,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t addr) {
   d |= static_cast<uint64_t>(2) << 61;                  // SWIZZLE_128B
   return d;
 }
+// Same for a K-major tile with 64-byte rows (32 bf16) and 64-byte swizzle: 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;           // SBO = 8 rows * 64 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                  // SWIZZLE_64B
+  return d;
+}
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |

@@ -160,7 +160,7 @@ def test_proposals_full_size_vs_oracle(ops, b, fh, fw, pre, post):
 # ------------------------------------------------------------------------------------ tensor-core GEMM / conv
 @pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("m,k,n", [(128, 64, 64), (300, 192, 72), (2394, 1024, 256), (1000, 1200, 1024), (77, 3136, 1024),
-                                   (1200, 2048, 4), (14700, 147, 1024)])
+                                   (1200, 2048, 4), (14700, 147, 1024), (300, 96, 512), (500, 416, 640)])
 def test_linear(ops, split, m, k, n):
     torch.manual_seed(m + k + n)
     kp = (k + 7) // 8 * 8                                                   # row pitch (TMA wants 16-byte strides)
