@@ -206,14 +206,26 @@ roi_align_fwd_kernel(const float* __restrict__ feat /*NHWC*/, const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pipeline RoIAlign (NHWC fp32 map -> [R][7][7][C]): same separable math as above, tuned for issue rate.
-//   * compact weight tables: per bin only the <= 16 taps that are non-zero, plus their first index
-//   * 8 channels per thread (two 16-byte loads per tap), pointers advanced by increments
-//   * optional fused outputs: fp32, bf16 hi/lo pair, and pair of (value + positional encoding[bin])
-//     (the query side of the head attention, dana.py:259) -- removes a 470 MB round trip per step.
-// grid (num_rois, C / (8 * blockDim.x)), block = min(128, C / 8) threads (>= 64).
+// 7x7 RoIAlign, the kernel of the pipeline and of the reference-layout operator (NHWC fp32 map in).
+//
+// Same separable math as above; organised so that the kernel is bound by the output write, not by the
+// gather.  The gather cost of an RoI is its taps, (sum_ph ny) x (sum_pw nx) 16-byte loads per 4 channels in
+// the plain per-bin form -- large RoIs dominate, and at one thread-private dependent load per tap the old
+// kernel was latency-bound (20 % of HBM peak).  Here:
+//   * grid (RoI, 512-channel slab), 128 threads x 4 consecutive channels: a warp load is one 512-byte run;
+//   * the x pass of a map row is fully unrolled over (7 bins x T taps), T = the RoI's widest bin rounded up
+//     to a compiled size, zero weights in the padding taps (the tap window of a narrower bin is shifted left
+//     so that every address stays inside the row): 7*T independent 16-byte loads in flight per thread;
+//   * the y pass ROLLS over the window rows: a row that two adjacent bins share is read once and added to
+//     both (two live accumulator sets) whenever no row is shared by three bins -- which holds for every RoI
+//     taller than ~14 feature rows, i.e. the expensive ones; small RoIs take the per-bin order;
+//   * compact per-bin weight tables (<= 16 taps) built once per CTA in the reference's expression order;
+//   * fused outputs: fp32, bf16 hi/lo pair, pair of (value + positional encoding[bin]) (dana.py:259), or
+//     (MODE 1) the reference's [R][C][7][7] layout staged through shared memory and written as one
+//     contiguous 100 KB run per CTA.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRoiTaps = 16;
+constexpr int kRoi7Threads = 128;
 
 __device__ __forceinline__ void build_axis_compact(float* w /*[kRoiTaps]*/, int* lo_out, int* n_out, int p, int size,
                                                    float start, float bin, int grid) {
@@ -234,91 +246,236 @@ __device__ __forceinline__ void build_axis_compact(float* w /*[kRoiTaps]*/, int*
   *n_out = lo < 0 ? 0 : min(hi - lo + 1, kRoiTaps);
 }
 
-__device__ __forceinline__ void store8_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, const float (&f)[8]) {
-  uint32_t ph[4], pl[4];
+struct Roi7Tables {
+  float wy[7][kRoiTaps];
+  float wx[7][kRoiTaps];
+  int ylo[7], ny[7], xlo[7], nx[7];
+  RoiGeom g;
+};
+
+__device__ __forceinline__ void store4_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, const float (&f)[4]) {
+  uint32_t ph[2], pl[2];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int e = 0; e < 2; ++e) {
     const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
     ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
     const __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * e] - __uint_as_float(ph[e] << 16),
                                                     f[2 * e + 1] - __uint_as_float(ph[e] & 0xFFFF0000u));
     pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
   }
-  *reinterpret_cast<uint4*>(hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-  if (lo != nullptr) *reinterpret_cast<uint4*>(lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2(ph[0], ph[1]);
+  if (lo != nullptr) *reinterpret_cast<uint2*>(lo + off) = make_uint2(pl[0], pl[1]);
 }
 
-__global__ void __launch_bounds__(128)
-roi_align_head_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restrict__ rois, int channels, int height,
-                      int width, float spatial_scale, int sampling_ratio, float* __restrict__ out,
-                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                      const float* __restrict__ pe, __nv_bfloat16* __restrict__ qpe_hi,
-                      __nv_bfloat16* __restrict__ qpe_lo) {
-  __shared__ float s_wy[7][kRoiTaps], s_wx[7][kRoiTaps];
-  __shared__ int s_ylo[7], s_ny[7], s_xlo[7], s_nx[7];
-  __shared__ RoiGeom s_g;
-  const int r = blockIdx.x, tid = threadIdx.x;
-  if (tid == 0) s_g = roi_geometry(rois + static_cast<long long>(r) * 5, spatial_scale, 7, 7, sampling_ratio);
-  __syncthreads();
-  const RoiGeom g = s_g;
-  if (tid < 7) build_axis_compact(s_wy[tid], &s_ylo[tid], &s_ny[tid], tid, height, g.start_h, g.bin_h, g.grid_h);
-  if (tid >= 32 && tid < 39)
-    build_axis_compact(s_wx[tid - 32], &s_xlo[tid - 32], &s_nx[tid - 32], tid - 32, width, g.start_w, g.bin_w, g.grid_w);
-  __syncthreads();
-  const int c0 = (blockIdx.y * blockDim.x + tid) * 8;
-  if (c0 >= channels) return;
-  const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
-  const float* fbase = feat + static_cast<long long>(g.batch_ind) * height * width * channels + c0;
-  const long long row_pitch = static_cast<long long>(width) * channels;
-  for (int ph = 0; ph < 7; ++ph) {
-    float acc[7][8];
+struct Roi7Out {
+  float* out;                 // MODE 0: [R][49][C] fp32 (optional); MODE 1: [R][C][49] fp32
+  __nv_bfloat16 *hi, *lo;     // MODE 0: bf16 pair (optional)
+  const float* pe;            // [49][C]
+  __nv_bfloat16 *qhi, *qlo;   // MODE 0: pair of value + pe[bin] (optional)
+};
+
+// x pass of one map row for this thread's 4 channels: rs[pw] = sum_k wx[pw][k] * F[row][xlo[pw] + k]
+template <int T, int CH>
+__device__ __forceinline__ void roi7_row_pass(const float* __restrict__ rowp, int channels, const Roi7Tables& s,
+                                              float4 (&rs)[7]) {
+  const int cs = CH ? CH : channels;
 #pragma unroll
-    for (int pw = 0; pw < 7; ++pw)
+  for (int pw = 0; pw < 7; ++pw) {
+    const float* px = rowp + static_cast<long long>(s.xlo[pw]) * cs;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (T > 0) {
+      float4 f[T];
 #pragma unroll
-      for (int v = 0; v < 8; ++v) acc[pw][v] = 0.0f;
-    const int ny = s_ny[ph];
-    const float* rowp = fbase + static_cast<long long>(s_ylo[ph]) * row_pitch;
-    for (int ky = 0; ky < ny; ++ky, rowp += row_pitch) {
-      const float wy = s_wy[ph][ky];
-      if (wy == 0.0f) continue;
+      for (int k = 0; k < T; ++k) f[k] = __ldg(reinterpret_cast<const float4*>(px + static_cast<long long>(k) * cs));
 #pragma unroll
-      for (int pw = 0; pw < 7; ++pw) {
-        const int nx = s_nx[pw];
-        const float* px = rowp + static_cast<long long>(s_xlo[pw]) * channels;
-        float rs[8];
-#pragma unroll
-        for (int v = 0; v < 8; ++v) rs[v] = 0.0f;
-        for (int kx = 0; kx < nx; ++kx, px += channels) {
-          const float wx = s_wx[pw][kx];
-          const float4 f0 = __ldg(reinterpret_cast<const float4*>(px));
-          const float4 f1 = __ldg(reinterpret_cast<const float4*>(px) + 1);
-          rs[0] += wx * f0.x; rs[1] += wx * f0.y; rs[2] += wx * f0.z; rs[3] += wx * f0.w;
-          rs[4] += wx * f1.x; rs[5] += wx * f1.y; rs[6] += wx * f1.z; rs[7] += wx * f1.w;
-        }
-#pragma unroll
-        for (int v = 0; v < 8; ++v) acc[pw][v] += wy * rs[v];
+      for (int k = 0; k < T; ++k) {
+        const float w = s.wx[pw][k];
+        a.x += w * f[k].x; a.y += w * f[k].y; a.z += w * f[k].z; a.w += w * f[k].w;
+      }
+    } else {
+      const int n = s.nx[pw];
+      for (int k = 0; k < n; ++k, px += cs) {
+        const float w = s.wx[pw][k];
+        const float4 f = __ldg(reinterpret_cast<const float4*>(px));
+        a.x += w * f.x; a.y += w * f.y; a.z += w * f.z; a.w += w * f.w;
       }
     }
+    rs[pw] = a;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, float inv_count, const float4 (&acc)[7],
+                                          const Roi7Out& o, float* s_stage, int tid) {
 #pragma unroll
-    for (int pw = 0; pw < 7; ++pw) {
-      float o[8];
+  for (int pw = 0; pw < 7; ++pw) {
+    const float v[4] = {acc[pw].x * inv_count, acc[pw].y * inv_count, acc[pw].z * inv_count, acc[pw].w * inv_count};
+    const int bin = ph * 7 + pw;
+    if constexpr (MODE == 1) {
 #pragma unroll
-      for (int v = 0; v < 8; ++v) o[v] = acc[pw][v] * inv_count;
-      const int bin = ph * 7 + pw;
+      for (int e = 0; e < 4; ++e) s_stage[(tid * 4 + e) * 49 + bin] = v[e];
+    } else {
       const long long off = (static_cast<long long>(r) * 49 + bin) * channels + c0;
-      if (out != nullptr) {
-        reinterpret_cast<float4*>(out + off)[0] = make_float4(o[0], o[1], o[2], o[3]);
-        reinterpret_cast<float4*>(out + off)[1] = make_float4(o[4], o[5], o[6], o[7]);
-      }
-      if (out_hi != nullptr) store8_pair(out_hi, out_lo, off, o);
-      if (qpe_hi != nullptr) {
-        const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(bin) * channels + c0));
-        const float4 p1 = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(bin) * channels + c0) + 1);
-        float qv[8] = {o[0] + p0.x, o[1] + p0.y, o[2] + p0.z, o[3] + p0.w, o[4] + p1.x, o[5] + p1.y, o[6] + p1.z, o[7] + p1.w};
-        store8_pair(qpe_hi, qpe_lo, off, qv);
+      if (o.out != nullptr) *reinterpret_cast<float4*>(o.out + off) = make_float4(v[0], v[1], v[2], v[3]);
+      if (o.hi != nullptr) store4_pair(o.hi, o.lo, off, v);
+      if (o.qhi != nullptr) {
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(o.pe + static_cast<long long>(bin) * channels + c0));
+        const float q[4] = {v[0] + p4.x, v[1] + p4.y, v[2] + p4.z, v[3] + p4.w};
+        store4_pair(o.qhi, o.qlo, off, q);
       }
     }
   }
+}
+
+// the y loop: window rows in rolling (two live bins) or per-bin order; see the header comment
+template <int T, int CH, int MODE>
+__device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int channels, int width, const Roi7Tables& s,
+                                            bool rolling, int r, int c0, float inv_count, const Roi7Out& o,
+                                            float* s_stage, int tid) {
+  const long long row_pitch = static_cast<long long>(width) * (CH ? CH : channels);
+  float4 acc_a[7], acc_b[7];
+#pragma unroll
+  for (int pw = 0; pw < 7; ++pw) acc_a[pw] = acc_b[pw] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = 0;
+  int y = s.ylo[0];
+  while (cur < 7) {
+    const int ylo_c = s.ylo[cur], ny_c = s.ny[cur];
+    if (y < ylo_c) y = ylo_c;
+    if (y >= ylo_c + ny_c) {       // bin `cur` is complete (or empty): write it, promote the next bin
+      roi7_emit<MODE>(r, cur, c0, channels, inv_count, acc_a, o, s_stage, tid);
+#pragma unroll
+      for (int pw = 0; pw < 7; ++pw) {
+        acc_a[pw] = acc_b[pw];
+        acc_b[pw] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ++cur;
+      if (!rolling && cur < 7) y = s.ylo[cur];
+      continue;
+    }
+    const float wa = s.wy[cur][y - ylo_c];
+    float wb = 0.0f;
+    if (rolling && cur < 6) {
+      const int d = y - s.ylo[cur + 1];
+      if (d >= 0 && d < s.ny[cur + 1]) wb = s.wy[cur + 1][d];
+    }
+    if (wa != 0.0f || wb != 0.0f) {
+      float4 rs[7];
+      roi7_row_pass<T, CH>(fbase + static_cast<long long>(y) * row_pitch, channels, s, rs);
+#pragma unroll
+      for (int pw = 0; pw < 7; ++pw) {
+        acc_a[pw].x += wa * rs[pw].x; acc_a[pw].y += wa * rs[pw].y; acc_a[pw].z += wa * rs[pw].z; acc_a[pw].w += wa * rs[pw].w;
+        acc_b[pw].x += wb * rs[pw].x; acc_b[pw].y += wb * rs[pw].y; acc_b[pw].z += wb * rs[pw].z; acc_b[pw].w += wb * rs[pw].w;
+      }
+    }
+    ++y;
+  }
+}
+
+// grid (num_rois, ceil(C / 512)), block 128.  MODE 0: NHWC outputs; MODE 1: [R][C][49] via shared memory.
+template <int MODE, int CH>
+__global__ void __launch_bounds__(kRoi7Threads, MODE == 1 ? 2 : 4)
+roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restrict__ rois, int channels, int height,
+                  int width, float spatial_scale, int sampling_ratio, Roi7Out o) {
+  extern __shared__ float s_stage[];   // MODE 1: [512][49]
+  __shared__ Roi7Tables s;
+  __shared__ int s_t, s_rolling;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) s.g = roi_geometry(rois + static_cast<long long>(r) * 5, spatial_scale, 7, 7, sampling_ratio);
+  __syncthreads();
+  const RoiGeom g = s.g;
+  if (tid < 7) build_axis_compact(s.wy[tid], &s.ylo[tid], &s.ny[tid], tid, height, g.start_h, g.bin_h, g.grid_h);
+  if (tid >= 32 && tid < 39)
+    build_axis_compact(s.wx[tid - 32], &s.xlo[tid - 32], &s.nx[tid - 32], tid - 32, width, g.start_w, g.bin_w, g.grid_w);
+  __syncthreads();
+  // compiled tap count T >= widest bin; 0 = dynamic loops (map narrower than the compiled size)
+  int maxn = 0;
+#pragma unroll
+  for (int pw = 0; pw < 7; ++pw) maxn = max(maxn, s.nx[pw]);
+  int t = maxn <= 2 ? 2 : maxn <= 3 ? 3 : maxn <= 4 ? 4 : maxn <= 6 ? 6 : maxn <= 8 ? 8 : maxn <= 12 ? 12 : 16;
+  if (t > width) t = 0;
+  if (t > 0 && tid >= 32 && tid < 39) {
+    // shift this bin's tap window left so that xlo + t <= width: padding taps read valid pixels with zero weight
+    const int pw = tid - 32;
+    const int lo = s.xlo[pw];
+    const int base = min(lo, width - t);
+    const int sh = lo - base;
+    if (sh > 0) {
+      for (int k = kRoiTaps - 1; k >= 0; --k) s.wx[pw][k] = (k >= sh) ? s.wx[pw][k - sh] : 0.0f;
+      s.xlo[pw] = base;
+    }
+  }
+  if (tid == 0) {
+    // rolling order is valid when no map row feeds three bins: first row of bin p+2 lies past the last row of bin p
+    bool ok = true;
+    for (int p = 0; p + 2 < 7; ++p)
+      if (s.ny[p] > 0 && s.ny[p + 2] > 0 && s.ylo[p + 2] < s.ylo[p] + s.ny[p]) ok = false;
+    // bins must be ordered (empty bins in the middle of an RoI cannot occur: validity is monotone at each border)
+    s_rolling = ok ? 1 : 0;
+    s_t = t;
+  }
+  __syncthreads();
+  const int c0 = (blockIdx.y * kRoi7Threads + tid) * 4;
+  const bool c_ok = c0 < channels;
+  const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
+  const float* fbase = feat + static_cast<long long>(g.batch_ind) * height * width * channels + (c_ok ? c0 : 0);
+  const bool rolling = s_rolling != 0;
+  if (c_ok || MODE == 1) {
+    switch (s_t) {
+      case 2: roi7_gather<2, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+      case 3: roi7_gather<3, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+      case 4: roi7_gather<4, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+      case 6: roi7_gather<6, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+      case 8: roi7_gather<8, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+      case 12: roi7_gather<12, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+      case 16: roi7_gather<16, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+      default: roi7_gather<0, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+    }
+  }
+  if constexpr (MODE == 1) {
+    __syncthreads();
+    // [R][C][49]: this CTA's channels are one contiguous run
+    const int cbase = blockIdx.y * kRoi7Threads * 4;
+    const int nch = min(kRoi7Threads * 4, channels - cbase);
+    float* dst = o.out + (static_cast<long long>(r) * channels + cbase) * 49;
+    const int total = nch * 49;
+    if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      for (int i = tid; i < total / 4; i += kRoi7Threads)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_stage)[i];
+    } else {
+      for (int i = tid; i < total; i += kRoi7Threads) dst[i] = s_stage[i];
+    }
+  }
+}
+
+template <int MODE>
+inline int roi_align7_launch(const float* feat_nhwc, const float* rois, int num_rois, int channels, int height, int width,
+                             float spatial_scale, int sampling_ratio, const Roi7Out& o, cudaStream_t stream) {
+  const int groups = (channels + kRoi7Threads * 4 - 1) / (kRoi7Threads * 4);
+  const size_t smem = MODE == 1 ? sizeof(float) * kRoi7Threads * 4 * 49 : 0;
+  if (MODE == 1) {
+    static bool configured = false;
+    if (!configured) {
+      DANA_CUDA_CHECK(cudaFuncSetAttribute(roi_align7_kernel<MODE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+      DANA_CUDA_CHECK(cudaFuncSetAttribute(roi_align7_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+      configured = true;
+    }
+  }
+  if (channels == 1024) {
+    roi_align7_kernel<MODE, 1024><<<dim3(num_rois, groups), kRoi7Threads, smem, stream>>>(
+        feat_nhwc, rois, channels, height, width, spatial_scale, sampling_ratio, o);
+  } else {
+    roi_align7_kernel<MODE, 0><<<dim3(num_rois, groups), kRoi7Threads, smem, stream>>>(
+        feat_nhwc, rois, channels, height, width, spatial_scale, sampling_ratio, o);
+  }
+  DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
+// adaptive sampling: a bin of more than 14 feature pixels does not fit the 16-tap tables
+inline bool roi_align7_supported(int channels, int height, int width, int sampling_ratio) {
+  return channels % 4 == 0 && (sampling_ratio > 0 ? sampling_ratio <= 7 : (height <= 7 * 14 && width <= 7 * 14));
 }
 
 inline int roi_align_head_run(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels,
@@ -328,17 +485,10 @@ inline int roi_align_head_run(const float* feat_nhwc, const float* rois, int num
   if (!feat_nhwc || !rois || num_rois < 0 || batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return DANA_EINVAL;
   if (!out && !out_hi && !qpe_hi) return DANA_EINVAL;
   if (qpe_hi && !pe) return DANA_EINVAL;
-  if (channels % 8 != 0) return DANA_ENOTSUP;
-  // compact tables hold 16 taps per bin: bins of at most 14 feature pixels
-  if (sampling_ratio <= 0 && (height > 7 * 14 || width > 7 * 14)) return DANA_ENOTSUP;
-  int threads = channels / 8 >= 128 ? 128 : ((channels / 8 + 31) / 32) * 32;
-  if (threads < 64) threads = 64;
-  const int groups = (channels / 8 + threads - 1) / threads;
-  roi_align_head_kernel<<<dim3(num_rois, groups), threads, 0, stream>>>(
-      feat_nhwc, rois, channels, height, width, spatial_scale, sampling_ratio, out, static_cast<__nv_bfloat16*>(out_hi),
-      static_cast<__nv_bfloat16*>(out_lo), pe, static_cast<__nv_bfloat16*>(qpe_hi), static_cast<__nv_bfloat16*>(qpe_lo));
-  DANA_LAUNCH_CHECK();
-  return DANA_OK;
+  if (!roi_align7_supported(channels, height, width, sampling_ratio)) return DANA_ENOTSUP;
+  Roi7Out o{out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), pe,
+            static_cast<__nv_bfloat16*>(qpe_hi), static_cast<__nv_bfloat16*>(qpe_lo)};
+  return roi_align7_launch<0>(feat_nhwc, rois, num_rois, channels, height, width, spatial_scale, sampling_ratio, o, stream);
 }
 
 // NCHW -> NHWC transpose of one feature map batch: [B][C][HW] -> [B][HW][C], 32x32 tiles
@@ -409,6 +559,10 @@ inline int roi_align_forward_run(const float* input, const float* rois, int num_
     const int hw = height * width;
     nchw_to_nhwc_kernel<<<dim3((hw + 31) / 32, (channels + 31) / 32, batch), dim3(32, 8), 0, stream>>>(input, nhwc,
                                                                                                       channels, hw);
+    if (pooled_h == 7 && pooled_w == 7 && roi_align7_supported(channels, height, width, sampling_ratio)) {
+      Roi7Out o{out, nullptr, nullptr, nullptr, nullptr, nullptr};
+      return roi_align7_launch<1>(nhwc, rois, num_rois, channels, height, width, spatial_scale, sampling_ratio, o, stream);
+    }
     const int threads = 128;
     const size_t smem = table_bytes + sizeof(float) * threads * pooled_h * pooled_w;
     static size_t configured = 0;
@@ -421,6 +575,10 @@ inline int roi_align_forward_run(const float* input, const float* rois, int num_
         nhwc, rois, channels, height, width, pooled_h, pooled_w, spatial_scale, sampling_ratio, out, nullptr, nullptr);
   } else if (layout == 1) {
     if (!out && !out_hi) return DANA_EINVAL;
+    if (pooled_h == 7 && pooled_w == 7 && roi_align7_supported(channels, height, width, sampling_ratio)) {
+      Roi7Out o{out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), nullptr, nullptr, nullptr};
+      return roi_align7_launch<0>(input, rois, num_rois, channels, height, width, spatial_scale, sampling_ratio, o, stream);
+    }
     if (channels % 4 != 0) return DANA_ENOTSUP;
     // >= 64 threads: warp 0 builds the y table, warp 1 the x table
     const int threads = (channels / 4 >= 256) ? 256 : (((channels / 4 + 31) / 32) * 32 < 64 ? 64 : ((channels / 4 + 31) / 32) * 32);

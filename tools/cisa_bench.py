@@ -21,6 +21,7 @@ ap.add_argument("--units", default="1,2,3,6,10,25,50,100")
 ap.add_argument("--ns", default="196,400")
 ap.add_argument("--precision", default="bf16x3,bf16")
 ap.add_argument("--only-unit", type=int, default=0)
+ap.add_argument("--eager", action="store_true", help="time eager launches (host launch overhead included) instead of a CUDA graph replay")
 a = ap.parse_args()
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) \
     else {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
@@ -49,6 +50,19 @@ for prec in a.precision.split(","):
             supp = ops.split_f32(sup.reshape(units, C, hs, hs).permute(0, 2, 3, 1).contiguous(), split)
             run = lambda: eng.rpn_attention(corr, supp, 1)  # noqa: E731
             for _ in range(3):
+                run()
+            if not a.eager:   # one graph replay per iteration: device time of the block, not python launch overhead
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    run()
+                    with torch.cuda.graph(graph, stream=side):
+                        run()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                run = graph.replay
                 run()
             tot = 0.0
             for _ in range(a.iters):

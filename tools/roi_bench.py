@@ -18,6 +18,8 @@ from dana_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--batch", type=int, default=4)
+ap.add_argument("--sweep", action="store_true", help="also time the fp32 NHWC kernel per RoI size class")
+ap.add_argument("--only", default="", help="run only the named variant (nchw|pair|head|f32) -- for ncu captures")
 a = ap.parse_args()
 b, c, h, w = a.batch, 1024, 38, 63
 rs = np.random.RandomState(0)
@@ -49,6 +51,20 @@ def timeit(fn):
     return tot / a.iters
 
 
+peak = 6405.0
+try:
+    import json
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+if a.only:
+    pe = torch.randn(49, c, device="cuda")
+    fn = {"nchw": lambda: ops.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0),
+          "pair": lambda: ops.roi_align_nhwc(nhwc, rois, 1.0 / 16, 7, 0, want_f32=False, want_pair=True),
+          "head": lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, pe=pe, want_f32=False, want_pair=True, want_qpe=True),
+          "f32": lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, want_f32=True, want_pair=False, want_qpe=False)}[a.only]
+    print("%s: %.4f ms" % (a.only, timeit(fn)))
+    sys.exit(0)
 ms = timeit(lambda: ops.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0))
 print("roi_align NCHW fp32 (reference layout, incl. NCHW->NHWC staging): %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
       (ms, alg_bytes / ms / 1e6, alg_bytes / 1e6))
@@ -64,3 +80,15 @@ print("roi_align_head NHWC -> pooled pair + (pooled+PE) pair:              %.4f 
 ms = timeit(lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, want_f32=True, want_pair=False, want_qpe=False))
 print("roi_align_head NHWC -> fp32 [R,7,7,C]:                              %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
       (ms, alg_bytes / ms / 1e6, alg_bytes / 1e6))
+print("fraction of the measured HBM peak (%.0f GB/s): %.1f %%" % (peak, 100 * alg_bytes / ms / 1e6 / peak))
+if a.sweep:
+    # the gather cost of an RoI grows with its area (adaptive sampling visits every feature pixel it covers), the
+    # output does not: per size class, where the kernel is write-bound and where it is gather-bound
+    print("size sweep (square RoIs, 1200 per class, fp32 [R,7,7,C] out):  side px | ms | GB/s algorithmic | % HBM peak")
+    for side in (32, 64, 112, 160, 224, 320, 448, 600):
+        cx, cy = rs.uniform(side / 2, 1000 - side / 2, r), rs.uniform(min(side, 599) / 2, 600 - min(side, 599) / 2, r)
+        hh = min(side, 599)
+        rr = np.stack([np.repeat(np.arange(b), 300), cx - side / 2, cy - hh / 2, cx + side / 2, cy + hh / 2], 1).astype(np.float32)
+        rr = torch.from_numpy(rr).cuda()
+        ms = timeit(lambda: ops.roi_align_head(nhwc, rr, 1.0 / 16, 0, want_f32=True, want_pair=False, want_qpe=False))
+        print("  %4d  %.4f ms  %6.0f GB/s  %5.1f %%" % (side, ms, alg_bytes / ms / 1e6, 100 * alg_bytes / ms / 1e6 / peak))
