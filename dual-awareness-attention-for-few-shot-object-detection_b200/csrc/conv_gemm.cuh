@@ -67,7 +67,11 @@ struct ConvGemmCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulators
   static constexpr int kXposeBytes = 8 * 4096;  // one 32x32 fp32 transposition buffer per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kXposeBytes + 2 * BLOCK_N * 4 /*scale,bias*/ + 256;
+  // softmax epilogue: (row max, row sum) exchange, 8 warps x 64 floats; it overlays the scale/bias arrays (unused
+  // by that epilogue) when they are large enough -- the <256, 2> budget has no 2 KB to spare
+  // (the softmax epilogue exists at BLOCK_N = 64 and 256 only; the <128, 2> budget is full as well)
+  static constexpr int kXchgBytes = (BLOCK_N <= 64) ? 8 * 64 * 4 : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kXposeBytes + 2 * BLOCK_N * 4 /*scale,bias*/ + kXchgBytes + 256;
 };
 
 // FAST epilogue: host-verified n_out % 32 == 0, bf16 pair output (no fp32 output / residual), every
@@ -116,6 +120,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int kStages = Cfg::kStages;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(kStages >= 2, "pipeline too shallow");
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared-memory budget");
 
   // No alignment slack: the budget of the <256, 2> configuration is within 1 KB of the 227 KB limit.  The dynamic
   // window starts at offset 0 of the CTA's shared memory (the kernel has no static __shared__), which is
@@ -125,7 +130,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   float* s_xpose = reinterpret_cast<float*>(tiles + kStages * Cfg::kStageBytes);   // [8 warps][32][32]
   float* s_scale = s_xpose + Cfg::kXposeBytes / 4;
   float* s_bias = s_scale + BLOCK_N;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
+  float* s_xchg = (Cfg::kXchgBytes == 0) ? s_scale : s_bias + BLOCK_N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N + Cfg::kXchgBytes / 4);
   uint64_t* full_bar = bars;                 // [kStages]
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* acc_full = bars + 2 * kStages;   // [2]
@@ -461,7 +467,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
       // stage per-channel scale (x alpha) / bias -- only when the N-tile (or, with per-image bias, the image)
       // changes, which with N-major tile order is once or twice per CTA
-      if (co_t != staged_co || (p.bias_sn != 0 && tn0 != staged_n)) {
+      if (!SOFTMAX && (co_t != staged_co || (p.bias_sn != 0 && tn0 != staged_n))) {
         staged_co = co_t;
         staged_n = tn0;
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -478,47 +484,94 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(&acc_full[acc], acc_phase, 104);
       tc_fence_after();
       if constexpr (SOFTMAX) {
+        static_assert(!SOFTMAX || Cfg::kXchgBytes > 0 || 2 * BLOCK_N * 4 >= 8 * 64 * 4, "no room for the softmax exchange");
+        // The segment's 32-column chunks are split between the two warps of the TMEM lane quarter.  Each warp
+        // pulls its chunks into registers with one tcgen05.ld burst and hands the accumulator back to the MMA
+        // warp at once; row max and row sum are combined with the partner through shared memory (64-thread
+        // named barrier per quarter); one ex2.approx per element, scale folded into the exponent.
         const int ns = p.sm_ns;
-        const int used = (ns + 31) >> 5;                       // chunks that hold keys
+        const int used = (ns + 31) >> 5;                       // chunks that hold keys (<= BLOCK_N / 32)
+        const int n_first = (used + 1) >> 1;
+        const int my_c0 = half ? n_first : 0;
+        const int my_n = half ? used - n_first : n_first;
+        constexpr int kMaxC = (kChunks + 1) / 2;
         const uint32_t trow0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-        // row statistics (lane = row): two passes over the segment in TMEM
+        uint32_t v[kMaxC][32];
+#pragma unroll
+        for (int ci = 0; ci < kMaxC; ++ci)
+          if (ci < my_n) tmem_ld32(trow0 + (my_c0 + ci) * 32, v[ci]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);           // the logits live in registers from here on
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        float* xs_mine = s_xchg + (warp - 2) * 64;
+        const float* xs_peer = s_xchg + ((warp - 2) ^ 4) * 64;
         float mx = -INFINITY;
-        for (int c = 0; c < used; ++c) {
-          uint32_t v[32];
-          tmem_ld32(trow0 + c * 32, v);
-          tmem_ld_wait();
+        // only the segment's last chunk can be partial: full chunks run without per-element predicates
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < ns) mx = fmaxf(mx, __uint_as_float(v[j]));
-        }
+        for (int ci = 0; ci < kMaxC; ++ci)
+          if (ci < my_n) {
+            const int nv = ns - (my_c0 + ci) * 32;   // valid columns of this chunk (>= 1)
+            if (nv >= 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[ci][j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) mx = fmaxf(mx, __uint_as_float(v[ci][j]));
+            }
+          }
+        xs_mine[lane] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        mx = fmaxf(mx, xs_peer[lane]);
+        const float sc = p.alpha * 1.4426950408889634f;
+        const float mb = mx * sc;
         float sum = 0.0f;
-        for (int c = 0; c < used; ++c) {
-          uint32_t v[32];
-          tmem_ld32(trow0 + c * 32, v);
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < ns) sum += expf((__uint_as_float(v[j]) - mx) * p.alpha);
-        }
+        for (int ci = 0; ci < kMaxC; ++ci)
+          if (ci < my_n) {
+            const int nv = ns - (my_c0 + ci) * 32;
+            float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // four independent sum chains
+            if (nv >= 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float e;
+                const float t = fmaf(__uint_as_float(v[ci][j]), sc, -mb);
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+                part[j & 3] += e;
+                v[ci][j] = __float_as_uint(e);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float e;
+                const float t = fmaf(__uint_as_float(v[ci][j]), sc, -mb);
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+                if (j >= nv) e = 0.0f;
+                part[j & 3] += e;
+                v[ci][j] = __float_as_uint(e);
+              }
+            }
+            sum += (part[0] + part[1]) + (part[2] + part[3]);
+          }
+        xs_mine[32 + lane] = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        sum += xs_peer[32 + lane];
         const float inv = 1.0f / sum;
         const long long seg_col = static_cast<long long>(co_t) * p.sm_pitch;
 #pragma unroll
-        for (int ci = 0; ci < kCpw; ++ci) {
-          const int c = c_begin + ci;
-          if (c >= kChunks || c * 32 >= p.sm_pitch) break;
-          uint32_t v[32];
-          tmem_ld32(trow0 + c * 32, v);
-          tmem_ld_wait();
+        for (int ci = 0; ci < kMaxC; ++ci) {
+          if (ci >= my_n) break;
+          const int c = my_c0 + ci;
           float4* trow = reinterpret_cast<float4*>(tb + lane * 32);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 o;
-            o.x = (c * 32 + g * 4 + 0 < ns) ? expf((__uint_as_float(v[g * 4 + 0]) - mx) * p.alpha) * inv : 0.0f;
-            o.y = (c * 32 + g * 4 + 1 < ns) ? expf((__uint_as_float(v[g * 4 + 1]) - mx) * p.alpha) * inv : 0.0f;
-            o.z = (c * 32 + g * 4 + 2 < ns) ? expf((__uint_as_float(v[g * 4 + 2]) - mx) * p.alpha) * inv : 0.0f;
-            o.w = (c * 32 + g * 4 + 3 < ns) ? expf((__uint_as_float(v[g * 4 + 3]) - mx) * p.alpha) * inv : 0.0f;
-            trow[g ^ (lane & 7)] = o;
-          }
+          for (int g = 0; g < 8; ++g)
+            trow[g ^ (lane & 7)] = make_float4(__uint_as_float(v[ci][g * 4 + 0]) * inv, __uint_as_float(v[ci][g * 4 + 1]) * inv,
+                                               __uint_as_float(v[ci][g * 4 + 2]) * inv, __uint_as_float(v[ci][g * 4 + 3]) * inv);
           __syncwarp();
           const int col = c * 32 + cg;
 #pragma unroll
@@ -544,13 +597,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
           }
           __syncwarp();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
         }
         continue;
       }

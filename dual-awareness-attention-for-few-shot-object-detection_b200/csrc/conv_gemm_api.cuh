@@ -169,6 +169,12 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   const long long sp_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
   const int sms = sm_count();
   int block_n = a->n_out > 128 ? 256 : (a->n_out > 64 ? 128 : 64);
+  // few M-tiles and a short K loop (the q/k projections of a single episode): narrower tiles spread the work over
+  // more SMs at no extra cost -- stream-K's partial-tile exchange costs more than such a launch (measured: q-proj
+  // 1900x256x1024 took 50 us as 15 stream-K'd 256-wide tiles)
+  if (static_cast<long long>(taps) * a->a_c <= 2048) {
+    while (block_n > 64 && sp_tiles * ((a->n_out + block_n - 1) / block_n) * 2 <= sms) block_n >>= 1;
+  }
   if (softmax) block_n = a->softmax_ns <= 64 ? 64 : 256;   // one N-tile per shot segment
   {
     const char* env = getenv("DANA_BLOCK_N");

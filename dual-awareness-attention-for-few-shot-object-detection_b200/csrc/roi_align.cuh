@@ -247,8 +247,9 @@ __device__ __forceinline__ void build_axis_compact(float* w /*[kRoiTaps]*/, int*
 }
 
 struct Roi7Tables {
-  float wy[7][kRoiTaps];
+  float wy[8][kRoiTaps];      // row 7 is never used with a non-zero count (keeps the look-ahead read in bounds)
   float wx[7][kRoiTaps];
+  float2 wx2[7][kRoiTaps];    // (w, w): operand of the packed FMA
   int ylo[7], ny[7], xlo[7], nx[7];
   RoiGeom g;
 };
@@ -274,42 +275,51 @@ struct Roi7Out {
   __nv_bfloat16 *qhi, *qlo;   // MODE 0: pair of value + pe[bin] (optional)
 };
 
+// Accumulators are float2 pairs and every multiply-add is the packed fma.rn.f32x2 (two fp32 FMAs per issue slot:
+// the kernel is issue-bound once its loads overlap); the x weights are stored duplicated (w, w) for that purpose.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
 // x pass of one map row for this thread's 4 channels: rs[pw] = sum_k wx[pw][k] * F[row][xlo[pw] + k]
 template <int T, int CH>
 __device__ __forceinline__ void roi7_row_pass(const float* __restrict__ rowp, int channels, const Roi7Tables& s,
-                                              float4 (&rs)[7]) {
+                                              float2 (&rs)[7][2]) {
   const int cs = CH ? CH : channels;
 #pragma unroll
   for (int pw = 0; pw < 7; ++pw) {
     const float* px = rowp + static_cast<long long>(s.xlo[pw]) * cs;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 a0 = f2(0.f, 0.f), a1 = f2(0.f, 0.f);
     if constexpr (T > 0) {
       float4 f[T];
 #pragma unroll
       for (int k = 0; k < T; ++k) f[k] = __ldg(reinterpret_cast<const float4*>(px + static_cast<long long>(k) * cs));
 #pragma unroll
       for (int k = 0; k < T; ++k) {
-        const float w = s.wx[pw][k];
-        a.x += w * f[k].x; a.y += w * f[k].y; a.z += w * f[k].z; a.w += w * f[k].w;
+        const float2 w = s.wx2[pw][k];
+        a0 = __ffma2_rn(w, f2(f[k].x, f[k].y), a0);
+        a1 = __ffma2_rn(w, f2(f[k].z, f[k].w), a1);
       }
     } else {
       const int n = s.nx[pw];
       for (int k = 0; k < n; ++k, px += cs) {
-        const float w = s.wx[pw][k];
+        const float2 w = s.wx2[pw][k];
         const float4 f = __ldg(reinterpret_cast<const float4*>(px));
-        a.x += w * f.x; a.y += w * f.y; a.z += w * f.z; a.w += w * f.w;
+        a0 = __ffma2_rn(w, f2(f.x, f.y), a0);
+        a1 = __ffma2_rn(w, f2(f.z, f.w), a1);
       }
     }
-    rs[pw] = a;
+    rs[pw][0] = a0;
+    rs[pw][1] = a1;
   }
 }
 
 template <int MODE>
-__device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, float inv_count, const float4 (&acc)[7],
+__device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, float inv_count, const float2 (&acc)[7][2],
                                           const Roi7Out& o, float* s_stage, int tid) {
+  const float2 ic = f2(inv_count, inv_count);
 #pragma unroll
   for (int pw = 0; pw < 7; ++pw) {
-    const float v[4] = {acc[pw].x * inv_count, acc[pw].y * inv_count, acc[pw].z * inv_count, acc[pw].w * inv_count};
+    const float2 v0 = __fmul2_rn(acc[pw][0], ic), v1 = __fmul2_rn(acc[pw][1], ic);
+    const float v[4] = {v0.x, v0.y, v1.x, v1.y};
     const int bin = ph * 7 + pw;
     if constexpr (MODE == 1) {
 #pragma unroll
@@ -327,47 +337,57 @@ __device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, f
   }
 }
 
-// the y loop: window rows in rolling (two live bins) or per-bin order; see the header comment
+// the y loop: bins in order, two accumulator sets that swap roles (no register shuffling); in rolling order a map
+// row shared with the next bin is added to both sets; see the header comment
 template <int T, int CH, int MODE>
 __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int channels, int width, const Roi7Tables& s,
                                             bool rolling, int r, int c0, float inv_count, const Roi7Out& o,
                                             float* s_stage, int tid) {
   const long long row_pitch = static_cast<long long>(width) * (CH ? CH : channels);
-  float4 acc_a[7], acc_b[7];
+  float2 acc_a[7][2], acc_b[7][2];
 #pragma unroll
-  for (int pw = 0; pw < 7; ++pw) acc_a[pw] = acc_b[pw] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int cur = 0;
-  int y = s.ylo[0];
-  while (cur < 7) {
-    const int ylo_c = s.ylo[cur], ny_c = s.ny[cur];
-    if (y < ylo_c) y = ylo_c;
-    if (y >= ylo_c + ny_c) {       // bin `cur` is complete (or empty): write it, promote the next bin
-      roi7_emit<MODE>(r, cur, c0, channels, inv_count, acc_a, o, s_stage, tid);
-#pragma unroll
-      for (int pw = 0; pw < 7; ++pw) {
-        acc_a[pw] = acc_b[pw];
-        acc_b[pw] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      ++cur;
-      if (!rolling && cur < 7) y = s.ylo[cur];
-      continue;
-    }
-    const float wa = s.wy[cur][y - ylo_c];
-    float wb = 0.0f;
+  for (int pw = 0; pw < 7; ++pw) acc_a[pw][0] = acc_a[pw][1] = acc_b[pw][0] = acc_b[pw][1] = f2(0.f, 0.f);
+  int y = 0;
+  auto do_bin = [&](float2 (&ca)[7][2], float2 (&na)[7][2], int cur) {
+    const int ylo_c = s.ylo[cur];
+    const int yend = ylo_c + s.ny[cur];
+    y = rolling ? max(y, ylo_c) : ylo_c;
+    int nlo = 0x3fffffff, nn = 0;
     if (rolling && cur < 6) {
-      const int d = y - s.ylo[cur + 1];
-      if (d >= 0 && d < s.ny[cur + 1]) wb = s.wy[cur + 1][d];
+      nlo = s.ylo[cur + 1];
+      nn = s.ny[cur + 1];
     }
-    if (wa != 0.0f || wb != 0.0f) {
-      float4 rs[7];
-      roi7_row_pass<T, CH>(fbase + static_cast<long long>(y) * row_pitch, channels, s, rs);
+    for (; y < yend; ++y) {
+      const float wa = s.wy[cur][y - ylo_c];
+      const int d = y - nlo;
+      const float wb = (d >= 0 && d < nn) ? s.wy[cur + 1][d] : 0.0f;
+      if (wa != 0.0f || wb != 0.0f) {
+        float2 rs[7][2];
+        roi7_row_pass<T, CH>(fbase + static_cast<long long>(y) * row_pitch, channels, s, rs);
+        const float2 wa2 = f2(wa, wa);
 #pragma unroll
-      for (int pw = 0; pw < 7; ++pw) {
-        acc_a[pw].x += wa * rs[pw].x; acc_a[pw].y += wa * rs[pw].y; acc_a[pw].z += wa * rs[pw].z; acc_a[pw].w += wa * rs[pw].w;
-        acc_b[pw].x += wb * rs[pw].x; acc_b[pw].y += wb * rs[pw].y; acc_b[pw].z += wb * rs[pw].z; acc_b[pw].w += wb * rs[pw].w;
+        for (int pw = 0; pw < 7; ++pw) {
+          ca[pw][0] = __ffma2_rn(wa2, rs[pw][0], ca[pw][0]);
+          ca[pw][1] = __ffma2_rn(wa2, rs[pw][1], ca[pw][1]);
+        }
+        if (wb != 0.0f) {
+          const float2 wb2 = f2(wb, wb);
+#pragma unroll
+          for (int pw = 0; pw < 7; ++pw) {
+            na[pw][0] = __ffma2_rn(wb2, rs[pw][0], na[pw][0]);
+            na[pw][1] = __ffma2_rn(wb2, rs[pw][1], na[pw][1]);
+          }
+        }
       }
     }
-    ++y;
+    roi7_emit<MODE>(r, cur, c0, channels, inv_count, ca, o, s_stage, tid);
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw) ca[pw][0] = ca[pw][1] = f2(0.f, 0.f);
+  };
+#pragma unroll 1
+  for (int cur = 0; cur < 7; cur += 2) {
+    do_bin(acc_a, acc_b, cur);
+    if (cur + 1 < 7) do_bin(acc_b, acc_a, cur + 1);
   }
 }
 
@@ -391,7 +411,7 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
   int maxn = 0;
 #pragma unroll
   for (int pw = 0; pw < 7; ++pw) maxn = max(maxn, s.nx[pw]);
-  int t = maxn <= 2 ? 2 : maxn <= 3 ? 3 : maxn <= 4 ? 4 : maxn <= 6 ? 6 : maxn <= 8 ? 8 : maxn <= 12 ? 12 : 16;
+  int t = maxn <= 2 ? 2 : maxn <= 6 ? maxn : maxn <= 8 ? 8 : maxn <= 10 ? 10 : maxn <= 12 ? 12 : 16;
   if (t > width) t = 0;
   if (t > 0 && tid >= 32 && tid < 39) {
     // shift this bin's tap window left so that xlo + t <= width: padding taps read valid pixels with zero weight
@@ -403,6 +423,10 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
       for (int k = kRoiTaps - 1; k >= 0; --k) s.wx[pw][k] = (k >= sh) ? s.wx[pw][k - sh] : 0.0f;
       s.xlo[pw] = base;
     }
+  }
+  if (tid >= 32 && tid < 39) {
+#pragma unroll
+    for (int k = 0; k < kRoiTaps; ++k) s.wx2[tid - 32][k] = make_float2(s.wx[tid - 32][k], s.wx[tid - 32][k]);
   }
   if (tid == 0) {
     // rolling order is valid when no map row feeds three bins: first row of bin p+2 lies past the last row of bin p
@@ -421,13 +445,11 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
   const bool rolling = s_rolling != 0;
   if (c_ok || MODE == 1) {
     switch (s_t) {
-      case 2: roi7_gather<2, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
-      case 3: roi7_gather<3, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
-      case 4: roi7_gather<4, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
-      case 6: roi7_gather<6, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
-      case 8: roi7_gather<8, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
-      case 12: roi7_gather<12, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
-      case 16: roi7_gather<16, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+#define DANA_ROI7_CASE(TT) \
+  case TT: roi7_gather<TT, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
+      DANA_ROI7_CASE(2) DANA_ROI7_CASE(3) DANA_ROI7_CASE(4) DANA_ROI7_CASE(5) DANA_ROI7_CASE(6) DANA_ROI7_CASE(8)
+      DANA_ROI7_CASE(10) DANA_ROI7_CASE(12) DANA_ROI7_CASE(16)
+#undef DANA_ROI7_CASE
       default: roi7_gather<0, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
     }
   }

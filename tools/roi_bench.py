@@ -1,7 +1,8 @@
 """RoIAlign microbenchmark at the BASELINE.json shape (map [B,1024,38,63], 300 RoIs per image): the
 reference-layout operator (NCHW fp32 -> [R,C,7,7] fp32, dana_roi_align_forward layout 0) and the
 pipeline variant (NHWC -> bf16 pair).  Algorithmic bytes: 4*R*C*49 + 4*C*h*w*B + 20*R.
-  ncu --set full --clock-control none --import-source on -k regex:roi_align_fwd -c 2 -o gpurun_out/roi python tools/roi_bench.py --iters 1
+  ncu --set full --clock-control none --import-source on -k regex:roi_align7 -c 3 -o gpurun_out/roi python tools/roi_bench.py --iters 1 --only f32
+L2 is flushed before every timed launch (256 MiB written, then 256 MiB read so that no dirty lines are left behind).
 """
 import argparse
 import os
@@ -33,6 +34,16 @@ rois = np.stack([np.repeat(np.arange(b), 300), np.clip(cx - bw / 2, 0, 999), np.
 rois = torch.from_numpy(rois).cuda()
 nhwc = feat.permute(0, 2, 3, 1).contiguous()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
+
+
+def l2_flush():
+    """Write a 256 MiB buffer (evicts everything), then READ another 256 MiB one: the write alone leaves ~126 MB of
+    dirty lines in L2 whose write-back would land inside the timed region of a write-bound kernel and be billed to it."""
+    flush.zero_()
+    flush_rd.sum()
+
+
 alg_bytes = 4.0 * r * c * 49 + 4.0 * c * h * w * b + 20.0 * r
 
 
@@ -41,7 +52,7 @@ def timeit(fn):
         fn()
     tot = 0.0
     for _ in range(a.iters):
-        flush.zero_()
+        l2_flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
