@@ -206,8 +206,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       SkRange rng = my_range();
       int wk = cluster_id - num_clusters, kb_lo = 0, kb_hi = num_kb;
       while (stream_k ? rng.next(wk, kb_lo, kb_hi) : ((wk += num_clusters) < num_work)) {
-        const int co_t = wk / m_groups;   // N-tile is the slow index: a CTA keeps its weights / scale / bias
-        const int sp = (wk % m_groups) * CM + cm_rank;
+        // N-tile is the FAST index: the tiles_co N-tiles of one M-tile run on neighbouring CTAs at the same time, so
+        // the activation tile (and, for 3x3 convs, its nine shifted views) is fetched from DRAM once and re-read from
+        // L2; the weights are small and L2-resident either way.  (With N slow, every pass over M re-streamed the
+        // whole activation: ncu showed 543 MB of DRAM traffic for the 350 MB layer4 conv3, 559 MB for the 136 MB RPN conv.)
+        const int mg = wk / p.tiles_co;
+        const int co_t = wk - mg * p.tiles_co;
+        const int sp = mg * CM + cm_rank;
         const int x0 = (sp % p.tiles_x) * p.bw;
         const int y0 = ((sp / p.tiles_x) % p.tiles_y) * p.bh;
         const int n0 = (sp / (p.tiles_x * p.tiles_y)) * p.bn;
@@ -393,8 +398,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       // once and the warp shares the results
       int co_t = 0, tx0 = 0, ty0 = 0, tn0 = 0;
       if (lane == 0) {
-        co_t = wk / m_groups;   // N-tile is the slow index: a CTA keeps its weights / scale / bias
-        const int sp = (wk - co_t * m_groups) * CM + cm_rank;
+        const int mg = wk / p.tiles_co;   // N-tile is the fast index (see the producer)
+        co_t = wk - mg * p.tiles_co;
+        const int sp = mg * CM + cm_rank;
         const int txy = p.tiles_x * p.tiles_y;
         const int tn = sp / txy;
         const int rem = sp - tn * txy;
@@ -408,6 +414,47 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       ty0 = __shfl_sync(0xffffffffu, ty0, 0);
       tn0 = __shfl_sync(0xffffffffu, tn0, 0);
       const int co0 = co_t * BLOCK_N;
+      if constexpr (FAST) {
+        // Residual stream: the layers that carry a residual are the HBM-bound ones (K = 64..512), and their
+        // epilogue stalled on the residual loads (ncu: long_scoreboard on the first use of the prefetched words --
+        // one chunk of look-ahead does not cover DRAM latency).  Pull the NEXT tile's residual rows into L2 now,
+        // a whole tile ahead: 2 threads per row, 128-byte lines, no registers held.
+        if (p.res_hi != nullptr && !stream_k) {
+          const int wn = wk + num_clusters;
+          if (wn < num_work) {
+            int nco = 0, nx0 = 0, ny0 = 0, nn0 = 0;
+            if (lane == 0) {
+              const int mg = wn / p.tiles_co;
+              nco = wn - mg * p.tiles_co;
+              const int sp = mg * CM + cm_rank;
+              const int txy = p.tiles_x * p.tiles_y;
+              const int tn = sp / txy;
+              const int rem = sp - tn * txy;
+              const int ty = rem / p.tiles_x;
+              nx0 = (rem - ty * p.tiles_x) * p.bw;
+              ny0 = ty * p.bh;
+              nn0 = tn * p.bn;
+            }
+            nco = __shfl_sync(0xffffffffu, nco, 0);
+            nx0 = __shfl_sync(0xffffffffu, nx0, 0);
+            ny0 = __shfl_sync(0xffffffffu, ny0, 0);
+            nn0 = __shfl_sync(0xffffffffu, nn0, 0);
+            const int m = et >> 1;
+            const int x = nx0 + (m & (p.bw - 1));
+            const int y = ny0 + ((m >> p.lbw) & (p.bh - 1));
+            const int n = nn0 + (m >> (p.lbw + p.lbh));
+            if (x < p.out_w && y < p.out_h && n < p.out_n) {
+              const long long off = static_cast<long long>(n) * p.sr_n + static_cast<long long>(y) * p.sr_y +
+                                    static_cast<long long>(x) * p.sr_x + nco * BLOCK_N + (et & 1) * (BLOCK_N / 2);
+              const int cols = min(BLOCK_N / 2, p.n_out - nco * BLOCK_N - (et & 1) * (BLOCK_N / 2));
+              for (int c = 0; c < cols; c += 64) {   // 64 bf16 = one 128-byte line
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_hi + off + c));
+                if (NSPLIT == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_lo + off + c));
+              }
+            }
+          }
+        }
+      }
       // the four rows this lane serves in phase B
       long long o_off[4], r_off[4];
       bool row_ok[4];

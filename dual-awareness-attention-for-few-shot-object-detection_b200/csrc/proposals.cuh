@@ -61,13 +61,16 @@ __global__ void proposals_decode_kernel(const float4* __restrict__ deltas, const
   keys[gid] = (static_cast<unsigned long long>(b) << 32) | static_cast<unsigned long long>(~ord);
 }
 
-// Greedy NMS against the kept set, one CTA (256 threads) per image, early exit at max_keep.
+// Greedy NMS against the kept set, one CTA (1024 threads) per image, early exit at max_keep.
 // Sorted candidates are taken 64 at a time: (1) each candidate is tested against every box kept so far
-// (4 threads per candidate, kept boxes in shared memory), (2) the 64x64 IoU bits inside the chunk are built
+// (16 threads per candidate, kept boxes in shared memory), (2) the 64x64 IoU bits inside the chunk are built
 // with warp ballots, (3) one thread resolves the chunk serially in registers.  Same fp32 arithmetic and
 // ">=" rule as nms.cuh (bit-exact keep set); work is O(examined x kept) instead of O(n^2).
+// The chain of chunks is serial, so its per-chunk latency is what matters: the next chunk's candidates
+// (order -> box, two dependent global loads) and keys are fetched while the current chunk is resolved.
 // Writes rois [B][post][5] (zero padded), optional scores / counts.
-__global__ void __launch_bounds__(256)
+constexpr int kPropNmsThreads = 1024;
+__global__ void __launch_bounds__(kPropNmsThreads)
 proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __restrict__ order,
                            const unsigned long long* __restrict__ keys_sorted, int hwa, int n_pre, int post,
                            float thresh, float min_score, int det_format, float* __restrict__ rois,
@@ -84,41 +87,61 @@ proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __re
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long seg = static_cast<long long>(b) * hwa;
   if (tid == 0) s_nkept = 0;
+  // software pipeline of the candidate fetch: box + key one chunk ahead, the `order` index two chunks ahead (the box
+  // address depends on it)
+  float4 next_bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned long long next_key = 0ull;
+  int ord_ahead = 0;
+  if (tid < 64) {
+    if (tid < n_pre) {
+      next_bx = boxes_all[seg + order[seg + tid]];
+      next_key = keys_sorted[seg + tid];
+    }
+    if (64 + tid < n_pre) ord_ahead = order[seg + 64 + tid];
+  }
+  unsigned long long my_key = 0ull;
   __syncthreads();
   for (int base = 0; base < n_pre; base += 64) {
     const int nkept = s_nkept;
     const int valid = min(64, n_pre - base);
     if (tid < 64) {
-      float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tid < valid) bx = boxes_all[seg + order[seg + base + tid]];
+      const float4 bx = next_bx;
+      my_key = next_key;
       s_cand[tid] = bx;
       s_cand_area[tid] = box_area_rn(bx);
       // candidates at or below the score floor never enter (detections: score > thresh, inference.py:130)
       unsigned int dead0 = 0;
       if (tid < valid && min_score > -INFINITY) {
-        const unsigned int ord = ~static_cast<unsigned int>(keys_sorted[seg + base + tid] & 0xFFFFFFFFull);
+        const unsigned int ord = ~static_cast<unsigned int>(my_key & 0xFFFFFFFFull);
         const unsigned int bits = (ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord;
         dead0 = !(__uint_as_float(bits) > min_score);
       }
       s_dead[tid] = dead0;
+      // prefetch the next chunk (consumed at the top of the next iteration)
+      next_bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (base + 64 + tid < n_pre) {
+        next_bx = boxes_all[seg + ord_ahead];
+        next_key = keys_sorted[seg + base + 64 + tid];
+      }
+      if (base + 128 + tid < n_pre) ord_ahead = order[seg + base + 128 + tid];
     }
     __syncthreads();
-    // (1) against the kept set: candidate = tid / 4, four threads stride the kept list
+    // (1) against the kept set: candidate = tid / 16, sixteen threads stride the kept list
     {
-      const int cj = tid >> 2, part = tid & 3;
+      const int cj = tid >> 4, part = tid & 15;
       const float4 cb = s_cand[cj];
       const float ca = s_cand_area[cj];
       bool dead = false;
-      for (int k = part; k < nkept && !dead; k += 4) dead = iou_suppresses(s_keep_box[k], s_keep_area[k], cb, ca, thresh);
+      for (int k = part; k < nkept && !dead; k += 16) dead = iou_suppresses(s_keep_box[k], s_keep_area[k], cb, ca, thresh);
       if (dead) s_dead[cj] = 1;   // benign race: all writers store 1
     }
-    // (2) IoU bits inside the chunk: warp w handles rows 8w..8w+7
+    // (2) IoU bits inside the chunk: warp w handles rows 2w, 2w+1
     {
       const float4 c0 = s_cand[lane], c1 = s_cand[lane + 32];
       const float a0 = s_cand_area[lane], a1 = s_cand_area[lane + 32];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int ri = warp * 8 + r;
+      for (int r = 0; r < 2; ++r) {
+        const int ri = warp * 2 + r;
         const float4 rb = s_cand[ri];
         const float ra = s_cand_area[ri];
         const bool p0 = (ri < valid) && (lane < valid) && (lane > ri) && iou_suppresses(rb, ra, c0, a0, thresh);
@@ -156,7 +179,7 @@ proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __re
       s_keep_area[pos] = s_cand_area[tid];
       float* row = rois + (static_cast<long long>(b) * post + pos) * 5;
       // recover the score from the sorted key (low 32 bits hold ~orderable(score))
-      const unsigned int ord = ~static_cast<unsigned int>(keys_sorted[seg + base + tid] & 0xFFFFFFFFull);
+      const unsigned int ord = ~static_cast<unsigned int>(my_key & 0xFFFFFFFFull);
       const unsigned int bits = (ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord;
       if (det_format) {           // (x1, y1, x2, y2, score), utils.py:312-317
         row[0] = bx.x;
@@ -179,7 +202,7 @@ proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __re
     if (s_nkept >= post) break;
   }
   const int cnt = s_nkept;
-  for (int k = cnt + tid; k < post; k += 256) {   // zero padding (proposal_layer.py:137,188-190)
+  for (int k = cnt + tid; k < post; k += kPropNmsThreads) {   // zero padding (proposal_layer.py:137,188-190)
     float* row = rois + (static_cast<long long>(b) * post + k) * 5;
     row[0] = det_format ? 0.0f : static_cast<float>(b);
     row[1] = row[2] = row[3] = row[4] = 0.0f;
@@ -266,7 +289,7 @@ inline int proposals_run(const float* fg_scores, const float* deltas, const floa
                                          static_cast<int>(keep_smem)));
     configured = keep_smem;
   }
-  proposals_nms_write_kernel<<<batch, 256, keep_smem, stream>>>(boxes_all, order, keys_out, hwa, w.n_pre,
+  proposals_nms_write_kernel<<<batch, kPropNmsThreads, keep_smem, stream>>>(boxes_all, order, keys_out, hwa, w.n_pre,
                                                                 post_nms_top_n, nms_thresh, -INFINITY, 0, rois,
                                                                 roi_scores, roi_counts);
   DANA_LAUNCH_CHECK();
@@ -343,7 +366,7 @@ inline int detections_run(const float* rois, const float* cls_prob, const float*
                                          static_cast<int>(keep_smem)));
     configured = keep_smem;
   }
-  proposals_nms_write_kernel<<<batch, 256, keep_smem, stream>>>(boxes_all, order, keys_out, r, r, r, nms_thresh,
+  proposals_nms_write_kernel<<<batch, kPropNmsThreads, keep_smem, stream>>>(boxes_all, order, keys_out, r, r, r, nms_thresh,
                                                                 score_thresh, 1, dets, nullptr, counts);
   DANA_LAUNCH_CHECK();
   return DANA_OK;

@@ -11,6 +11,8 @@
 // loop bounds are warp-uniform.  Sample coordinates are evaluated with explicit round-to-nearest
 // intrinsics in the reference's expression order so floor()/validity decisions agree bit for bit.
 #pragma once
+#include <stdlib.h>
+
 #include "api_common.cuh"
 #include "tc_common.cuh"
 
@@ -337,18 +339,22 @@ __device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, f
   }
 }
 
-// the y loop: bins in order, two accumulator sets that swap roles (no register shuffling); in rolling order a map
-// row shared with the next bin is added to both sets; see the header comment
-template <int T, int CH, int MODE>
+// The y loop: bins in order, two accumulator sets (current bin, next bin); in rolling order a map row shared with
+// the next bin is added to both sets; see the header comment.  ONE copy of the loop nest, with the compiled tap
+// count selected by a uniform switch around the row pass only: the per-CTA instruction footprint stays a few KB
+// (an earlier version instantiated the whole nest per tap count and spent 40 % of its stall samples on
+// instruction fetch, ncu `stalled_no_instructions`).
+template <int CH, int MODE>
 __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int channels, int width, const Roi7Tables& s,
-                                            bool rolling, int r, int c0, float inv_count, const Roi7Out& o,
+                                            int taps, bool rolling, int r, int c0, float inv_count, const Roi7Out& o,
                                             float* s_stage, int tid) {
   const long long row_pitch = static_cast<long long>(width) * (CH ? CH : channels);
-  float2 acc_a[7][2], acc_b[7][2];
+  float2 ca[7][2], na[7][2];
 #pragma unroll
-  for (int pw = 0; pw < 7; ++pw) acc_a[pw][0] = acc_a[pw][1] = acc_b[pw][0] = acc_b[pw][1] = f2(0.f, 0.f);
+  for (int pw = 0; pw < 7; ++pw) ca[pw][0] = ca[pw][1] = na[pw][0] = na[pw][1] = f2(0.f, 0.f);
   int y = 0;
-  auto do_bin = [&](float2 (&ca)[7][2], float2 (&na)[7][2], int cur) {
+#pragma unroll 1
+  for (int cur = 0; cur < 7; ++cur) {
     const int ylo_c = s.ylo[cur];
     const int yend = ylo_c + s.ny[cur];
     y = rolling ? max(y, ylo_c) : ylo_c;
@@ -357,43 +363,52 @@ __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int
       nlo = s.ylo[cur + 1];
       nn = s.ny[cur + 1];
     }
+#pragma unroll 1
     for (; y < yend; ++y) {
       const float wa = s.wy[cur][y - ylo_c];
       const int d = y - nlo;
       const float wb = (d >= 0 && d < nn) ? s.wy[cur + 1][d] : 0.0f;
-      if (wa != 0.0f || wb != 0.0f) {
-        float2 rs[7][2];
-        roi7_row_pass<T, CH>(fbase + static_cast<long long>(y) * row_pitch, channels, s, rs);
-        const float2 wa2 = f2(wa, wa);
+      if (wa == 0.0f && wb == 0.0f) continue;
+      float2 rs[7][2];
+      const float* rowp = fbase + static_cast<long long>(y) * row_pitch;
+      switch (taps) {
+        case 2: roi7_row_pass<2, CH>(rowp, channels, s, rs); break;
+        case 3: roi7_row_pass<3, CH>(rowp, channels, s, rs); break;
+        case 4: roi7_row_pass<4, CH>(rowp, channels, s, rs); break;
+        case 6: roi7_row_pass<6, CH>(rowp, channels, s, rs); break;
+        case 8: roi7_row_pass<8, CH>(rowp, channels, s, rs); break;
+        case 12: roi7_row_pass<12, CH>(rowp, channels, s, rs); break;
+        case 16: roi7_row_pass<16, CH>(rowp, channels, s, rs); break;
+        default: roi7_row_pass<0, CH>(rowp, channels, s, rs); break;
+      }
+      const float2 wa2 = f2(wa, wa);
+#pragma unroll
+      for (int pw = 0; pw < 7; ++pw) {
+        ca[pw][0] = __ffma2_rn(wa2, rs[pw][0], ca[pw][0]);
+        ca[pw][1] = __ffma2_rn(wa2, rs[pw][1], ca[pw][1]);
+      }
+      if (wb != 0.0f) {
+        const float2 wb2 = f2(wb, wb);
 #pragma unroll
         for (int pw = 0; pw < 7; ++pw) {
-          ca[pw][0] = __ffma2_rn(wa2, rs[pw][0], ca[pw][0]);
-          ca[pw][1] = __ffma2_rn(wa2, rs[pw][1], ca[pw][1]);
-        }
-        if (wb != 0.0f) {
-          const float2 wb2 = f2(wb, wb);
-#pragma unroll
-          for (int pw = 0; pw < 7; ++pw) {
-            na[pw][0] = __ffma2_rn(wb2, rs[pw][0], na[pw][0]);
-            na[pw][1] = __ffma2_rn(wb2, rs[pw][1], na[pw][1]);
-          }
+          na[pw][0] = __ffma2_rn(wb2, rs[pw][0], na[pw][0]);
+          na[pw][1] = __ffma2_rn(wb2, rs[pw][1], na[pw][1]);
         }
       }
     }
     roi7_emit<MODE>(r, cur, c0, channels, inv_count, ca, o, s_stage, tid);
 #pragma unroll
-    for (int pw = 0; pw < 7; ++pw) ca[pw][0] = ca[pw][1] = f2(0.f, 0.f);
-  };
-#pragma unroll 1
-  for (int cur = 0; cur < 7; cur += 2) {
-    do_bin(acc_a, acc_b, cur);
-    if (cur + 1 < 7) do_bin(acc_b, acc_a, cur + 1);
+    for (int pw = 0; pw < 7; ++pw) {
+      ca[pw][0] = na[pw][0];
+      ca[pw][1] = na[pw][1];
+      na[pw][0] = na[pw][1] = f2(0.f, 0.f);
+    }
   }
 }
 
 // grid (num_rois, ceil(C / 512)), block 128.  MODE 0: NHWC outputs; MODE 1: [R][C][49] via shared memory.
-template <int MODE, int CH>
-__global__ void __launch_bounds__(kRoi7Threads, MODE == 1 ? 2 : 4)
+template <int MODE, int CH, int OCC = (MODE == 1 ? 2 : 4)>
+__global__ void __launch_bounds__(kRoi7Threads, OCC)
 roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restrict__ rois, int channels, int height,
                   int width, float spatial_scale, int sampling_ratio, Roi7Out o) {
   extern __shared__ float s_stage[];   // MODE 1: [512][49]
@@ -411,7 +426,7 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
   int maxn = 0;
 #pragma unroll
   for (int pw = 0; pw < 7; ++pw) maxn = max(maxn, s.nx[pw]);
-  int t = maxn <= 2 ? 2 : maxn <= 6 ? maxn : maxn <= 8 ? 8 : maxn <= 10 ? 10 : maxn <= 12 ? 12 : 16;
+  int t = maxn <= 2 ? 2 : maxn <= 3 ? 3 : maxn <= 4 ? 4 : maxn <= 6 ? 6 : maxn <= 8 ? 8 : maxn <= 12 ? 12 : 16;
   if (t > width) t = 0;
   if (t > 0 && tid >= 32 && tid < 39) {
     // shift this bin's tap window left so that xlo + t <= width: padding taps read valid pixels with zero weight
@@ -444,14 +459,7 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
   const float* fbase = feat + static_cast<long long>(g.batch_ind) * height * width * channels + (c_ok ? c0 : 0);
   const bool rolling = s_rolling != 0;
   if (c_ok || MODE == 1) {
-    switch (s_t) {
-#define DANA_ROI7_CASE(TT) \
-  case TT: roi7_gather<TT, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
-      DANA_ROI7_CASE(2) DANA_ROI7_CASE(3) DANA_ROI7_CASE(4) DANA_ROI7_CASE(5) DANA_ROI7_CASE(6) DANA_ROI7_CASE(8)
-      DANA_ROI7_CASE(10) DANA_ROI7_CASE(12) DANA_ROI7_CASE(16)
-#undef DANA_ROI7_CASE
-      default: roi7_gather<0, CH, MODE>(fbase, channels, width, s, rolling, r, c0, inv_count, o, s_stage, tid); break;
-    }
+    roi7_gather<CH, MODE>(fbase, channels, width, s, s_t, rolling, r, c0, inv_count, o, s_stage, tid);
   }
   if constexpr (MODE == 1) {
     __syncthreads();
@@ -485,8 +493,20 @@ inline int roi_align7_launch(const float* feat_nhwc, const float* rois, int num_
     }
   }
   if (channels == 1024) {
-    roi_align7_kernel<MODE, 1024><<<dim3(num_rois, groups), kRoi7Threads, smem, stream>>>(
-        feat_nhwc, rois, channels, height, width, spatial_scale, sampling_ratio, o);
+    // CTAs per SM the register allocation is compiled for (MODE 0): 4 (128 registers, no spills) or 5 (96 registers,
+    // ~150 bytes of spills); DANA_ROI_OCC selects, for A/B measurements
+    static int occ = -1;
+    if (occ < 0) {
+      const char* env = getenv("DANA_ROI_OCC");
+      occ = (env != nullptr && atoi(env) == 5) ? 5 : 4;
+    }
+    if (MODE == 0 && occ == 5) {
+      roi_align7_kernel<0, 1024, 5><<<dim3(num_rois, groups), kRoi7Threads, smem, stream>>>(
+          feat_nhwc, rois, channels, height, width, spatial_scale, sampling_ratio, o);
+    } else {
+      roi_align7_kernel<MODE, 1024><<<dim3(num_rois, groups), kRoi7Threads, smem, stream>>>(
+          feat_nhwc, rois, channels, height, width, spatial_scale, sampling_ratio, o);
+    }
   } else {
     roi_align7_kernel<MODE, 0><<<dim3(num_rois, groups), kRoi7Threads, smem, stream>>>(
         feat_nhwc, rois, channels, height, width, spatial_scale, sampling_ratio, o);

@@ -1,5 +1,6 @@
 """One profiled forward step for ncu (never a benchmark number):
-  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+  ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+      --clock-control none --csv \
       --log-file gpurun_out/launches.csv python tools/profile_step.py [--precision bf16x3] [--batch 4]
 """
 import argparse
@@ -8,12 +9,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch  # noqa: E402
 
 import dana_b200  # noqa: E402,F401
-import dana_oracle as O  # noqa: E402  (synthetic weights / inputs only)
 from dana_b200.engine import DanaEngine  # noqa: E402
+from dana_b200.synthetic import synthetic_episode, synthetic_state_dict  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--precision", default="bf16x3")
@@ -24,8 +24,8 @@ ap.add_argument("--shots", type=int, default=3)
 ap.add_argument("--sets", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=2)
 a = ap.parse_args()
-p = O.make_params(1996)
-im, info, sup = O.synth_inputs(3, a.batch, a.height, a.width, a.shots * a.sets)
+p = synthetic_state_dict(1996)
+im, info, sup = synthetic_episode(3, a.batch, a.height, a.width, a.shots * a.sets)
 im, info, sup = im.cuda(), info.cuda(), sup.cuda()
 eng = DanaEngine(p, n_shot=a.shots, precision=a.precision)
 for _ in range(a.warmup):
