@@ -33,6 +33,9 @@ __device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_
   const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
   const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
   const float inter = __fmul_rn(w, h);
+  // disjoint boxes (the common case): 0 / union is 0, -0 or NaN, none of which is >= a positive threshold -- same
+  // decision as the division below, without the division
+  if (inter == 0.0f && thresh > 0.0f) return false;
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
   return ovr >= thresh;
 }

@@ -153,22 +153,29 @@ proposals_nms_write_kernel(const float4* __restrict__ boxes_all, const int* __re
     }
     __syncthreads();
     // (3) serial resolution of the chunk
-    if (tid == 0) {
-      unsigned long long removed = 0;
+    if (warp == 0) {
+      // the chunk's dead bits by ballot; the 64 diagonal words go to registers first so that the serial chain below
+      // is pure ALU (it used to pay one shared-memory round trip per kept box)
+      const unsigned dlo = __ballot_sync(0xffffffffu, s_dead[lane] != 0);
+      const unsigned dhi = __ballot_sync(0xffffffffu, s_dead[lane + 32] != 0);
+      if (lane == 0) {
+        unsigned long long removed = static_cast<unsigned long long>(dlo) | (static_cast<unsigned long long>(dhi) << 32);
+        unsigned long long d[64];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) removed |= static_cast<unsigned long long>(s_dead[j] != 0) << j;
-      unsigned long long keep = 0;
-      int room = post - nkept;
+        for (int j = 0; j < 64; ++j) d[j] = s_diag[j];
+        unsigned long long keep = 0;
+        int room = post - nkept;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const bool alive = (j < valid) && !((removed >> j) & 1ull) && room > 0;
-        if (alive) {
-          keep |= (1ull << j);
-          removed |= s_diag[j];
-          --room;
+        for (int j = 0; j < 64; ++j) {
+          const bool alive = (j < valid) && !((removed >> j) & 1ull) && room > 0;
+          if (alive) {
+            keep |= (1ull << j);
+            removed |= d[j];
+            --room;
+          }
         }
+        s_keepbits = keep;
       }
-      s_keepbits = keep;
     }
     __syncthreads();
     const unsigned long long keep = s_keepbits;
