@@ -42,6 +42,16 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def gemm_traffic():
+    """DRAM bytes per launch of the GEMM kernel (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 116
+    launches of one step), from the committed ncu launch list of this round; None when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return round(json.load(f)["dram_bytes_per_launch"])
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -204,7 +214,7 @@ def run_ours(args):
                      "achieved": round(g_flops / (g_ms * 1e-3) / 1e12, 1) if g_ms > 0 else None,
                      "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": round(g_flops / (g_ms * 1e-3) / 1e12 / peaks["tf_sustained"], 4) if g_ms > 0 else None,
-                     "traffic": None, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a step)",
+                     "traffic": gemm_traffic(), "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a step)",
                      "launches_per_step": len(trace), "gemm_ms_per_step": round(g_ms, 3),
                      "algorithmic_gflop_per_step": round(g_flops / 1e9, 1),
                      "step_gflop_model": GF_PER_QUERY * b},
