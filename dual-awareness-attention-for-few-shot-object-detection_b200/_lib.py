@@ -4,7 +4,7 @@ The library is the only compute path of this package: if it is missing or fails 
 import raises -- there is no CPU or eager fallback."""
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdana_b200.so")
@@ -64,6 +64,8 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_roi_align_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_int, c_void_p, c_void_p]),
+    "dana_episode_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_double, c_double,
+                                    c_int, c_int, c_float, c_float, c_float, c_void_p, c_int, c_int, c_void_p]),
     "dana_conv_gemm_workspace_bytes": (c_int64, []),
     "dana_conv_gemm": (c_int, [POINTER(ConvGemmArgs), c_void_p]),
     "dana_stem_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

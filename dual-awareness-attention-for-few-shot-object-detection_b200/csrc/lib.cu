@@ -8,6 +8,7 @@
 #include "proposals.cuh"
 #include "roi_align.cuh"
 #include "dana_ops.cuh"
+#include "episode.cuh"
 
 using namespace dana;
 
@@ -104,6 +105,14 @@ int64_t dana_conv_gemm_workspace_bytes(void) { return 4096 + static_cast<int64_t
 
 int dana_conv_gemm(const dana_conv_gemm_args* args, void* stream) {
   return conv_gemm_dispatch(args, static_cast<cudaStream_t>(stream));
+}
+
+int dana_episode_resize(const void* src, int src_is_f32, int src_h, int src_w, int64_t src_row_pitch, int crop_x,
+                        int crop_y, int crop_w, int crop_h, double scale_x, double scale_y, int dst_w, int dst_h,
+                        float mean0, float mean1, float mean2, float* out, int out_h, int out_w, void* stream) {
+  return episode_resize_run(src, src_is_f32, src_h, src_w, src_row_pitch, crop_x, crop_y, crop_w, crop_h, scale_x,
+                            scale_y, dst_w, dst_h, mean0, mean1, mean2, out, out_h, out_w,
+                            static_cast<cudaStream_t>(stream));
 }
 
 #include "dana_ops_api.inc"

@@ -103,6 +103,21 @@ int dana_roi_align_backward(const float* grad_out, const float* rois, int num_ro
                             int sampling_ratio, float* grad_input, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Episode construction -- replaces, on the device, the per-image host work of
+ *   prep_im_for_blob (lib/model/utils/blob.py:35-52): astype(float32) - PIXEL_MEANS, cv2.resize(INTER_LINEAR)
+ *   the support crop -> resize -> zero-pad of lib/roi_data_layer/fs_loader.py:113-138 and
+ *   lib/roi_data_layer/inference_loader.py:95-109, and the HWC -> CHW permute of the loaders.
+ * src: HWC image, 3 channels (BGR), u8 (src_is_f32 = 0) or f32, `src_row_pitch` elements between rows.
+ * The window (crop_x, crop_y, crop_w, crop_h) is what cv2.resize would see as its source; scale_x / scale_y are
+ * source pixels per destination pixel (1 / fx when the reference passes fx, crop_w / dst_w when it passes dsize).
+ * mean0..2 are subtracted BEFORE interpolation (pass 0 for an already prepared image).
+ * out: [3][out_h][out_w] fp32, planes of the resized dst_h x dst_w image, zero elsewhere (the padded canvas).
+ * cv2's CV_32F arithmetic order is followed (row pass, then column pass; see csrc/episode.cuh). */
+int dana_episode_resize(const void* src, int src_is_f32, int src_h, int src_w, int64_t src_row_pitch, int crop_x,
+                        int crop_y, int crop_w, int crop_h, double scale_x, double scale_y, int dst_w, int dst_h,
+                        float mean0, float mean1, float mean2, float* out, int out_h, int out_w, void* stream);
+
+/* ------------------------------------------------------------------------
  * Tensor-core implicit-GEMM convolution / GEMM (tcgen05 + TMA).  Replaces the
  * cuDNN / cuBLAS calls behind nn.Conv2d + BatchNorm2d(eval) + ReLU + residual
  * (lib/model/framework/resnet.py:66-102, lib/model/rpn/rpn.py:28-36,63-72) and

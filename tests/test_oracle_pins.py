@@ -112,3 +112,38 @@ def test_ref_extension_matches_oracle_when_present():
     a = O.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0).numpy()
     b = ref_c.roi_align_forward(torch.from_numpy(feat), torch.from_numpy(rois), 1.0 / 16, 7, 7, 0).numpy()
     np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------------------ episode construction
+@pytest.mark.parametrize("case", ["down", "up", "same", "thin", "one"])
+def test_episode_resize_vs_cv2(golden_dir, case):
+    """oracle/episode_oracle.py against the real cv2 (oracle/make_golden_episode.py): bit-exact with cv2's generic
+    C++ path, within 1e-3 (8-bit pixel scale) of the default SIMD build the reference's loaders actually run."""
+    import episode_oracle as E
+    g = _g(golden_dir, "episode_cv2.npz")
+    src, dst = g[case + "_src"], g[case + "_dst"]
+    got = E.resize_linear_f32(src, dst.shape[1], dst.shape[0])
+    np.testing.assert_array_equal(got, g[case + "_dst_generic"])
+    np.testing.assert_allclose(got, dst, rtol=0, atol=1e-3)
+
+
+def test_episode_prep_im_vs_cv2(golden_dir):
+    import episode_oracle as E
+    g = _g(golden_dir, "episode_cv2.npz")
+    got, scale = E.prep_im_for_blob(g["prep_im"], [102.9801, 115.9465, 122.7717], 48)
+    assert scale == float(g["prep_scale"])
+    np.testing.assert_array_equal(got, g["prep_dst_generic"])
+    np.testing.assert_allclose(got, g["prep_dst"], rtol=0, atol=1e-3)
+
+
+def test_episode_support_crop_layout():
+    """fs_loader.py:117-138 on a synthetic image: long side -> 320, zero padding, CHW."""
+    import episode_oracle as E
+    rs = np.random.RandomState(3)
+    im = rs.standard_normal((90, 140, 3)).astype(np.float32) * 50
+    out = E.support_from_box(im, (10.2, 20.7, 60.9, 50.1), 1.5, 320)
+    assert out.shape == (3, 320, 320)
+    # box*1.5 -> int16 (15, 31, 91, 75): w 76 > h 44 -> width 320, height int(44 * 320 / 76) = 185
+    assert np.all(out[:, 185:, :] == 0) and np.any(out[:, 184, :] != 0)
+    tall = E.support_from_image((rs.rand(50, 20, 3) * 255).astype(np.uint8), [1.0, 2.0, 3.0], 320)
+    assert np.all(tall[:, :, 128:] == 0) and np.any(tall[:, :, 127] != 0)
