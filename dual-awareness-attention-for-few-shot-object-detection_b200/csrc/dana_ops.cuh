@@ -188,44 +188,102 @@ avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* _
 //   Vc = V' - mean_n V'  -> A operand of the k projection (the Linear bias cancels, :140-141)
 //   V'^T -> B operand of the P.V contraction (:147)
 // ---------------------------------------------------------------------------------------------
-// rows = maps*ns, warp per row.  v_out = in + pe[row % ns]; logit[row] = v . wvec + wb (if wvec)
-__global__ void support_pe_logit_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
-                                        const float* __restrict__ in_f32, const float* __restrict__ pe, int rows, int ns,
-                                        int c, const float* __restrict__ wvec, const float* __restrict__ wb,
-                                        float* __restrict__ v_out, float* __restrict__ logit) {
+// Three passes over the support maps instead of five, from three identities (exact in real arithmetic):
+//   * V' = V + 1 h^T with h = gamma * leaky_relu(g) a row-constant shift, so softmax_n(V' a + a0) = softmax_n(V a + a0):
+//     both logit vectors (BA and unary) come from ONE pass over V;
+//   * u^T V' = u^T V + h (the weights sum to one): g, the unary sum and the column mean come from ONE more pass;
+//   * V' - mean_n V' = V - mean_n V: the centred k-projection operand does not depend on g at all.
+// V itself (= S + PE) is never written back: every pass rebuilds it from the input pair (4 bytes per element, the
+// same traffic as reading an fp32 copy, minus the copy's write).
+//   pass 1  support_logits2_kernel    l1[row] = V c + c0,  l2[row] = V a + a0
+//   pass 2  support_wsum2_kernel      w = softmax(l1), u = softmax(l2);  g = w^T V;  r = u^T V + h;  colmean
+//   pass 3  support_finalize2_kernel  Vc = V - colmean (pair, A operand of the k projection),  V'^T = (V + h)^T (pair)
+__device__ __forceinline__ float support_x(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const float* f32,
+                                           const float* pe_row, long long i, int ch) {
+  float v = f32 ? __ldg(f32 + i) : ld_pair(hi, lo, i);
+  if (pe_row) v += __ldg(pe_row + ch);
+  return v;
+}
+// 8 consecutive channels (c % 8 == 0, 16-byte aligned rows)
+__device__ __forceinline__ void support_x8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const float* f32,
+                                           const float* pe_row, long long i, int ch, float (&x)[8]) {
+  if (f32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(f32 + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(f32 + i) + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + i));
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      x[2 * e] = __uint_as_float(hw[e] << 16);
+      x[2 * e + 1] = __uint_as_float(hw[e] & 0xFFFF0000u);
+    }
+    if (lo) {
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + i));
+      const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        x[2 * e] += __uint_as_float(lw[e] << 16);
+        x[2 * e + 1] += __uint_as_float(lw[e] & 0xFFFF0000u);
+      }
+    }
+  }
+  if (pe_row) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(pe_row + ch));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(pe_row + ch) + 1);
+    x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w; x[4] += b.x; x[5] += b.y; x[6] += b.z; x[7] += b.w;
+  }
+}
+
+// warp per row (rows = maps * ns)
+__global__ void __launch_bounds__(256)
+support_logits2_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                       const float* __restrict__ in_f32, const float* __restrict__ pe, int rows, int ns, int c,
+                       const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                       const float* __restrict__ b2, float* __restrict__ l1, float* __restrict__ l2, int vec8) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const long long base = static_cast<long long>(row) * c;
   const float* per = pe ? pe + static_cast<long long>(row % ns) * c : nullptr;
-  float dot = 0.0f;
-  for (int ch = lane; ch < c; ch += 32) {
-    float v = in_f32 ? in_f32[base + ch] : ld_pair(in_hi, in_lo, base + ch);
-    if (per) v += per[ch];
-    v_out[base + ch] = v;
-    if (wvec) dot += v * __ldg(wvec + ch);
+  float d1 = 0.0f, d2 = 0.0f;
+  if (vec8) {   // c % 8 == 0 and every row pointer 16-byte aligned (checked by the launcher)
+    for (int ch = lane * 8; ch < c; ch += 256) {
+      float x[8];
+      support_x8(in_hi, in_lo, in_f32, per, base + ch, ch, x);
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(w2 + ch)), a1 = __ldg(reinterpret_cast<const float4*>(w2 + ch) + 1);
+      d2 += x[0] * a0.x + x[1] * a0.y + x[2] * a0.z + x[3] * a0.w + x[4] * a1.x + x[5] * a1.y + x[6] * a1.z + x[7] * a1.w;
+      if (w1) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(w1 + ch)), c1 = __ldg(reinterpret_cast<const float4*>(w1 + ch) + 1);
+        d1 += x[0] * c0.x + x[1] * c0.y + x[2] * c0.z + x[3] * c0.w + x[4] * c1.x + x[5] * c1.y + x[6] * c1.z + x[7] * c1.w;
+      }
+    }
+  } else {
+    for (int ch = lane; ch < c; ch += 32) {
+      const float x = support_x(in_hi, in_lo, in_f32, per, base + ch, ch);
+      d2 += x * __ldg(w2 + ch);
+      if (w1) d1 += x * __ldg(w1 + ch);
+    }
   }
-  if (wvec) {
-    dot = warp_sum(dot);
-    if (lane == 0) logit[row] = dot + __ldg(wb);
+  d2 = warp_sum(d2);
+  if (w1) d1 = warp_sum(d1);
+  if (lane == 0) {
+    l2[row] = d2 + __ldg(b2);
+    if (w1) l1[row] = d1 + __ldg(b1);
   }
 }
 
-// grid (maps, c/32), block 256: p = softmax_n(logit); wsum[c] = sum_n p_n v[n][c]; colmean[c] = mean_n v[n][c]
-__global__ void __launch_bounds__(256)
-support_softmax_wsum_kernel(const float* __restrict__ v, const float* __restrict__ logit, int ns, int c,
-                            float* __restrict__ wsum, float* __restrict__ colmean) {
-  extern __shared__ float s_p[];  // ns
-  __shared__ float s_red[32];
-  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* lg = logit + static_cast<long long>(m) * ns;
+// softmax weights of one map's logits into shared memory (all threads of the CTA); returns nothing, p[] normalised
+__device__ __forceinline__ void cta_softmax_to_smem(const float* __restrict__ lg, int ns, float* s_p, float* s_red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   float mx = -INFINITY;
   for (int i = tid; i < ns; i += blockDim.x) mx = fmaxf(mx, lg[i]);
   mx = warp_max(mx);
   if (lane == 0) s_red[warp] = mx;
   __syncthreads();
   mx = s_red[0];
-  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, s_red[i]);
+  for (int i = 1; i < nw; ++i) mx = fmaxf(mx, s_red[i]);
   __syncthreads();
   float sum = 0.0f;
   for (int i = tid; i < ns; i += blockDim.x) {
@@ -237,87 +295,138 @@ support_softmax_wsum_kernel(const float* __restrict__ v, const float* __restrict
   if (lane == 0) s_red[warp] = sum;
   __syncthreads();
   sum = 0.0f;
-  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += s_red[i];
+  for (int i = 0; i < nw; ++i) sum += s_red[i];
   const float inv = 1.0f / sum;
   __syncthreads();
-  // this CTA's 32-channel slab: lane = channel (128-byte coalesced rows), 8 warps stride the positions
-  __shared__ float s_a[8][33], s_m[8][33];
-  const int ch = blockIdx.y * 32 + lane;
-  const float* vm = v + static_cast<long long>(m) * ns * c;
-  float a = 0.0f, mean = 0.0f;
-  if (ch < c) {
-    for (int n = warp; n < ns; n += 8) {
-      const float x = vm[static_cast<long long>(n) * c + ch];
-      a += (s_p[n] * inv) * x;
-      mean += x;
+  for (int i = tid; i < ns; i += blockDim.x) s_p[i] *= inv;
+  __syncthreads();
+}
+
+// grid (maps, ceil(c / 64)), block 256: lane = 2 channels of the CTA's 64-channel slab, 8 warps stride the positions
+__global__ void __launch_bounds__(256)
+support_wsum2_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                     const float* __restrict__ in_f32, const float* __restrict__ pe, int ns, int c,
+                     const float* __restrict__ l1, const float* __restrict__ l2, float gamma, float* __restrict__ g,
+                     float* __restrict__ r, float* __restrict__ colmean) {
+  extern __shared__ float s_dyn2[];     // p1[ns], p2[ns]
+  __shared__ float s_red[32];
+  __shared__ float s_acc[8][3][64];
+  float* s_p1 = s_dyn2;
+  float* s_p2 = s_dyn2 + ns;
+  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (l1) cta_softmax_to_smem(l1 + static_cast<long long>(m) * ns, ns, s_p1, s_red);
+  cta_softmax_to_smem(l2 + static_cast<long long>(m) * ns, ns, s_p2, s_red);
+  const int ch = blockIdx.y * 64 + lane * 2;
+  float a1[2] = {0.f, 0.f}, a2[2] = {0.f, 0.f}, mean[2] = {0.f, 0.f};
+  const long long mbase = static_cast<long long>(m) * ns * c;
+  for (int n = warp; n < ns; n += 8) {
+    const float* per = pe ? pe + static_cast<long long>(n) * c : nullptr;
+    const float p1 = l1 ? s_p1[n] : 0.0f, p2 = s_p2[n];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (ch + e < c) {
+        const float x = support_x(in_hi, in_lo, in_f32, per, mbase + static_cast<long long>(n) * c + ch + e, ch + e);
+        a1[e] += p1 * x;
+        a2[e] += p2 * x;
+        mean[e] += x;
+      }
     }
   }
-  s_a[warp][lane] = a;
-  s_m[warp][lane] = mean;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    s_acc[warp][0][lane * 2 + e] = a1[e];
+    s_acc[warp][1][lane * 2 + e] = a2[e];
+    s_acc[warp][2][lane * 2 + e] = mean[e];
+  }
   __syncthreads();
-  if (warp == 0 && ch < c) {
-    float ta = 0.0f, tm = 0.0f;
+  if (tid < 64 && blockIdx.y * 64 + tid < c) {
+    float t1 = 0.f, t2 = 0.f, tm = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      ta += s_a[i][lane];
-      tm += s_m[i][lane];
+      t1 += s_acc[i][0][tid];
+      t2 += s_acc[i][1][tid];
+      tm += s_acc[i][2][tid];
     }
-    if (wsum) wsum[static_cast<long long>(m) * c + ch] = ta;
-    if (colmean) colmean[static_cast<long long>(m) * c + ch] = tm / static_cast<float>(ns);
+    const long long o = static_cast<long long>(m) * c + blockIdx.y * 64 + tid;
+    float h = 0.0f;
+    if (l1) {
+      g[o] = t1;
+      h = gamma * (t1 > 0.0f ? t1 : 0.01f * t1);
+    }
+    r[o] = t2 + h;                       // u^T V' = u^T V + h
+    colmean[o] = tm / static_cast<float>(ns);
   }
 }
 
-// warp per row: v[row] += gamma * leaky_relu(g[map]) (in place); logit[row] = v . wvec + wb
-__global__ void support_enhance_logit_kernel(float* __restrict__ v, const float* __restrict__ g, float gamma, int rows,
-                                             int ns, int c, const float* __restrict__ wvec,
-                                             const float* __restrict__ wb, float* __restrict__ logit) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const long long base = static_cast<long long>(row) * c;
-  const float* gm = g ? g + static_cast<long long>(row / ns) * c : nullptr;
-  float dot = 0.0f;
-  for (int ch = lane; ch < c; ch += 32) {
-    float x = v[base + ch];
-    if (gm) {
-      const float gg = gm[ch];
-      x += gamma * (gg > 0.0f ? gg : 0.01f * gg);
-      v[base + ch] = x;
-    }
-    dot += x * __ldg(wvec + ch);
-  }
-  dot = warp_sum(dot);
-  if (lane == 0) logit[row] = dot + __ldg(wb);
-}
-
-// Vc = v - colmean -> bf16 pair [rows][c];  v^T -> bf16 pair vt[set][c][slot*ns_pitch... + n]
-// vt layout: vt[(map / shots)][ch][ (map % shots) * ns + n ] with row pitch vt_pitch
-// grid: (ceil(ns/32), ceil(c/32), maps), block (32, 8)
-__global__ void support_finalize_kernel(const float* __restrict__ v, const float* __restrict__ colmean, int ns, int c,
-                                        int shots, int seg_pitch, long long vt_pitch, __nv_bfloat16* __restrict__ vc_hi,
-                                        __nv_bfloat16* __restrict__ vc_lo, __nv_bfloat16* __restrict__ vt_hi,
-                                        __nv_bfloat16* __restrict__ vt_lo) {
-  __shared__ float tile[32][33];
+// Vc = V - colmean -> bf16 pair [rows][c];  V'^T = (V + h)^T -> bf16 pair vt[set][ch][slot * seg_pitch + n]
+// grid (ceil(ns / 64), ceil(c / 64), maps), block 256; 64 x 64 tiles, two elements per lane on both sides so that
+// every store is a 4-byte bf16 pair (128 bytes per warp and row)
+__global__ void __launch_bounds__(256)
+support_finalize2_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                         const float* __restrict__ in_f32, const float* __restrict__ pe,
+                         const float* __restrict__ colmean, const float* __restrict__ g, float gamma, int ns, int c,
+                         int shots, int seg_pitch, long long vt_pitch, __nv_bfloat16* __restrict__ vc_hi,
+                         __nv_bfloat16* __restrict__ vc_lo, __nv_bfloat16* __restrict__ vt_hi,
+                         __nv_bfloat16* __restrict__ vt_lo) {
+  __shared__ float tile[64][65];
   const int m = blockIdx.z;
-  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const float* vm = v + static_cast<long long>(m) * ns * c;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int n = n0 + i, ch = c0 + threadIdx.x;
-    float x = 0.0f;
-    if (n < ns && ch < c) {
-      x = vm[static_cast<long long>(n) * c + ch];
-      const long long o = (static_cast<long long>(m) * ns + n) * c + ch;
-      st_pair(vc_hi, vc_lo, o, x - colmean[static_cast<long long>(m) * c + ch]);
+  const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long mbase = static_cast<long long>(m) * ns * c;
+  const bool vec = ((c & 1) == 0);
+  for (int i = warp; i < 64; i += 8) {
+    const int n = n0 + i;
+    const int ch = c0 + lane * 2;
+    float x[2] = {0.f, 0.f};
+    if (n < ns) {
+      const float* per = pe ? pe + static_cast<long long>(n) * c : nullptr;
+      const long long o = mbase + static_cast<long long>(n) * c + ch;
+      float d[2] = {0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (ch + e < c) {
+          x[e] = support_x(in_hi, in_lo, in_f32, per, o + e, ch + e);
+          d[e] = x[e] - colmean[static_cast<long long>(m) * c + ch + e];
+        }
+      }
+      if (vec && ch + 1 < c) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(d[0], h0, l0);
+        split_bf16(d[1], h1, l1);
+        *reinterpret_cast<uint32_t*>(vc_hi + o) = pack_bf16x2(h0, h1);
+        if (vc_lo) *reinterpret_cast<uint32_t*>(vc_lo + o) = pack_bf16x2(l0, l1);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (ch + e < c) st_pair(vc_hi, vc_lo, o + e, d[e]);
+      }
     }
-    tile[i][threadIdx.x] = x;
+    tile[i][lane * 2] = x[0];
+    tile[i][lane * 2 + 1] = x[1];
   }
   __syncthreads();
   const int set = m / shots, slot = m % shots;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int ch = c0 + i, n = n0 + threadIdx.x;
-    if (ch < c && n < ns) {
-      const long long o = (static_cast<long long>(set) * c + ch) * vt_pitch + static_cast<long long>(slot) * seg_pitch + n;
-      st_pair(vt_hi, vt_lo, o, tile[threadIdx.x][i]);
+  const bool vec_t = ((seg_pitch & 1) == 0) && ((vt_pitch & 1) == 0);
+  for (int i = warp; i < 64; i += 8) {
+    const int ch = c0 + i;
+    if (ch >= c) continue;
+    float h = 0.0f;
+    if (g) {
+      const float gg = g[static_cast<long long>(m) * c + ch];
+      h = gamma * (gg > 0.0f ? gg : 0.01f * gg);
+    }
+    const int n = n0 + lane * 2;
+    const long long o = (static_cast<long long>(set) * c + ch) * vt_pitch + static_cast<long long>(slot) * seg_pitch + n;
+    const float v0 = tile[lane * 2][i] + h, v1 = tile[lane * 2 + 1][i] + h;
+    if (vec_t && n + 1 < ns) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v0, h0, l0);
+      split_bf16(v1, h1, l1);
+      *reinterpret_cast<uint32_t*>(vt_hi + o) = pack_bf16x2(h0, h1);
+      if (vt_lo) *reinterpret_cast<uint32_t*>(vt_lo + o) = pack_bf16x2(l0, l1);
+    } else {
+      if (n < ns) st_pair(vt_hi, vt_lo, o, v0);
+      if (n + 1 < ns) st_pair(vt_hi, vt_lo, o + 1, v1);
     }
   }
 }

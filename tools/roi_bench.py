@@ -20,6 +20,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--sweep", action="store_true", help="also time the fp32 NHWC kernel per RoI size class")
+ap.add_argument("--side", type=int, default=0, help="square RoIs of this side (pixels) instead of the mixture")
+ap.add_argument("--no-flush", action="store_true", help="leave L2 warm between iterations (diagnostic)")
 ap.add_argument("--only", default="", help="run only the named variant (nchw|pair|head|f32) -- for ncu captures")
 a = ap.parse_args()
 b, c, h, w = a.batch, 1024, 38, 63
@@ -31,6 +33,10 @@ cx, cy = rs.uniform(0, 1000, r), rs.uniform(0, 600, r)
 bw, bh = np.exp(rs.uniform(np.log(16), np.log(600), r)), np.exp(rs.uniform(np.log(16), np.log(500), r))
 rois = np.stack([np.repeat(np.arange(b), 300), np.clip(cx - bw / 2, 0, 999), np.clip(cy - bh / 2, 0, 599),
                  np.clip(cx + bw / 2, 0, 999), np.clip(cy + bh / 2, 0, 599)], 1).astype(np.float32)
+if a.side > 0:
+    hh = min(a.side, 599)
+    cx, cy = rs.uniform(a.side / 2, 1000 - a.side / 2, r), rs.uniform(hh / 2, 600 - hh / 2, r)
+    rois = np.stack([np.repeat(np.arange(b), 300), cx - a.side / 2, cy - hh / 2, cx + a.side / 2, cy + hh / 2], 1).astype(np.float32)
 rois = torch.from_numpy(rois).cuda()
 nhwc = feat.permute(0, 2, 3, 1).contiguous()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -40,6 +46,8 @@ flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
 def l2_flush():
     """Write a 256 MiB buffer (evicts everything), then READ another 256 MiB one: the write alone leaves ~126 MB of
     dirty lines in L2 whose write-back would land inside the timed region of a write-bound kernel and be billed to it."""
+    if a.no_flush:
+        return
     flush.zero_()
     flush_rd.sum()
 
@@ -92,6 +100,13 @@ ms = timeit(lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, want_f32=True, w
 print("roi_align_head NHWC -> fp32 [R,7,7,C]:                              %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
       (ms, alg_bytes / ms / 1e6, alg_bytes / 1e6))
 print("fraction of the measured HBM peak (%.0f GB/s): %.1f %%" % (peak, 100 * alg_bytes / ms / 1e6 / peak))
+# reference points under the same protocol: what a pure write / a copy of the output-sized buffer achieves
+_o = torch.empty((r, 7, 7, c), device="cuda")
+_o2 = torch.empty((r, 7, 7, c), device="cuda")
+ms = timeit(lambda: _o.zero_())
+print("reference: memset of the %.0f MB output (pure write): %.4f ms  %.0f GB/s" % (_o.numel() * 4 / 1e6, ms, _o.numel() * 4 / ms / 1e6))
+ms = timeit(lambda: _o.copy_(_o2))
+print("reference: copy of the output (read + write, %.0f MB moved): %.4f ms  %.0f GB/s" % (_o.numel() * 8 / 1e6, ms, _o.numel() * 8 / ms / 1e6))
 if a.sweep:
     # the gather cost of an RoI grows with its area (adaptive sampling visits every feature pixel it covers), the
     # output does not: per size class, where the kernel is write-bound and where it is gather-bound
