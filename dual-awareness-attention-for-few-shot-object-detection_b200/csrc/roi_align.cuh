@@ -314,13 +314,16 @@ __device__ __forceinline__ void roi7_row_pass(const float* __restrict__ rowp, in
   }
 }
 
+// writes bin row `ph`: value = (w0 * a + w1 * b) / count   (general order: w0 = 1, w1 = 0)
 template <int MODE>
-__device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, float inv_count, const float2 (&acc)[7][2],
-                                          const Roi7Out& o, float* s_stage, int tid) {
-  const float2 ic = f2(inv_count, inv_count);
+__device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, float inv_count, const float2 (&a)[7][2],
+                                          const float2 (&b)[7][2], float w0, float w1, const Roi7Out& o, float* s_stage,
+                                          int tid) {
+  const float2 k0 = f2(w0 * inv_count, w0 * inv_count), k1 = f2(w1 * inv_count, w1 * inv_count);
 #pragma unroll
   for (int pw = 0; pw < 7; ++pw) {
-    const float2 v0 = __fmul2_rn(acc[pw][0], ic), v1 = __fmul2_rn(acc[pw][1], ic);
+    const float2 v0 = __ffma2_rn(b[pw][0], k1, __fmul2_rn(a[pw][0], k0));
+    const float2 v1 = __ffma2_rn(b[pw][1], k1, __fmul2_rn(a[pw][1], k0));
     const float v[4] = {v0.x, v0.y, v1.x, v1.y};
     const int bin = ph * 7 + pw;
     if constexpr (MODE == 1) {
@@ -339,36 +342,59 @@ __device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, f
   }
 }
 
-// The y loop: bins in order, two accumulator sets (current bin, next bin); in rolling order a map row shared with
-// the next bin is added to both sets; see the header comment.  ONE copy of the loop nest, with the compiled tap
-// count selected by a uniform switch around the row pass only: the per-CTA instruction footprint stays a few KB
-// (an earlier version instantiated the whole nest per tap count and spent 40 % of its stall samples on
-// instruction fetch, ncu `stalled_no_instructions`).
+// The y loop: bins in order, two register sets.  Three orders, chosen per RoI (uniform):
+//   rolling   (no map row feeds three bins; every RoI taller than ~14 feature rows): the sets accumulate the current
+//             and the next bin, a row shared by both is read once and added to both;
+//   two-row   (every bin has <= 2 row taps, i.e. grid_h == 1, RoIs up to 112 px tall): the sets CACHE the x passes of
+//             two map rows (tagged with their row index); a bin is w0 * row(l) + w1 * row(l + 1), and since l advances
+//             by 0 or 1 from bin to bin every window row is passed once (3..8 passes instead of 14);
+//   per-bin   otherwise: each bin passes its own rows.
+// ONE copy of the loop nest and ONE call site of the row pass, with the compiled tap count selected by a uniform
+// switch: the per-CTA instruction footprint stays a few KB (an earlier version instantiated the whole nest per tap
+// count and spent 40 % of its stall samples on instruction fetch, ncu `stalled_no_instructions`).
 template <int CH, int MODE>
 __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int channels, int width, const Roi7Tables& s,
-                                            int taps, bool rolling, int r, int c0, float inv_count, const Roi7Out& o,
+                                            int taps, int order, int r, int c0, float inv_count, const Roi7Out& o,
                                             float* s_stage, int tid) {
+  const bool rolling = order == 1, tworow = order == 2;
   const long long row_pitch = static_cast<long long>(width) * (CH ? CH : channels);
   float2 ca[7][2], na[7][2];
 #pragma unroll
   for (int pw = 0; pw < 7; ++pw) ca[pw][0] = ca[pw][1] = na[pw][0] = na[pw][1] = f2(0.f, 0.f);
   int y = 0;
+  int tag0 = -1, tag1 = -1;   // two-row order: map rows whose x pass sits in ca / na
 #pragma unroll 1
   for (int cur = 0; cur < 7; ++cur) {
     const int ylo_c = s.ylo[cur];
-    const int yend = ylo_c + s.ny[cur];
+    const int nyc = s.ny[cur];
+    const int yend = ylo_c + nyc;
     y = rolling ? max(y, ylo_c) : ylo_c;
     int nlo = 0x3fffffff, nn = 0;
     if (rolling && cur < 6) {
       nlo = s.ylo[cur + 1];
       nn = s.ny[cur + 1];
     }
+    if (tworow && nyc > 0 && tag0 != ylo_c && tag1 == ylo_c) {   // the row cached in `na` becomes this bin's first row
+#pragma unroll
+      for (int pw = 0; pw < 7; ++pw) {
+        ca[pw][0] = na[pw][0];
+        ca[pw][1] = na[pw][1];
+      }
+      tag0 = ylo_c;
+      tag1 = -1;
+    }
 #pragma unroll 1
     for (; y < yend; ++y) {
-      const float wa = s.wy[cur][y - ylo_c];
-      const int d = y - nlo;
-      const float wb = (d >= 0 && d < nn) ? s.wy[cur + 1][d] : 0.0f;
-      if (wa == 0.0f && wb == 0.0f) continue;
+      float wa = 0.0f, wb = 0.0f;
+      const bool first = (y == ylo_c);
+      if (tworow) {
+        if (first ? (tag0 == y) : (tag1 == y)) continue;      // already cached
+      } else {
+        wa = s.wy[cur][y - ylo_c];
+        const int d = y - nlo;
+        wb = (d >= 0 && d < nn) ? s.wy[cur + 1][d] : 0.0f;
+        if (wa == 0.0f && wb == 0.0f) continue;
+      }
       float2 rs[7][2];
       const float* rowp = fbase + static_cast<long long>(y) * row_pitch;
       switch (taps) {
@@ -380,6 +406,24 @@ __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int
         case 12: roi7_row_pass<12, CH>(rowp, channels, s, rs); break;
         case 16: roi7_row_pass<16, CH>(rowp, channels, s, rs); break;
         default: roi7_row_pass<0, CH>(rowp, channels, s, rs); break;
+      }
+      if (tworow) {
+        if (first) {
+#pragma unroll
+          for (int pw = 0; pw < 7; ++pw) {
+            ca[pw][0] = rs[pw][0];
+            ca[pw][1] = rs[pw][1];
+          }
+          tag0 = y;
+        } else {
+#pragma unroll
+          for (int pw = 0; pw < 7; ++pw) {
+            na[pw][0] = rs[pw][0];
+            na[pw][1] = rs[pw][1];
+          }
+          tag1 = y;
+        }
+        continue;
       }
       const float2 wa2 = f2(wa, wa);
 #pragma unroll
@@ -396,12 +440,18 @@ __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int
         }
       }
     }
-    roi7_emit<MODE>(r, cur, c0, channels, inv_count, ca, o, s_stage, tid);
+    if (tworow) {
+      const float w0 = nyc > 0 ? s.wy[cur][0] : 0.0f;
+      const float w1 = nyc > 1 ? s.wy[cur][1] : 0.0f;
+      roi7_emit<MODE>(r, cur, c0, channels, inv_count, ca, na, w0, w1, o, s_stage, tid);
+    } else {
+      roi7_emit<MODE>(r, cur, c0, channels, inv_count, ca, na, 1.0f, 0.0f, o, s_stage, tid);
 #pragma unroll
-    for (int pw = 0; pw < 7; ++pw) {
-      ca[pw][0] = na[pw][0];
-      ca[pw][1] = na[pw][1];
-      na[pw][0] = na[pw][1] = f2(0.f, 0.f);
+      for (int pw = 0; pw < 7; ++pw) {
+        ca[pw][0] = na[pw][0];
+        ca[pw][1] = na[pw][1];
+        na[pw][0] = na[pw][1] = f2(0.f, 0.f);
+      }
     }
   }
 }
@@ -449,7 +499,10 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
     for (int p = 0; p + 2 < 7; ++p)
       if (s.ny[p] > 0 && s.ny[p + 2] > 0 && s.ylo[p + 2] < s.ylo[p] + s.ny[p]) ok = false;
     // bins must be ordered (empty bins in the middle of an RoI cannot occur: validity is monotone at each border)
-    s_rolling = ok ? 1 : 0;
+    bool small = true;          // two-row order: every bin has at most two row taps
+    for (int p = 0; p < 7; ++p)
+      if (s.ny[p] > 2) small = false;
+    s_rolling = small ? 2 : (ok ? 1 : 0);
     s_t = t;
   }
   __syncthreads();
@@ -457,9 +510,8 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
   const bool c_ok = c0 < channels;
   const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
   const float* fbase = feat + static_cast<long long>(g.batch_ind) * height * width * channels + (c_ok ? c0 : 0);
-  const bool rolling = s_rolling != 0;
   if (c_ok || MODE == 1) {
-    roi7_gather<CH, MODE>(fbase, channels, width, s, s_t, rolling, r, c0, inv_count, o, s_stage, tid);
+    roi7_gather<CH, MODE>(fbase, channels, width, s, s_t, s_rolling, r, c0, inv_count, o, s_stage, tid);
   }
   if constexpr (MODE == 1) {
     __syncthreads();
