@@ -245,7 +245,9 @@ __device__ __forceinline__ void build_axis_compact(float* w /*[kRoiTaps]*/, int*
     hi = h;
   }
   *lo_out = lo < 0 ? 0 : lo;
-  *n_out = lo < 0 ? 0 : min(hi - lo + 1, kRoiTaps);
+  // a bin of more than kRoiTaps - 2 map pixels does not fit the table; the kernel sends such RoIs to the direct path
+  // before the tables are built (bin > 14), so the marker kRoiTaps + 1 below is a guard that never fires
+  *n_out = lo < 0 ? 0 : (hi - lo + 1 > kRoiTaps ? kRoiTaps + 1 : hi - lo + 1);
 }
 
 struct Roi7Tables {
@@ -456,6 +458,62 @@ __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int
   }
 }
 
+// Direct form for RoIs whose bins do not fit the tap tables (only RoIs several times larger than the map, which the
+// proposal layer never emits but the operator boundary accepts): every grid sample is evaluated as in
+// ROIAlign_cpu.cpp:56-109, four taps each.  Correct for any geometry, not tuned.  The kernel branches to it right
+// after the geometry, before any table state is live (branching later, next to the gather, cost the common path
+// 30 % in register spills; a second launch for these RoIs cost 7 %).
+template <int MODE>
+__device__ __forceinline__ void roi7_direct(const float* __restrict__ fbase, int channels, int height, int width,
+                                         const RoiGeom& g, int r, int c0, float inv_count, const Roi7Out& o,
+                                         float* s_stage, int tid) {
+  const long long cs = channels;
+  for (int ph = 0; ph < 7; ++ph) {
+    float2 acc[7][2];
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw) acc[pw][0] = acc[pw][1] = f2(0.f, 0.f);
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const float y = sample_coord(g.start_h, g.bin_h, ph, iy, g.grid_h);
+      int yl, yh;
+      float wyl, wyh;
+      if (!axis_taps(y, height, yl, yh, wyl, wyh)) continue;
+#pragma unroll
+      for (int pw = 0; pw < 7; ++pw) {
+        for (int ix = 0; ix < g.grid_w; ++ix) {
+          const float x = sample_coord(g.start_w, g.bin_w, pw, ix, g.grid_w);
+          int xl, xh;
+          float wxl, wxh;
+          if (!axis_taps(x, width, xl, xh, wxl, wxh)) continue;
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(fbase + (static_cast<long long>(yl) * width + xl) * cs));
+          const float4 v2 = __ldg(reinterpret_cast<const float4*>(fbase + (static_cast<long long>(yl) * width + xh) * cs));
+          const float4 v3 = __ldg(reinterpret_cast<const float4*>(fbase + (static_cast<long long>(yh) * width + xl) * cs));
+          const float4 v4 = __ldg(reinterpret_cast<const float4*>(fbase + (static_cast<long long>(yh) * width + xh) * cs));
+          const float w1 = wyl * wxl, w2 = wyl * wxh, w3 = wyh * wxl, w4 = wyh * wxh;
+          acc[pw][0].x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+          acc[pw][0].y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+          acc[pw][1].x += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+          acc[pw][1].y += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+        }
+      }
+    }
+    roi7_emit<MODE>(r, ph, c0, channels, inv_count, acc, acc, 1.0f, 0.0f, o, s_stage, tid);
+  }
+}
+
+// MODE 1: [R][C][49] -- this CTA's channels are one contiguous run of the output
+__device__ __forceinline__ void roi7_copy_out(const Roi7Out& o, int r, int channels, const float* s_stage, int tid) {
+  const int cbase = blockIdx.y * kRoi7Threads * 4;
+  const int nch = min(kRoi7Threads * 4, channels - cbase);
+  float* dst = o.out + (static_cast<long long>(r) * channels + cbase) * 49;
+  const int total = nch * 49;
+  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    for (int i = tid; i < total / 4; i += kRoi7Threads)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_stage)[i];
+  } else {
+    for (int i = tid; i < total; i += kRoi7Threads) dst[i] = s_stage[i];
+  }
+}
+
 // grid (num_rois, ceil(C / 512)), block 128.  MODE 0: NHWC outputs; MODE 1: [R][C][49] via shared memory.
 template <int MODE, int CH, int OCC = (MODE == 1 ? 2 : 4)>
 __global__ void __launch_bounds__(kRoi7Threads, OCC)
@@ -468,16 +526,35 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
   if (tid == 0) s.g = roi_geometry(rois + static_cast<long long>(r) * 5, spatial_scale, 7, 7, sampling_ratio);
   __syncthreads();
   const RoiGeom g = s.g;
+  if (g.bin_w > 14.0f || g.bin_h > 14.0f) {
+    // bins that may not fit the 16-tap tables (an RoI much larger than the map): direct sampling, decided before any
+    // of the table machinery is live
+    const int c0d = (blockIdx.y * kRoi7Threads + tid) * 4;
+    const bool okd = c0d < channels;
+    const float* fb = feat + static_cast<long long>(g.batch_ind) * height * width * channels + (okd ? c0d : 0);
+    if (okd || MODE == 1)
+      roi7_direct<MODE>(fb, channels, height, width, g, r, c0d, 1.0f / static_cast<float>(g.grid_h * g.grid_w), o, s_stage, tid);
+    if constexpr (MODE == 1) {
+      __syncthreads();
+      roi7_copy_out(o, r, channels, s_stage, tid);
+    }
+    return;
+  }
   if (tid < 7) build_axis_compact(s.wy[tid], &s.ylo[tid], &s.ny[tid], tid, height, g.start_h, g.bin_h, g.grid_h);
   if (tid >= 32 && tid < 39)
     build_axis_compact(s.wx[tid - 32], &s.xlo[tid - 32], &s.nx[tid - 32], tid - 32, width, g.start_w, g.bin_w, g.grid_w);
   __syncthreads();
   // compiled tap count T >= widest bin; 0 = dynamic loops (map narrower than the compiled size)
-  int maxn = 0;
+  int maxn = 0, maxny = 0;
 #pragma unroll
-  for (int pw = 0; pw < 7; ++pw) maxn = max(maxn, s.nx[pw]);
+  for (int pw = 0; pw < 7; ++pw) {
+    maxn = max(maxn, s.nx[pw]);
+    maxny = max(maxny, s.ny[pw]);
+  }
+  const bool overflow = maxn > kRoiTaps || maxny > kRoiTaps;   // uniform: read from shared memory by every thread
   int t = maxn <= 2 ? 2 : maxn <= 3 ? 3 : maxn <= 4 ? 4 : maxn <= 6 ? 6 : maxn <= 8 ? 8 : maxn <= 12 ? 12 : 16;
   if (t > width) t = 0;
+  if (overflow) t = 0;
   if (t > 0 && tid >= 32 && tid < 39) {
     // shift this bin's tap window left so that xlo + t <= width: padding taps read valid pixels with zero weight
     const int pw = tid - 32;
@@ -510,22 +587,12 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
   const bool c_ok = c0 < channels;
   const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
   const float* fbase = feat + static_cast<long long>(g.batch_ind) * height * width * channels + (c_ok ? c0 : 0);
-  if (c_ok || MODE == 1) {
+  if ((c_ok || MODE == 1) && !overflow) {   // (overflow cannot occur past the early branch: bins <= 14 px -> <= 16 taps)
     roi7_gather<CH, MODE>(fbase, channels, width, s, s_t, s_rolling, r, c0, inv_count, o, s_stage, tid);
   }
   if constexpr (MODE == 1) {
     __syncthreads();
-    // [R][C][49]: this CTA's channels are one contiguous run
-    const int cbase = blockIdx.y * kRoi7Threads * 4;
-    const int nch = min(kRoi7Threads * 4, channels - cbase);
-    float* dst = o.out + (static_cast<long long>(r) * channels + cbase) * 49;
-    const int total = nch * 49;
-    if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      for (int i = tid; i < total / 4; i += kRoi7Threads)
-        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_stage)[i];
-    } else {
-      for (int i = tid; i < total; i += kRoi7Threads) dst[i] = s_stage[i];
-    }
+    roi7_copy_out(o, r, channels, s_stage, tid);
   }
 }
 
@@ -567,9 +634,10 @@ inline int roi_align7_launch(const float* feat_nhwc, const float* rois, int num_
   return DANA_OK;
 }
 
-// adaptive sampling: a bin of more than 14 feature pixels does not fit the 16-tap tables
-inline bool roi_align7_supported(int channels, int height, int width, int sampling_ratio) {
-  return channels % 4 == 0 && (sampling_ratio > 0 ? sampling_ratio <= 7 : (height <= 7 * 14 && width <= 7 * 14));
+// (bins that do not fit the 16-tap tables -- maps larger than 98 pixels, RoIs larger than the map -- are handled
+// per RoI by the direct path)
+inline bool roi_align7_supported(int channels, int /*height*/, int /*width*/, int /*sampling_ratio*/) {
+  return channels % 4 == 0;
 }
 
 inline int roi_align_head_run(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels,

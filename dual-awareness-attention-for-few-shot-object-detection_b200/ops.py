@@ -267,7 +267,7 @@ def roi_align_forward(inp, rois, spatial_scale, pooled_h, pooled_w, sampling_rat
     lib = _lib.load()
     wsb = lib.dana_roi_align_workspace_bytes(b, c, h, w, 0)
     ws = torch.empty((wsb,), dtype=torch.uint8, device=inp.device)
-    _count(2)
+    _count(2)                                                                  # transpose + gather
     check(lib.dana_roi_align_forward(_p(inp), _p(rois), r, b, c, h, w, pooled_h, pooled_w, float(spatial_scale),
                                      int(sampling_ratio), 0, _p(out), None, None, _p(ws), wsb, _stream()),
           "dana_roi_align_forward")
@@ -397,7 +397,7 @@ def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b
     vc = Pair.empty((maps * ns, c), dev, split=split)
     vt = Pair.zeros((sets, c, vt_pitch), dev, split=split)
     rbar = torch.empty((sets, c), **f)
-    _count(6)
+    _count(4)                                  # logits, weighted sums, finalize, rbar
     check(_lib.load().dana_support_prepare(in_hi, in_lo, in_f32, _p(pe), maps, shots, ns, c, _p(ba_w), _p(ba_b),
                                            float(gamma), _p(un_w), _p(un_b), float(unary_gamma), _p(v), _p(logit),
                                            _p(g), _p(r), _p(colmean), _p(vc.hi), _p(vc.lo), _p(vt.hi), _p(vt.lo),

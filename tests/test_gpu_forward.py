@@ -154,3 +154,27 @@ def test_support_feature_cache_matches_full_forward(small_case):
     b = eng.forward(im.cuda(), info.cuda(), None, support_feats=cache)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_res101_five_sets_vs_oracle():
+    """BASELINE.json configs[3] in miniature: the res101 trunk (layer3 = 23 blocks) with 5 support sets x 1 shot,
+    every stage against the oracle.  (the reference builds resnet50 for every
+    num_layers and ignores n_way in eval; both generalisations are stated in DESIGN.md.)"""
+    import dana_b200  # noqa: F401
+    from dana_b200.engine import DanaEngine
+    k, sets = 1, 5
+    p = O.make_params(101, num_layers=101, attn_std=0.05)
+    im, info, sup = O.synth_inputs(11, 1, 96, 160, k * sets)
+    with torch.no_grad():
+        ref = O.dana_forward_eval(p, im, info, sup, k, cfg={"num_layers": 101})
+    eng = DanaEngine(p, num_layers=101, n_shot=k, precision="bf16x3")
+    want = ("base_feat", "dense", "pooled", "fc7")
+    rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want,
+                                           teacher={"rois": ref["rois"].cuda()})
+    assert relerr(ex["base_feat"], ref["base_feat"]) <= TOL
+    assert relerr(ex["dense"], ref["dense"]) <= TOL
+    assert relerr(ex["pooled"], ref["pooled"]) <= TOL
+    assert relerr(ex["fc7"], ref["fc7"]) <= TOL
+    assert relerr(bbox, ref["bbox_pred"]) <= TOL
+    assert relerr(cls_prob, ref["cls_prob"]) <= TOL
+    assert tuple(cls_prob.shape) == (sets * 300, 2)

@@ -240,3 +240,28 @@ def test_roi_align_head_fused_outputs(ops):
     assert relerr(pair.float().permute(0, 3, 1, 2), want) <= 2e-5
     want_q = want.reshape(r, 64, 49).transpose(1, 2) + pe.unsqueeze(0)             # [R,49,C]
     assert relerr(qpe.float().reshape(r, 49, 64), want_q) <= 2e-5
+
+
+@pytest.mark.parametrize("b,c,h,w", [(1, 8, 5, 3), (2, 16, 9, 11), (1, 1024, 3, 40), (2, 512, 38, 63)])
+def test_roi_align_orders_and_tiny_maps(ops, b, c, h, w):
+    """Every gather order of the 7x7 kernel (two-row cache for RoIs with <= 2 row taps per bin, rolling for tall RoIs,
+    per-bin in between) and the dynamic tap loop taken when the map is narrower than the compiled tap count, against
+    the oracle: RoI sizes from a fraction of a pixel to several times the map, all three layouts."""
+    rs = np.random.RandomState(b * 100 + c + h + w)
+    feat = rs.standard_normal((b, c, h, w)).astype(np.float32)
+    r = 160
+    iw, ih = w * 16.0, h * 16.0
+    x1, y1 = rs.uniform(-0.2 * iw, iw, r), rs.uniform(-0.2 * ih, ih, r)
+    ww = np.exp(rs.uniform(np.log(0.5), np.log(2.5 * iw), r))
+    hh = np.exp(rs.uniform(np.log(0.5), np.log(2.5 * ih), r))
+    rois = np.stack([rs.randint(0, b, r).astype(np.float64), x1, y1, x1 + ww, y1 + hh], 1).astype(np.float32)
+    want = O.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0)
+    f, rr = torch.from_numpy(feat).cuda(), torch.from_numpy(rois).cuda()
+    assert relerr(ops.roi_align_forward(f, rr, 1.0 / 16, 7, 7, 0), want) <= 1e-5
+    nhwc = f.permute(0, 2, 3, 1).contiguous()
+    if c % 4 == 0:
+        out, _, _ = ops.roi_align_head(nhwc, rr, 1.0 / 16, 0, want_f32=True, want_pair=False, want_qpe=False)
+        assert relerr(out.permute(0, 3, 1, 2), want) <= 1e-5
+    # fixed sampling ratio 2 (grid_h = 2 everywhere: three row taps per bin on small RoIs)
+    want2 = O.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 2)
+    assert relerr(ops.roi_align_forward(f, rr, 1.0 / 16, 7, 7, 2), want2) <= 1e-5
