@@ -48,6 +48,7 @@ struct ConvGemmParams {
   int* sk_flags;        // [grid]
   int sk_epoch;         // value a flag takes when this launch's partial is published; 0 = stream-K off
   int sm_ns, sm_pitch;  // SOFTMAX epilogue: keys per segment, column pitch of a segment in the output
+  int n_fast;           // tile order: 1 = the N-tiles of an M-tile are consecutive work items, 0 = N is the slow index
 };
 
 constexpr int kGemmThreads = 320;
@@ -210,8 +211,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // the activation tile (and, for 3x3 convs, its nine shifted views) is fetched from DRAM once and re-read from
         // L2; the weights are small and L2-resident either way.  (With N slow, every pass over M re-streamed the
         // whole activation: ncu showed 543 MB of DRAM traffic for the 350 MB layer4 conv3, 559 MB for the 136 MB RPN conv.)
-        const int mg = wk / p.tiles_co;
-        const int co_t = wk - mg * p.tiles_co;
+        // (launches that fit one wave -- every tile in flight at once under stream-K -- keep N slow: n_fast = 0)
+        const int mg = p.n_fast ? wk / p.tiles_co : wk % m_groups;
+        const int co_t = p.n_fast ? wk - mg * p.tiles_co : wk / m_groups;
         const int sp = mg * CM + cm_rank;
         const int x0 = (sp % p.tiles_x) * p.bw;
         const int y0 = ((sp / p.tiles_x) % p.tiles_y) * p.bh;
@@ -398,8 +400,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       // once and the warp shares the results
       int co_t = 0, tx0 = 0, ty0 = 0, tn0 = 0;
       if (lane == 0) {
-        const int mg = wk / p.tiles_co;   // N-tile is the fast index (see the producer)
-        co_t = wk - mg * p.tiles_co;
+        const int mg = p.n_fast ? wk / p.tiles_co : wk % m_groups;   // tile order: see the producer
+        co_t = p.n_fast ? wk - mg * p.tiles_co : wk / m_groups;
         const int sp = mg * CM + cm_rank;
         const int txy = p.tiles_x * p.tiles_y;
         const int tn = sp / txy;
@@ -424,8 +426,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (wn < num_work) {
             int nco = 0, nx0 = 0, ny0 = 0, nn0 = 0;
             if (lane == 0) {
-              const int mg = wn / p.tiles_co;
-              nco = wn - mg * p.tiles_co;
+              const int mg = p.n_fast ? wn / p.tiles_co : wn % m_groups;
+              nco = p.n_fast ? wn - mg * p.tiles_co : wn / m_groups;
               const int sp = mg * CM + cm_rank;
               const int txy = p.tiles_x * p.tiles_y;
               const int tn = sp / txy;
