@@ -198,6 +198,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (CM > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (see the launcher): everything above touched only shared memory, TMEM and the
+  // kernel parameters.  Wait for the preceding grids (their global writes are visible afterwards), then let the
+  // next launch in the stream be scheduled as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
