@@ -51,3 +51,44 @@ class EpisodePrefetcher:
             main.wait_event(self.ready[slot])
             yield self.holders[slot]
             self.free[slot].record(main)                     # recorded after the consumer enqueued its work
+
+
+class ResultFetcher:
+    """Device -> host read of a step's results without stalling the GPU: the copies go into pinned host buffers
+    (`depth` rotating sets) right behind the step on the main stream, and the host waits for them only after the
+    NEXT step has been enqueued.  The reference reads every result with blocking `.cpu()` calls (inference.py:104-107),
+    which leaves the GPU idle while python prepares the following step.
+
+        fetch = ResultFetcher(device)
+        pending = None
+        for tensors in prefetcher.run(batches):
+            out = model(*tensors)[:3]
+            ticket = fetch.start(out)            # async D2H of (rois, cls_prob, bbox_pred)
+            if pending is not None:
+                host = fetch.wait(pending)       # results of the previous step, now on the host
+            pending = ticket
+        host = fetch.wait(pending)
+    """
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.buffers = [None] * depth
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.count = 0
+
+    def start(self, tensors):
+        slot = self.count % self.depth
+        self.count += 1
+        if self.buffers[slot] is None or any(b.shape != t.shape or b.dtype != t.dtype
+                                             for b, t in zip(self.buffers[slot], tensors)):
+            self.buffers[slot] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        for dst, src in zip(self.buffers[slot], tensors):
+            dst.copy_(src, non_blocking=True)
+        self.events[slot].record(torch.cuda.current_stream(self.device))
+        return slot
+
+    def wait(self, slot):
+        """Host tensors of the step that `start` returned `slot` for (valid until the slot comes round again)."""
+        self.events[slot].synchronize()
+        return self.buffers[slot]

@@ -41,3 +41,26 @@ def test_graph_replay_equals_eager():
     # same input again gives the same result as the first call (static buffers are refreshed per call)
     for x, y in zip(outs[1][0], outs[1][2]):
         assert torch.equal(x, y)
+
+
+def test_prefetcher_and_result_fetcher_pipeline():
+    """The e2e loop of bench.py in miniature: inputs prefetched H2D on a side stream, results fetched D2H one step late;
+    every step's host results must equal a blocking read of the same step."""
+    import dana_b200  # noqa: F401
+    from dana_b200.pipeline import EpisodePrefetcher, ResultFetcher
+    dev = torch.device("cuda")
+    batches = [(torch.full((64, 33), float(i)).pin_memory(), torch.arange(7, dtype=torch.float32).pin_memory() + i)
+               for i in range(6)]
+    pf, fetch = EpisodePrefetcher(dev), ResultFetcher(dev)
+    got, pending = [], None
+    for a, b in pf.run(iter(batches)):
+        out = (a * 2 + 1, b.sum().reshape(1))
+        ticket = fetch.start(out)
+        if pending is not None:
+            got.append([t.clone() for t in fetch.wait(pending)])
+        pending = ticket
+    got.append([t.clone() for t in fetch.wait(pending)])
+    assert len(got) == 6
+    for i, (x, y) in enumerate(got):
+        assert torch.equal(x, torch.full((64, 33), 2.0 * i + 1))
+        assert float(y) == float(sum(range(7)) + 7 * i)
