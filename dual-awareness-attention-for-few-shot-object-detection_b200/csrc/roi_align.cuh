@@ -344,13 +344,14 @@ __device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, f
   }
 }
 
-// The y loop: bins in order, two register sets.  Three orders, chosen per RoI (uniform):
-//   rolling   (no map row feeds three bins; every RoI taller than ~14 feature rows): the sets accumulate the current
-//             and the next bin, a row shared by both is read once and added to both;
+// The y loop: bins in order, two register sets.  Two orders, chosen per RoI (uniform):
+//   rolling   the sets accumulate the current and the next bin; a map row shared by both is read once and added to
+//             both.  A bin starts at the first row not yet counted for it, or at the first row of the NEXT bin if
+//             that lies lower (rows shared by three bins, RoIs 112..168 px tall, are read twice instead of three
+//             times); window rows of an RoI taller than ~170 px are each read exactly once;
 //   two-row   (every bin has <= 2 row taps, i.e. grid_h == 1, RoIs up to 112 px tall): the sets CACHE the x passes of
 //             two map rows (tagged with their row index); a bin is w0 * row(l) + w1 * row(l + 1), and since l advances
-//             by 0 or 1 from bin to bin every window row is passed once (3..8 passes instead of 14);
-//   per-bin   otherwise: each bin passes its own rows.
+//             by 0 or 1 from bin to bin every window row is passed once (3..8 passes instead of 14).
 // ONE copy of the loop nest and ONE call site of the row pass, with the compiled tap count selected by a uniform
 // switch: the per-CTA instruction footprint stays a few KB (an earlier version instantiated the whole nest per tap
 // count and spent 40 % of its stall samples on instruction fetch, ncu `stalled_no_instructions`).
@@ -358,24 +359,26 @@ template <int CH, int MODE>
 __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int channels, int width, const Roi7Tables& s,
                                             int taps, int order, int r, int c0, float inv_count, const Roi7Out& o,
                                             float* s_stage, int tid) {
-  const bool rolling = order == 1, tworow = order == 2;
+  const bool tworow = order == 2;
   const long long row_pitch = static_cast<long long>(width) * (CH ? CH : channels);
   float2 ca[7][2], na[7][2];
 #pragma unroll
   for (int pw = 0; pw < 7; ++pw) ca[pw][0] = ca[pw][1] = na[pw][0] = na[pw][1] = f2(0.f, 0.f);
-  int y = 0;
+  int y_cont = 0;             // rolling order: map rows below y_cont are already accumulated in `ca`
   int tag0 = -1, tag1 = -1;   // two-row order: map rows whose x pass sits in ca / na
 #pragma unroll 1
   for (int cur = 0; cur < 7; ++cur) {
     const int ylo_c = s.ylo[cur];
     const int nyc = s.ny[cur];
     const int yend = ylo_c + nyc;
-    y = rolling ? max(y, ylo_c) : ylo_c;
     int nlo = 0x3fffffff, nn = 0;
-    if (rolling && cur < 6) {
+    if (!tworow && cur < 6 && s.ny[cur + 1] > 0) {
       nlo = s.ylo[cur + 1];
       nn = s.ny[cur + 1];
     }
+    // rolling: continue below the last row already counted for this bin, but not past the first row of the next bin
+    // (a row that the bin before last also used is read again, for the next bin only)
+    int y = tworow ? ylo_c : max(ylo_c, min(y_cont, nlo));
     if (tworow && nyc > 0 && tag0 != ylo_c && tag1 == ylo_c) {   // the row cached in `na` becomes this bin's first row
 #pragma unroll
       for (int pw = 0; pw < 7; ++pw) {
@@ -392,7 +395,7 @@ __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int
       if (tworow) {
         if (first ? (tag0 == y) : (tag1 == y)) continue;      // already cached
       } else {
-        wa = s.wy[cur][y - ylo_c];
+        wa = (y >= y_cont) ? s.wy[cur][y - ylo_c] : 0.0f;
         const int d = y - nlo;
         wb = (d >= 0 && d < nn) ? s.wy[cur + 1][d] : 0.0f;
         if (wa == 0.0f && wb == 0.0f) continue;
@@ -448,6 +451,7 @@ __device__ __forceinline__ void roi7_gather(const float* __restrict__ fbase, int
       roi7_emit<MODE>(r, cur, c0, channels, inv_count, ca, na, w0, w1, o, s_stage, tid);
     } else {
       roi7_emit<MODE>(r, cur, c0, channels, inv_count, ca, na, 1.0f, 0.0f, o, s_stage, tid);
+      y_cont = max(y_cont, yend);
 #pragma unroll
       for (int pw = 0; pw < 7; ++pw) {
         ca[pw][0] = na[pw][0];
@@ -571,15 +575,10 @@ roi_align7_kernel(const float* __restrict__ feat /*NHWC*/, const float* __restri
     for (int k = 0; k < kRoiTaps; ++k) s.wx2[tid - 32][k] = make_float2(s.wx[tid - 32][k], s.wx[tid - 32][k]);
   }
   if (tid == 0) {
-    // rolling order is valid when no map row feeds three bins: first row of bin p+2 lies past the last row of bin p
-    bool ok = true;
-    for (int p = 0; p + 2 < 7; ++p)
-      if (s.ny[p] > 0 && s.ny[p + 2] > 0 && s.ylo[p + 2] < s.ylo[p] + s.ny[p]) ok = false;
-    // bins must be ordered (empty bins in the middle of an RoI cannot occur: validity is monotone at each border)
     bool small = true;          // two-row order: every bin has at most two row taps
     for (int p = 0; p < 7; ++p)
       if (s.ny[p] > 2) small = false;
-    s_rolling = small ? 2 : (ok ? 1 : 0);
+    s_rolling = small ? 2 : 1;
     s_t = t;
   }
   __syncthreads();

@@ -244,8 +244,8 @@ def test_roi_align_head_fused_outputs(ops):
 
 @pytest.mark.parametrize("b,c,h,w", [(1, 8, 5, 3), (2, 16, 9, 11), (1, 1024, 3, 40), (2, 512, 38, 63)])
 def test_roi_align_orders_and_tiny_maps(ops, b, c, h, w):
-    """Every gather order of the 7x7 kernel (two-row cache for RoIs with <= 2 row taps per bin, rolling for tall RoIs,
-    per-bin in between) and the dynamic tap loop taken when the map is narrower than the compiled tap count, against
+    """Every gather order of the 7x7 kernel (two-row cache for RoIs with <= 2 row taps per bin, rolling otherwise, the
+    direct path for RoIs larger than the map) and the dynamic tap loop taken when the map is narrower than the compiled tap count, against
     the oracle: RoI sizes from a fraction of a pixel to several times the map, all three layouts."""
     rs = np.random.RandomState(b * 100 + c + h + w)
     feat = rs.standard_normal((b, c, h, w)).astype(np.float32)
