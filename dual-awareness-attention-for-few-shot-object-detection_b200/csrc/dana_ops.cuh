@@ -460,9 +460,10 @@ __global__ void center_rows_kernel(const float* __restrict__ in, int group_rows,
     st_pair(hi, lo, o, in[o] - mean);
   }
 }
-// large groups (RPN level, thousands of rows): partial column sums with atomics, then subtract
+// large groups (RPN level, thousands of rows): per-block partial column sums, combined in a fixed order (no float
+// atomics: the forward is bit-reproducible run to run), then subtract
 __global__ void colsum_partial_kernel(const float* __restrict__ in, int group_rows, int c, int rows_per_block,
-                                      float* __restrict__ sums) {
+                                      float* __restrict__ partial /*[gridDim.x][groups][c]*/) {
   const int g = blockIdx.z;
   const int ch = blockIdx.y * blockDim.x + threadIdx.x;
   if (ch >= c) return;
@@ -471,7 +472,15 @@ __global__ void colsum_partial_kernel(const float* __restrict__ in, int group_ro
   const long long base = static_cast<long long>(g) * group_rows * c + ch;
   float s = 0.0f;
   for (int r = r0; r < r1; ++r) s += in[base + static_cast<long long>(r) * c];
-  atomicAdd(sums + static_cast<long long>(g) * c + ch, s);
+  partial[(static_cast<long long>(blockIdx.x) * gridDim.z + g) * c + ch] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblk, int groups, int c,
+                                    float* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * c) return;
+  float s = 0.0f;
+  for (int b = 0; b < nblk; ++b) s += partial[static_cast<long long>(b) * groups * c + i];
+  sums[i] = s;
 }
 __global__ void center_apply_kernel(const float* __restrict__ in, const float* __restrict__ sums, int group_rows, int c,
                                     long long total, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {

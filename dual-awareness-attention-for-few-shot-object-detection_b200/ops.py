@@ -410,8 +410,9 @@ def center_rows(x_f32, groups, group_rows, split=True):
     c = x_f32.shape[-1]
     dev = x_f32.device
     out = Pair.empty((groups * group_rows, c), dev, split=split)
-    sums = torch.empty((groups, c), dtype=torch.float32, device=dev) if group_rows > 256 else None
-    _count(2)
+    # scratch of the large-group path: final column sums + per-block partial sums (fixed-order reduction, no atomics)
+    sums = torch.empty((groups * (1 + (group_rows + 63) // 64), c), dtype=torch.float32, device=dev) if group_rows > 256 else None
+    _count(3 if group_rows > 256 else 1)
     check(_lib.load().dana_center_rows(_p(x_f32), groups, group_rows, c, _p(out.hi), _p(out.lo), _p(sums), _stream()),
           "dana_center_rows")
     return out

@@ -195,7 +195,9 @@ int dana_support_prepare(const void* in_hi, const void* in_lo, const float* in_f
                          const float* un_w, const float* un_b, float unary_gamma, float* v, float* logit, float* g,
                          float* r, float* colmean, void* vc_hi, void* vc_lo, void* vt_hi, void* vt_lo,
                          int64_t vt_pitch, int seg_pitch, float* rbar, void* stream);
-/* x - x.mean(1, keepdim=True) over groups of rows (dana.py:125,141,267,272) -> pair. */
+/* x - x.mean(1, keepdim=True) over groups of rows (dana.py:125,141,267,272) -> pair.
+ * sums: fp32 scratch of groups*c*(1 + ceil(group_rows/64)) elements, needed when group_rows > 256 (column sums are
+ * reduced in a fixed order, no float atomics: results are bit-reproducible); may be NULL for small groups. */
 int dana_center_rows(const float* in, int groups, int group_rows, int c, void* out_hi, void* out_lo, float* sums,
                      void* stream);
 /* F.softmax(logits, dim=2) per shot segment (dana.py:143,274) -> pair, pad columns zeroed. */
