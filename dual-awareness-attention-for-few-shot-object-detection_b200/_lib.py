@@ -84,6 +84,8 @@ SIGNATURES = {
     "dana_spatial_mean": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_softmax2": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dana_nhwc_pair_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dana_transpose_segments": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                        c_void_p]),
 }
 
 _lib = None

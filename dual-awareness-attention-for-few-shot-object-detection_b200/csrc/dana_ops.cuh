@@ -431,6 +431,23 @@ support_finalize2_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfl
   }
 }
 
+// Key-major relayout of a per-position matrix: in fp32 [maps][ns][c] -> pair out[set][ch][slot * seg_pitch + n] with row
+// pitch vt_pitch, zero in the pad columns (the B operand of a contraction over the keys of a support set; used for
+// (V W^T)^T in the head, where the 2048->64 transform is applied to the support values BEFORE the attention-weighted
+// sum -- (P V) W^T = P (V W^T), dana.py:281-288).  grid (sets, c), one output row per CTA; the data is a few hundred KB.
+__global__ void transpose_segments_kernel(const float* __restrict__ in, int shots, int ns, int c, int seg_pitch,
+                                          int vt_pitch, __nv_bfloat16* __restrict__ out_hi,
+                                          __nv_bfloat16* __restrict__ out_lo) {
+  const int set = blockIdx.x, ch = blockIdx.y;
+  const long long orow = (static_cast<long long>(set) * c + ch) * vt_pitch;
+  for (int j = threadIdx.x; j < vt_pitch; j += blockDim.x) {
+    const int slot = j / seg_pitch, n = j - slot * seg_pitch;
+    float v = 0.0f;
+    if (slot < shots && n < ns) v = in[((static_cast<long long>(set) * shots + slot) * ns + n) * c + ch];
+    st_pair(out_hi, out_lo, orow + j, v);
+  }
+}
+
 // rbar[set][c] = (unary_gamma / shots) * sum_k r[set*shots + k][c]     (:146 + shot mean :150)
 __global__ void support_rbar_kernel(const float* __restrict__ r, int sets, int shots, int c, float unary_gamma,
                                     float* __restrict__ rbar) {

@@ -185,7 +185,8 @@ class DanaEngine:
         """Column pitch of one shot's key segment in P / V^T: 8-aligned where the fused softmax epilogue is used."""
         return (ns + 7) // 8 * 8 if ns <= 256 else ns
 
-    def _attention(self, qc: Pair, kc_all: Pair, vt_all: Pair, rbar_all, set_index, sets, batch, ns, out: Pair):
+    def _attention(self, qc: Pair, kc_all: Pair, vt_all: Pair, rbar_all, set_index, sets, batch, ns, out: Pair,
+                   res_f32=None):
         """CISA contractions for one support set (dana.py:142-150 / :273-281).
         qc [batch*rows, 256] centred queries; kc_all [batch*sets*K*ns, 256]; vt_all [batch*sets, C, pitch];
         rbar_all [batch*sets, C].  Writes the attended feature into `out` [batch*rows, C] (any row pitch).
@@ -216,7 +217,7 @@ class DanaEngine:
         vt = vt_all[set_index:]
         vt2 = Pair(vt.hi.view(-1, pitch), None if vt.lo is None else vt.lo.view(-1, pitch))
         ops.linear(p_view, vt2, c, alpha=1.0 / k, bias=rbar_all[set_index:], bias_sn=sets * c, out=out, batch=batch,
-                   b_batch_stride=sets * c * pitch)
+                   b_batch_stride=sets * c * pitch, res_f32=res_f32)
         return out
 
     def rpn_attention(self, corr: Pair, sup: Pair, sets=1):
@@ -362,10 +363,22 @@ class DanaEngine:
         if "support_pooled" in want:
             extra["support_pooled"] = s_pooled.permute(0, 3, 1, 2)
         pitch_h = (k * self.seg_pitch(bins) + 7) // 8 * 8
-        vc_h, vt_h, rbar_h = ops.support_prepare(s_pooled.view(maps, bins, c), self.pe(bins), k, un_w=self.rcnn_un_w,
-                                                 un_b=self.rcnn_un_b, unary_gamma=self.unary_gamma, vt_pitch=pitch_h,
-                                                 seg_pitch=self.seg_pitch(bins), split=split)
+        sp_h = self.seg_pitch(bins)
+        vc_h, _vt_h, rbar_h, cm_h = ops.support_prepare(s_pooled.view(maps, bins, c), self.pe(bins), k,
+                                                        un_w=self.rcnn_un_w, un_b=self.rcnn_un_b,
+                                                        unary_gamma=self.unary_gamma, vt_pitch=pitch_h, seg_pitch=sp_h,
+                                                        split=split, want_colmean=True)
         kc_h = ops.linear(vc_h, self.rcnn_k_w, 256, split=split)
+        # (P V) W^T = P (V W^T): the dense half of the 2048 -> 64 transform (:288) is applied to the support values
+        # BEFORE the attention-weighted sum (:281), so the [R*49, 1024] attended feature (241 MB per support set) is
+        # never materialised.  V = Vc + 1 m^T (m = column mean) and the rows of P sum to one, hence
+        #   dense W_d^T = (1/K) sum_k P_k (Vc_k W_d^T) + (rbar + mean_k m_k) W_d^T.
+        z = torch.empty((maps * bins, 64), dtype=torch.float32, device=dev)
+        ops.linear(vc_h, self.tr_wd, 64, out_f32=z)
+        zt = ops.transpose_segments(z.view(maps, bins, 64), k, sp_h, pitch_h, split=split)   # [B*sets, 64, pitch]
+        cbar = rbar_h + cm_h.view(b * sets, k, c).mean(1)
+        c64 = torch.empty((b * sets, 64), dtype=torch.float32, device=dev)
+        ops.linear(ops.split_f32(cbar.contiguous(), split), self.tr_wd, 64, out_f32=c64)
         if qpe is None:
             qpe = Pair.empty((r * bins, c), dev, split)
             ops.add_pe_split(pooled_f32, self.pe(bins), bins, qpe, c)     # :259
@@ -376,10 +389,8 @@ class DanaEngine:
         ops.linear(qpe, self.tr_wq, 64, bias=self.tr_b, out_f32=t_q)      # query half of :288 (shared by all sets)
         cls_scores = torch.empty((sets * r, 2), dtype=torch.float32, device=dev)
         for s in range(sets):
-            dense_h = Pair.empty((r * bins, c), dev, split)
-            self._attention(qc_h, kc_h, vt_h, rbar_h, s, sets, b, bins, dense_h)
             t = Pair.empty((r * bins, 64), dev, split)
-            ops.linear(dense_h, self.tr_wd, 64, out=t, res_f32=t_q)        # dense half of :288
+            self._attention(qc_h, kc_h, zt, c64, s, sets, b, bins, t, res_f32=t_q)   # :273-288, dense half folded in
             hid = ops.linear(t.view(r, bins * 64), self.ffn1_w, 1024, bias=self.ffn1_b, relu=True, split=split)
             ops.linear(hid, self.ffn2_w, 2, bias=self.ffn2_b, out_f32=cls_scores[s * r:(s + 1) * r])
         cls_prob = ops.softmax2(cls_scores)                               # :290

@@ -376,7 +376,7 @@ def avgpool(x: Pair, k: int):
 
 
 def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b, unary_gamma=0.1, vt_pitch,
-                    seg_pitch=None, split=True):
+                    seg_pitch=None, split=True, want_colmean=False):
     """Support side of BA+CISA.  x: Pair or fp32 tensor [maps, ns, c].  Returns (vc pair [maps*ns, c],
     vt pair [sets, c, vt_pitch], rbar fp32 [sets, c])."""
     if isinstance(x, Pair):
@@ -403,7 +403,20 @@ def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b
                                            _p(g), _p(r), _p(colmean), _p(vc.hi), _p(vc.lo), _p(vt.hi), _p(vt.lo),
                                            int(vt_pitch), int(seg_pitch if seg_pitch is not None else ns), _p(rbar),
                                            _stream()), "dana_support_prepare")
+    if want_colmean:
+        return vc, vt, rbar, colmean
     return vc, vt, rbar
+
+
+def transpose_segments(x_f32, shots, seg_pitch, vt_pitch, split=True):
+    """x [maps, ns, c] fp32 -> pair [maps/shots, c, vt_pitch] with element (set, ch, slot*seg_pitch + n), pads zero."""
+    _need_cuda(x_f32)
+    maps, ns, c = x_f32.shape
+    out = Pair.empty((maps // shots, c, vt_pitch), x_f32.device, split=split)
+    _count(1)
+    check(_lib.load().dana_transpose_segments(_p(x_f32.contiguous()), maps, shots, ns, c, int(seg_pitch), int(vt_pitch),
+                                              _p(out.hi), _p(out.lo), _stream()), "dana_transpose_segments")
+    return out
 
 
 def center_rows(x_f32, groups, group_rows, split=True):

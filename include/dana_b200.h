@@ -216,6 +216,11 @@ int dana_spatial_mean(const void* in_hi, const void* in_lo, int64_t items, int s
                       void* out_lo, void* stream);
 int dana_softmax2(const float* in, int64_t rows, float* out, void* stream);
 int dana_nhwc_pair_to_nchw(const void* in_hi, const void* in_lo, int batch, int c, int hw, float* out, void* stream);
+/* Key-major relayout: in fp32 [maps][ns][c] -> pair out[maps/shots][c][vt_pitch], element (set, ch, slot*seg_pitch + n),
+ * pad columns zeroed.  Builds the B operand (V W^T)^T of the head, where the Linear(2048->64) of dana.py:288 is applied
+ * to the support values before the attention-weighted sum of :281 ((P V) W^T = P (V W^T)). */
+int dana_transpose_segments(const float* in, int maps, int shots, int ns, int c, int seg_pitch, int64_t vt_pitch,
+                            void* out_hi, void* out_lo, void* stream);
 
 #ifdef __cplusplus
 }
