@@ -9,7 +9,7 @@
 // issues hi*hi + hi*lo + lo*hi, which restores fp32-equivalent products with fp32 TMEM accumulation
 // (the reference runs fp32 end to end; SURVEY.md section 7 hard part 1).
 //
-// Structure: persistent CTAs (one per SM), 6 warps.
+// Structure: persistent CTAs (one per SM), 10 warps.
 //   warp 0      TMA producer: walks (tap, 64-channel block) k-blocks through a smem ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, double-buffered accumulators
 //   warps 2..9  epilogue: tcgen05.ld -> scale/bias (folded BN), residual, ReLU -> bf16 hi/lo or fp32
