@@ -184,6 +184,10 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   const long long sp_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
   const int sms = sm_count();
   int block_n = a->n_out > 128 ? 256 : (a->n_out > 64 ? 128 : 64);
+  // Split precision: 256-wide tiles only pay off for long K (tensor-bound: RPN 3x3 0.34 vs 0.41 ms, layer4 3x3 0.18 vs
+  // 0.20); up to K = 2304 the 128-wide tile is 13..22 % faster on every trunk layer (three 64 KB stages instead of
+  // two 96 KB ones, half-size epilogues, finer wave granularity) -- profiles/r01_gemm_blockn.txt.
+  if (a->a_lo != nullptr && block_n == 256 && static_cast<long long>(taps) * a->a_c <= 2304) block_n = 128;
   // few M-tiles and a short K loop (the q/k projections of a single episode): narrower tiles spread the work over
   // more SMs at no extra cost -- stream-K's partial-tile exchange costs more than such a launch (measured: q-proj
   // 1900x256x1024 took 50 us as 15 stream-K'd 256-wide tiles)
