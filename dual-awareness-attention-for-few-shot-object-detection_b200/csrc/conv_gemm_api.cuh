@@ -227,6 +227,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     const char* env = getenv("DANA_KTILE");
     if (env != nullptr && nsplit == 2 && block_n == 256 && cm == 1 && !softmax && (a->a_c % 32) == 0)
       ktile = atoi(env) == 32 ? 32 : 64;
+    // (128-wide tiles stay at KT = 64: six 32 KB stages instead of three 64 KB ones measured 7 % slower on the step)
   }
   p.c_blocks = static_cast<int>((a->a_c + ktile - 1) / ktile);
   // tensor maps

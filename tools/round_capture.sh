@@ -10,7 +10,7 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref
 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/launches_bf16x3.csv python tools/profile_step.py > $O/prof.log 2>&1
 # the launch list of the bench command itself (graph replays are profiled node by node): the GEMM kernel's share of
 # the launches of `bench.py` must agree with its share of the step
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
 python tools/summarize_launches.py $O/launches_bench.csv 12 > $O/launches_bench_summary.txt 2>&1
 gzip -f $O/launches_bench.csv
 timeout 300 python tools/gemm_bench.py > $O/gemm_bench.txt 2>&1
