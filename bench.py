@@ -263,6 +263,49 @@ def cpu_forward_fn(batch):
     return step, kind
 
 
+def cpu_operator_baseline():
+    """The reference's two custom CPU operators on ONE host thread (they are single-threaded, ROIAlign_cpu.cpp:133,
+    nms_cpu.cpp:17-64) at the benchmark's per-image sizes: RoIAlign of 300 RoIs on a [1,1024,38,63] map and NMS of
+    6000 boxes.  Uses the reference's own compiled operators when oracle/_ref travelled, else
+    the oracle's C restatement."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dana_oracle as O
+    roi_fn, nms_fn, kind = O.roi_align_forward, O.nms, "port (oracle/c/dana_oracle.c)"
+    try:
+        import build_ref
+        ref_c = build_ref.load()
+        if ref_c is not None:
+            roi_fn = lambda f, r, s, ph, pw, sr: ref_c.roi_align_forward(torch.as_tensor(f), torch.as_tensor(r), s, ph, pw, sr)  # noqa: E731
+            nms_fn = lambda bx, sc, th: ref_c.nms(torch.as_tensor(bx), torch.as_tensor(sc), th)  # noqa: E731
+            kind = "reference (oracle/_ref: lib/model/csrc/cpu compiled in place)"
+    except Exception:  # noqa: BLE001
+        pass
+    rs = np.random.RandomState(0)
+    feat = rs.standard_normal((1, 1024, 38, 63)).astype(np.float32)
+    cx, cy = rs.uniform(0, 1000, 300), rs.uniform(0, 600, 300)
+    bw, bh = np.exp(rs.uniform(np.log(16), np.log(600), 300)), np.exp(rs.uniform(np.log(16), np.log(500), 300))
+    rois = np.stack([np.zeros(300), np.clip(cx - bw / 2, 0, 999), np.clip(cy - bh / 2, 0, 599),
+                     np.clip(cx + bw / 2, 0, 999), np.clip(cy + bh / 2, 0, 599)], 1).astype(np.float32)
+    n = 6000
+    x1, y1 = rs.uniform(0, 900, n), rs.uniform(0, 500, n)
+    boxes = np.stack([x1, y1, x1 + rs.uniform(1, 200, n), y1 + rs.uniform(1, 200, n)], 1).astype(np.float32)
+    scores = (rs.permutation(n) / n).astype(np.float32)
+    prev = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        t0 = time.perf_counter()
+        roi_fn(feat, rois, 1.0 / 16, 7, 7, 0)
+        t_roi = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        nms_fn(boxes, scores, 0.7)
+        t_nms = time.perf_counter() - t0
+    finally:
+        torch.set_num_threads(prev)
+    return {"threads": 1, "kind": kind, "roi_align_300_rois_ms": round(t_roi * 1e3, 1), "nms_6000_boxes_ms": round(t_nms * 1e3, 1)}
+
+
 def cpu_baseline(sample_batch=1, reps=2):
     step, kind = cpu_forward_fn(sample_batch)
     step()
@@ -270,9 +313,14 @@ def cpu_baseline(sample_batch=1, reps=2):
     for _ in range(reps):
         step()
     dt = (time.perf_counter() - t0) / reps
-    return {"value": round(sample_batch / dt, 4), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-            "detail": kind, "sample": "%d query 600x1000 + 6 support crops per step, %d timed steps (+1 warm-up), torch CPU fp32, "
-                                      "%d threads" % (sample_batch, reps, os.cpu_count() or 1)}
+    out = {"value": round(sample_batch / dt, 4), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+           "detail": kind, "sample": "%d query 600x1000 + 6 support crops per step, %d timed steps (+1 warm-up), torch CPU fp32, "
+                                     "%d threads" % (sample_batch, reps, os.cpu_count() or 1)}
+    try:
+        out["operators_single_thread"] = cpu_operator_baseline()
+    except Exception as e:  # noqa: BLE001  -- the operator timings are an extra, never a reason to lose the line
+        out["operators_single_thread"] = {"error": repr(e)[:200]}
+    return out
 
 
 def run_reference(args):

@@ -265,3 +265,21 @@ def test_roi_align_orders_and_tiny_maps(ops, b, c, h, w):
     # fixed sampling ratio 2 (grid_h = 2 everywhere: three row taps per bin on small RoIs)
     want2 = O.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 2)
     assert relerr(ops.roi_align_forward(f, rr, 1.0 / 16, 7, 7, 2), want2) <= 1e-5
+
+
+@pytest.mark.parametrize("maps,shots,ns,c,seg", [(6, 3, 49, 64, 56), (4, 1, 196, 32, 200), (10, 5, 7, 8, 8)])
+def test_transpose_segments(ops, maps, shots, ns, c, seg):
+    """Key-major relayout used by the head ((V W^T)^T as the B operand of the P contraction): exact data movement
+    plus the bf16 pair split, pad columns zero."""
+    g = torch.Generator().manual_seed(maps * ns)
+    x = torch.randn(maps, ns, c, generator=g)
+    pitch = (shots * seg + 7) // 8 * 8 + 8
+    out = ops.transpose_segments(x.cuda(), shots, seg, pitch)
+    got = out.float().cpu()                                     # hi + lo
+    want = torch.zeros(maps // shots, c, pitch)
+    for m in range(maps):
+        want[m // shots, :, (m % shots) * seg:(m % shots) * seg + ns] = x[m].t()
+    assert tuple(got.shape) == tuple(want.shape)
+    assert (got - want).abs().max().item() <= 2e-5 * x.abs().max().item()
+    mask = want == 0
+    assert (got[mask] == 0).all()
