@@ -178,3 +178,30 @@ def test_res101_five_sets_vs_oracle():
     assert relerr(bbox, ref["bbox_pred"]) <= TOL
     assert relerr(cls_prob, ref["cls_prob"]) <= TOL
     assert tuple(cls_prob.shape) == (sets * 300, 2)
+
+
+def test_full_size_query_vs_oracle():
+    """The headline configuration itself (BASELINE.json configs[1], one episode of it): a 600x1000 query with 2 support
+    sets x 3 shots of 320x320 crops, every stage against the oracle at the north-star tolerance (1e-3, max-norm)."""
+    import dana_b200  # noqa: F401
+    from dana_b200.engine import DanaEngine
+    k, sets = 3, 2
+    p = O.make_params(1996, attn_std=0.05)
+    im, info, sup = O.synth_inputs(21, 1, 600, 1000, k * sets)
+    with torch.no_grad():
+        ref = O.dana_forward_eval(p, im, info, sup, k)
+    eng = DanaEngine(p, n_shot=k, precision="bf16x3")
+    want = ("base_feat", "dense", "pooled", "fc7", "rpn_fg")
+    rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want)
+    assert tuple(ex["base_feat"].shape) == (1, 1024, 38, 63)
+    assert relerr(ex["base_feat"], ref["base_feat"]) <= TOL
+    assert relerr(ex["dense"], ref["dense"]) <= TOL
+    assert relerr(ex["rpn_fg"], ref["rpn_cls_prob"][:, 12:].permute(0, 2, 3, 1).reshape(1, -1)) <= TOL
+    assert roi_set_match(rois, ref["rois"]) >= 0.97
+    rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want,
+                                           teacher={"rois": ref["rois"].cuda()})
+    assert relerr(ex["pooled"], ref["pooled"]) <= TOL
+    assert relerr(ex["fc7"], ref["fc7"]) <= TOL
+    assert relerr(bbox, ref["bbox_pred"]) <= TOL
+    assert relerr(cls_prob, ref["cls_prob"]) <= TOL
+    assert tuple(cls_prob.shape) == (sets * 300, 2)
