@@ -263,6 +263,17 @@ def cpu_forward_fn(batch):
     return step, kind
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_operator_baseline():
     """The reference's two custom CPU operators on ONE host thread (they are single-threaded, ROIAlign_cpu.cpp:133,
     nms_cpu.cpp:17-64) at the benchmark's per-image sizes: RoIAlign of 300 RoIs on a [1,1024,38,63] map and NMS of
@@ -313,8 +324,8 @@ def cpu_baseline(sample_batch=1, reps=2):
     for _ in range(reps):
         step()
     dt = (time.perf_counter() - t0) / reps
-    out = {"value": round(sample_batch / dt, 4), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-           "detail": kind, "sample": "%d query 600x1000 + 6 support crops per step, %d timed steps (+1 warm-up), torch CPU fp32, "
+    out = {"value": round(sample_batch / dt, 4), "unit": "images/s", "cores": os.cpu_count(), "cpu": cpu_model(),
+           "kind": "port", "detail": kind, "sample": "%d query 600x1000 + 6 support crops per step, %d timed steps (+1 warm-up), torch CPU fp32, "
                                      "%d threads" % (sample_batch, reps, os.cpu_count() or 1)}
     try:
         out["operators_single_thread"] = cpu_operator_baseline()
@@ -343,7 +354,8 @@ def run_reference(args):
             "ms_per_step": round(1e3 * dt / steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": "1 query + 6 supports per step on the host cores"},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "detail": kind,
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "cpu": cpu_model(), "kind": "port",
+                             "detail": kind,
                              "sample": "%d steps x 1 query 600x1000 (2-way 3-shot), torch CPU fp32, %d threads" % (steps, os.cpu_count() or 1)},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
