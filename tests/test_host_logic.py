@@ -150,3 +150,23 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_episode_host_geometry_matches_oracle():
+    """The host-side arithmetic of dana_b200.episode (output sizes, short-side truncation, cvRound) against the oracle's
+    restatement of the loaders, without a GPU (the kernel itself is checked in test_gpu_episode.py)."""
+    import dana_b200  # noqa: F401
+    import episode_oracle as E
+    from dana_b200 import episode
+    rs = np.random.RandomState(0)
+    for _ in range(200):
+        bh, bw = int(rs.randint(1, 700)), int(rs.randint(1, 700))
+        assert episode._fit(bh, bw, 320) == E._fit(bh, bw, 320)
+    for v in (0.5, 1.5, 2.5, 959.5, 960.4999, 1000.0):
+        assert episode.cv_round(v) == E.cv_round(v) == int(np.rint(v))
+    # prep_im_for_blob output size: cvRound(side * 600 / min side) -- e.g. 375x500 -> 600x800, 333x500 -> 600x901
+    for h, w, want in [(375, 500, (600, 800)), (333, 500, (600, 901)), (480, 640, (600, 800)), (600, 1000, (600, 1000))]:
+        s = 600.0 / min(h, w)
+        assert (episode.cv_round(h * s), episode.cv_round(w * s)) == want
+    with pytest.raises(RuntimeError):
+        episode.prep_im_for_blob(torch.zeros((8, 8, 3), dtype=torch.uint8), [0, 0, 0], 8)    # CPU tensor: no fallback
