@@ -147,3 +147,58 @@ def test_episode_support_crop_layout():
     assert np.all(out[:, 185:, :] == 0) and np.any(out[:, 184, :] != 0)
     tall = E.support_from_image((rs.rand(50, 20, 3) * 255).astype(np.uint8), [1.0, 2.0, 3.0], 320)
     assert np.all(tall[:, :, 128:] == 0) and np.any(tall[:, :, 127] != 0)
+
+
+# ------------------------------------------------------------------ training branch: oracle only
+def test_train_forward_vs_reference(golden_dir):
+    """oracle/train_oracle.py (anchor targets, RPN losses, proposal targets, both head passes, hard-negative-mined
+    classification loss) against the UNMODIFIED reference run in train mode on CPU (oracle/make_golden_train.py), same
+    numpy RNG seed: sampled labels identical, losses to 1e-6 relative."""
+    import make_golden_train as MT
+    import train_oracle as T
+    g = _g(golden_dir, "forward_train_small.npz")
+    tc = MT.TRAIN_CASE
+    p = O.make_params(tc["seed"], attn_std=tc["attn_std"])
+    im, info, gt, nb, sup = MT.train_inputs()
+    np.random.seed(tc["np_seed"])
+    with torch.no_grad():
+        out = T.dana_forward_train(p, im, info, gt, nb, sup, tc["n_shot"])
+    got = np.array([float(out[k]) for k in ("rpn_loss_cls", "rpn_loss_box", "RCNN_loss_cls", "RCNN_loss_bbox")])
+    np.testing.assert_allclose(got, g["losses"], rtol=1e-6)
+    np.testing.assert_array_equal(out["rois_label"].numpy(), g["rois_label"])
+    np.testing.assert_array_equal(out["rpn_targets"][0].numpy().astype(np.int8), g["rpn_labels"])
+    np.testing.assert_allclose(out["rois"].numpy(), g["rois"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(out["cls_prob"].numpy(), g["cls_prob"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out["bbox_pred"].numpy(), g["bbox_pred"], rtol=0, atol=1e-6)
+    assert abs(float(out["rpn_targets"][1].abs().sum()) - float(g["rpn_bbox_targets_abs_sum"])) <= 1e-3
+    assert abs(float(out["rpn_targets"][3].sum()) - float(g["rpn_outside_sum"])) <= 1e-5
+    assert tuple(out["rois"].shape) == (2, 128, 5) and tuple(out["cls_prob"].shape) == (512, 2)
+
+
+def test_train_target_layers_edge_cases():
+    """Target layers on hand-made inputs: zero-padded gt columns never match, an anchor that is the best for a gt is
+    positive even below the threshold, images without positives contribute no regression weight."""
+    import train_oracle as T
+    base = torch.from_numpy(O.generate_anchors(scales=(4, 8, 16, 32))).float()
+    gt = torch.zeros(1, 5, 5)
+    gt[0, 0] = torch.tensor([10.0, 12.0, 70.0, 60.0, 1.0])
+    info = torch.tensor([[160.0, 224.0, 1.0]])
+    np.random.seed(0)
+    labels, tgt, iw, ow = T.anchor_target_layer(10, 14, gt, info, base)
+    assert tuple(labels.shape) == (1, 1, 12 * 10, 14) and tuple(tgt.shape) == (1, 48, 10, 14)
+    assert int((labels == 1).sum()) >= 1 and set(np.unique(labels.numpy())) <= {-1.0, 0.0, 1.0}
+    assert float(iw.sum()) == 4.0 * int((labels == 1).sum())
+    n_ex = int((labels >= 0).sum())
+    assert abs(float(ow.sum()) - 4.0) <= 1e-5 and n_ex <= 256
+    ov = T.bbox_overlaps_batch(torch.tensor([[10.0, 12.0, 70.0, 60.0], [0.0, 0.0, 0.0, 0.0]]), gt)
+    assert float(ov[0, 0, 0]) == 1.0 and (ov[0, 0, 1:] == 0).all() and (ov[0, 1] == -1).all()
+    rois = torch.zeros(1, 6, 5)
+    rois[0, :, 1:] = torch.tensor([[10.0, 12.0, 70.0, 60.0], [12.0, 14.0, 68.0, 58.0], [100.0, 100.0, 150.0, 150.0],
+                                   [0.0, 0.0, 30.0, 30.0], [150.0, 20.0, 220.0, 90.0], [5.0, 5.0, 200.0, 150.0]])
+    np.random.seed(1)
+    r, lab, t, iw2, ow2 = T.proposal_target_layer(rois, gt)
+    assert tuple(r.shape) == (1, 128, 5) and int(lab.sum()) >= 1 and int(lab.sum()) <= 32
+    assert torch.equal(iw2 > 0, ow2 > 0) and float(iw2.sum()) == 4.0 * int(lab.sum())
+    loss = T.smooth_l1_loss(torch.zeros(2, 4), torch.tensor([[0.5, 2.0, 0.0, -3.0], [0.0, 0.0, 0.0, 0.0]]),
+                            torch.ones(2, 4), torch.ones(2, 4))
+    assert abs(float(loss) - (0.125 + 1.5 + 2.5) / 2) <= 1e-6
