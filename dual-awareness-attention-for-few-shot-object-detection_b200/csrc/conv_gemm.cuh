@@ -49,6 +49,7 @@ struct ConvGemmParams {
   int sk_epoch;         // value a flag takes when this launch's partial is published; 0 = stream-K off
   int sm_ns, sm_pitch;  // SOFTMAX epilogue: keys per segment, column pitch of a segment in the output
   int n_fast;           // tile order: 1 = the N-tiles of an M-tile are consecutive work items, 0 = N is the slow index
+  int a_prefetch;       // producer prefetches the next tile's activation boxes into L2
 };
 
 constexpr int kGemmThreads = 320;
@@ -224,6 +225,32 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int y0 = ((sp / p.tiles_x) % p.tiles_y) * p.bh;
         const int n0 = (sp / (p.tiles_x * p.tiles_y)) * p.bn;
         const int bcoord = p.b_batched ? n0 : 0;
+        if (p.a_prefetch && !stream_k) {
+          // Experiment kept as an opt-in (see the launcher: measured slower).  The stages hold at most ~190 KB in flight
+          // per SM; when a stage contains DRAM misses its latency is 2-3 us and the main loop of the narrow layers runs
+          // at 190 KB / 3.4 us (ncu: the epilogue waits on the accumulator barrier, L2 at 30 %).  This asks L2 for the
+          // NEXT tile's activation boxes (centre tap only: the other taps are the same pixels shifted) a tile ahead.
+          const int wn = wk + num_clusters;
+          if (wn < num_work) {
+            const int mgn = p.n_fast ? wn / p.tiles_co : wn % m_groups;
+            const int spn = mgn * CM + cm_rank;
+            const int xn = (spn % p.tiles_x) * p.bw;
+            const int yn = ((spn / p.tiles_x) % p.tiles_y) * p.bh;
+            const int nn = (spn / (p.tiles_x * p.tiles_y)) * p.bn;
+            const bool same_a = p.n_fast && (wn / p.tiles_co == wk / p.tiles_co);   // next item: same M-tile, other N-tile
+            if (!same_a) {
+              const int taps = p.taps_r * p.taps_s;
+              const int t0 = (taps == 9) ? 4 : 0, t1 = (taps == 9) ? 5 : taps;
+              for (int tap = t0; tap < t1; ++tap) {
+                const int r = tap / p.taps_s, s2 = tap - r * p.taps_s;
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                  tma_prefetch_4d(&p.tm_a_hi, cb * kTileK, xn + s2 - p.pad_x, yn + r - p.pad_y, nn);
+                  if (NSPLIT == 2) tma_prefetch_4d(&p.tm_a_lo, cb * kTileK, xn + s2 - p.pad_x, yn + r - p.pad_y, nn);
+                }
+              }
+            }
+          }
+        }
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           const int tap = kb / p.c_blocks;
           const int cb = kb - tap * p.c_blocks;

@@ -268,6 +268,17 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   // an M-tile share its activation reads in L2; a launch whose tiles are all in flight at once (stream-K over a few
   // long-K tiles, e.g. the P.V contraction of a single query) reads less with N slow (measured: 300 MB vs 586 MB)
   p.n_fast = (num_work > max_clusters) ? 1 : 0;
+  {
+    // L2 prefetch of the next tile's activation boxes (opt-in, DANA_A_PREFETCH=1; multi-wave launches only).
+    // Measured: no layer gains, the 1x1 layers lose 3-20 % and the step drops from 584 to 554 images/s -- the extra
+    // L2 requests compete with the loads they were meant to help.  Off by default.
+    static int a_pf = -1;
+    if (a_pf < 0) {
+      const char* env = getenv("DANA_A_PREFETCH");
+      a_pf = (env != nullptr && atoi(env) == 1) ? 1 : 0;
+    }
+    p.a_prefetch = (a_pf && num_work > max_clusters && !softmax) ? 1 : 0;
+  }
   // stream-K when whole-tile scheduling would leave SMs idle (partial last round or fewer tiles than SMs)
   p.sk_epoch = 0;
   {
