@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
 import dana_oracle as O  # noqa: E402
 import ref_loader  # noqa: E402
 
-TRAIN_CASE = dict(seed=1996, attn_std=0.05, input_seed=5, batch=2, height=160, width=224, n_shot=2, np_seed=7)
+TRAIN_CASE = dict(seed=1996, attn_std=0.05, input_seed=5, batch=2, height=256, width=384, n_shot=2, np_seed=7)
 
 
 def train_inputs():
@@ -23,7 +23,7 @@ def train_inputs():
     im, info, sup = O.synth_inputs(tc["input_seed"], tc["batch"], tc["height"], tc["width"], 2 * tc["n_shot"])
     gt = torch.zeros(tc["batch"], 50, 5)
     gt[0, 0] = torch.tensor([20.0, 30.0, 120.0, 140.0, 1.0])
-    gt[0, 1] = torch.tensor([100.0, 10.0, 200.0, 90.0, 1.0])
+    gt[0, 1] = torch.tensor([150.0, 10.0, 370.0, 230.0, 1.0])
     gt[1, 0] = torch.tensor([50.0, 40.0, 180.0, 150.0, 1.0])
     return im, info, gt, torch.tensor([2, 1]), sup
 
