@@ -170,3 +170,70 @@ def test_episode_host_geometry_matches_oracle():
         assert (episode.cv_round(h * s), episode.cv_round(w * s)) == want
     with pytest.raises(RuntimeError):
         episode.prep_im_for_blob(torch.zeros((8, 8, 3), dtype=torch.uint8), [0, 0, 0], 8)    # CPU tensor: no fallback
+
+
+def _grad_sync_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import dana_b200  # noqa: F401
+    from dana_b200.grad_sync import BucketedGradAllReduce
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                        # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.ReLU(), torch.nn.Linear(64, 19), torch.nn.ReLU(),
+                              torch.nn.Linear(19, 3))
+    net[2].bias.requires_grad_(False)                            # a frozen parameter (the reference freezes BN / conv1)
+    unused = torch.nn.Parameter(torch.ones(5))                   # a parameter that receives no gradient this step
+    params = list(net.parameters()) + [unused]
+    g = torch.Generator().manual_seed(100 + rank)                # different data per rank
+    x, y = torch.randn(8, 37, generator=g), torch.randn(8, 3, generator=g)
+    sync = BucketedGradAllReduce(params, bucket_bytes=200)       # several small buckets
+    results = {}
+    for mode in ("overlap", "after"):
+        for p in params:
+            p.grad = None
+        if mode == "overlap":
+            sync.arm()
+        loss = ((net(x) - y) ** 2).mean()
+        loss.backward()
+        local = [None if p.grad is None else p.grad.clone() for p in params]
+        if mode == "overlap":
+            sync.finish()
+        else:
+            sync.reduce_now()
+        results[mode] = ([None if p.grad is None else p.grad.clone() for p in params], local)
+    # reference result: plain all_reduce of every local gradient, averaged
+    want = []
+    for p, lg in zip(params, results["after"][1]):
+        if not p.requires_grad:
+            want.append(None)
+            continue
+        t = lg.clone() if lg is not None else torch.zeros_like(p)
+        dist.all_reduce(t)
+        want.append(t / world)
+    ok = len(sync.buckets) >= 3
+    for mode in ("overlap", "after"):
+        for got, w, p in zip(results[mode][0], want, params):
+            if w is None:
+                ok = ok and (got is None)
+            else:
+                ok = ok and got is not None and torch.allclose(got, w, rtol=0, atol=1e-7)
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_bucketed_grad_allreduce_gloo_world2():
+    """The training step's only collective: bucketed, hook-driven gradient averaging equals a plain
+    per-parameter all-reduce mean, with frozen and unused parameters, in both the overlapped and the after-backward mode."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_grad_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
