@@ -77,3 +77,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inc", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "dana_oracle" not in text and "import oracle" not in text and "oracle/" not in text, f
+
+
+def test_header_is_plain_c():
+    """include/dana_b200.h is the drop-in boundary: it must compile as C99 and as C++ without any CUDA / torch header."""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "h.c")
+        with open(src, "w") as f:
+            f.write('#include "include/dana_b200.h"\nint main(void) { return dana_abi_version == 0; }\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-fsyntax-only", "-I", ROOT, src], cwd=ROOT)
+        if shutil.which("g++") is not None:
+            subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", ROOT, src], cwd=ROOT)
