@@ -67,8 +67,19 @@ inline int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint
   return DANA_OK;
 }
 
+// Kernel attributes (opt-in dynamic shared memory) are per device: the "already configured" flags of the launchers are
+// indexed by the current device, so a single process driving several GPUs (the per-GPU threads of nn.DataParallel,
+// train.py:104-105) configures every one of them.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+
 inline int sm_count() {
-  static int n = 0;
+  static int n_dev[kMaxDevices] = {};
+  int& n = n_dev[current_device()];
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -35,7 +35,8 @@ inline TileChoice choose_tile(int w, int h, int n, bool batched_b) {
 template <int BLOCK_N, int NSPLIT, int EPI, int CM, int KT = 64>
 inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM, KT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -278,7 +278,8 @@ inline int nms_run(const float* boxes, const float* scores, int n, float thresh,
   gather_boxes_kernel<<<gb, tb, 0, stream>>>(reinterpret_cast<const float4*>(boxes), order_used, n, sorted);
   nms_mask_kernel<<<dim3(nblk, nblk, 1), 256, 0, stream>>>(sorted, nullptr, n, thresh, mask,
                                                            static_cast<long long>(nblk) * n);
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     DANA_CUDA_CHECK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;

@@ -290,7 +290,8 @@ inline int proposals_run(const float* fg_scores, const float* deltas, const floa
   size_t cub_bytes = static_cast<size_t>(w.cub_bytes);
   DANA_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys, keys_out, idx_all, order,
                                                   static_cast<int>(tot), 0, proposals_key_bits(batch), stream));
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {};
+  size_t& configured = configured_dev[current_device()];
   if (keep_smem > 40 * 1024 && keep_smem > configured) {
     DANA_CUDA_CHECK(cudaFuncSetAttribute(proposals_nms_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(keep_smem)));
@@ -367,7 +368,8 @@ inline int detections_run(const float* rois, const float* cls_prob, const float*
   size_t cub_bytes = static_cast<size_t>(w.cub_bytes);
   DANA_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys, keys_out, idx_all, order, tot, 0,
                                                   proposals_key_bits(batch), stream));
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {};
+  size_t& configured = configured_dev[current_device()];
   if (keep_smem > 40 * 1024 && keep_smem > configured) {
     DANA_CUDA_CHECK(cudaFuncSetAttribute(proposals_nms_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(keep_smem)));

@@ -601,7 +601,8 @@ inline int roi_align7_launch(const float* feat_nhwc, const float* rois, int num_
   const int groups = (channels + kRoi7Threads * 4 - 1) / (kRoi7Threads * 4);
   const size_t smem = MODE == 1 ? sizeof(float) * kRoi7Threads * 4 * 49 : 0;
   if (MODE == 1) {
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool& configured = configured_dev[current_device()];
     if (!configured) {
       DANA_CUDA_CHECK(cudaFuncSetAttribute(roi_align7_kernel<MODE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem)));
@@ -715,7 +716,8 @@ inline int roi_align_forward_run(const float* input, const float* rois, int num_
     }
     const int threads = 128;
     const size_t smem = table_bytes + sizeof(float) * threads * pooled_h * pooled_w;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};
+    size_t& configured = configured_dev[current_device()];
     if (smem > 48 * 1024 && smem > configured) {
       DANA_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem)));
@@ -733,7 +735,8 @@ inline int roi_align_forward_run(const float* input, const float* rois, int num_
     // >= 64 threads: warp 0 builds the y table, warp 1 the x table
     const int threads = (channels / 4 >= 256) ? 256 : (((channels / 4 + 31) / 32) * 32 < 64 ? 64 : ((channels / 4 + 31) / 32) * 32);
     const int cg = threads * 4;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};
+    size_t& configured = configured_dev[current_device()];
     if (table_bytes > 48 * 1024 && table_bytes > configured) {
       DANA_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(table_bytes)));
