@@ -202,3 +202,63 @@ def test_train_target_layers_edge_cases():
     loss = T.smooth_l1_loss(torch.zeros(2, 4), torch.tensor([[0.5, 2.0, 0.0, -3.0], [0.0, 0.0, 0.0, 0.0]]),
                             torch.ones(2, 4), torch.ones(2, 4))
     assert abs(float(loss) - (0.125 + 1.5 + 2.5) / 2) <= 1e-6
+
+
+def _ref_available():
+    import ref_loader
+    return ref_loader.available()
+
+
+@pytest.mark.skipif(not _ref_available(), reason="/root/reference is mounted in the build container only")
+@pytest.mark.parametrize("seed,n_gt", [(0, 3), (1, 40), (2, 1)])
+def test_train_target_layers_vs_reference_live(seed, n_gt):
+    """The reference's own _AnchorTargetLayer / _ProposalTargetLayer (imported live) against the oracle restatement on
+    random inputs, same numpy seed: every sampling branch (more than 128 positive anchors, background subsampling,
+    fg + bg / bg-only proposal sampling) must produce identical labels, targets and weights."""
+    import ref_loader
+    import train_oracle as T
+    ref_loader.load()
+    from model.utils.config import cfg_from_file, cfg_from_list
+    cfg_from_file("/root/reference/cfgs/res50.yml")
+    cfg_from_list(["ANCHOR_SCALES", "[4,8,16,32]", "ANCHOR_RATIOS", "[0.5,1,2]", "MAX_NUM_GT_BOXES", "50"])
+    from model.rpn.anchor_target_layer import _AnchorTargetLayer
+    from model.rpn.proposal_target_layer_cascade import _ProposalTargetLayer
+    rs = np.random.RandomState(seed)
+    b, fh, fw = 2, 24, 36
+    info = torch.tensor([[fh * 16.0, fw * 16.0, 1.0]] * b)
+    gt = torch.zeros(b, 50, 5)
+    for i in range(b):
+        for j in range(n_gt):
+            w, h = rs.uniform(30, 300), rs.uniform(30, 250)
+            x1, y1 = rs.uniform(0, fw * 16 - w - 1), rs.uniform(0, fh * 16 - h - 1)
+            gt[i, j] = torch.tensor([x1, y1, x1 + w, y1 + h, 1.0])
+    nb = torch.tensor([n_gt] * b)
+    score = torch.zeros(b, 24, fh, fw)
+    ref_at = _AnchorTargetLayer(16, [4, 8, 16, 32], [0.5, 1, 2])
+    np.random.seed(100 + seed)
+    want = ref_at((score, gt, info, nb))
+    base = torch.from_numpy(O.generate_anchors(scales=(4, 8, 16, 32))).float()
+    np.random.seed(100 + seed)
+    got = T.anchor_target_layer(fh, fw, gt, info, base)
+    for w_, g_ in zip(want, got):
+        assert torch.equal(w_, g_)
+    if n_gt == 40:
+        assert int((got[0] == 1).sum()) == 2 * 128          # the fg subsampling branch was taken on both images
+    # proposals: jittered copies of the gt boxes (fg) + random boxes (bg), or only far-away boxes (bg-only branch)
+    r = 300
+    rois = torch.zeros(b, r, 5)
+    for i in range(b):
+        x1, y1 = rs.uniform(0, fw * 16 - 60, r), rs.uniform(0, fh * 16 - 60, r)
+        boxes = np.stack([x1, y1, x1 + rs.uniform(10, 59, r), y1 + rs.uniform(10, 59, r)], 1)
+        if seed != 2:
+            k = min(n_gt, 20)
+            boxes[:k] = gt[i, :k, :4].numpy() + rs.normal(0, 3, (k, 4))
+        rois[i, :, 0] = i
+        rois[i, :, 1:] = torch.from_numpy(boxes.astype(np.float32))
+    ref_pt = _ProposalTargetLayer(2)
+    np.random.seed(200 + seed)
+    want = ref_pt(rois, gt, nb)
+    np.random.seed(200 + seed)
+    got = T.proposal_target_layer(rois, gt)
+    for w_, g_ in zip(want, got):
+        assert torch.equal(w_, g_.to(w_.dtype))
