@@ -12,15 +12,25 @@ def _cuda_only(t, what):
         raise RuntimeError("%s: Not implemented on the CPU (dana_b200 is a CUDA-only build)" % what)
 
 
-def nms(dets, scores, threshold):
+def nms(dets, scores, threshold, strict_gt=False):
     """nms(dets[N,4] f32, scores[N] f32, threshold) -> LongTensor[M] of kept input indices, ascending
-    (csrc/nms.h:10-28).  Empty input returns an empty CPU long tensor, like the reference (:17-18)."""
+    (csrc/nms.h:10-28).  Empty input returns an empty CPU long tensor, like the reference (:17-18).
+
+    Comparison semantics: a box is suppressed when IoU >= threshold -- the reference's CPU operator
+    (csrc/cpu/nms_cpu.cpp:60), which is the parity target (bit-exact keep indices).  The reference's CUDA operator
+    compares with a strict `>` (csrc/cuda/nms.cu:60), so the two reference back ends disagree when an IoU equals the
+    threshold exactly; `strict_gt=True` selects the CUDA operator's rule (IoU > t  <=>  IoU >= nextafter(t, +inf) in
+    fp32, so the same kernel serves both)."""
     _cuda_only(dets, "nms")
     if dets.dtype != torch.float32:
         raise RuntimeError("nms: only float32 boxes are supported (csrc/cuda/nms.cu:71)")
     if dets.numel() == 0:
         return torch.empty((0,), dtype=torch.long, device="cpu")
-    return ops.nms(dets, scores, float(threshold))
+    thr = float(threshold)
+    if strict_gt:
+        import numpy as np
+        thr = float(np.nextafter(np.float32(thr), np.float32(np.inf)))
+    return ops.nms(dets, scores, thr)
 
 
 def roi_align_forward(input, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio):

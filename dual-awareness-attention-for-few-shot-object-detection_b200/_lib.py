@@ -40,6 +40,7 @@ class ConvGemmArgs(Structure):
         ("alpha", c_float), ("relu", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_int64), ("sk_epoch", c_int32),
         ("softmax_ns", c_int32), ("softmax_pitch", c_int32),
+        ("ab_f16", c_int32), ("io_f16", c_int32),
     ]
 
 
@@ -61,7 +62,7 @@ SIGNATURES = {
     "dana_roi_align_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dana_roi_align_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_roi_align_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_int, c_void_p, c_void_p]),
     "dana_episode_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_double, c_double,
@@ -74,14 +75,16 @@ SIGNATURES = {
     "dana_support_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
     "dana_center_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_attn_softmax": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dana_rpn_fg_prob": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dana_add_pe_split": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "dana_split_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "dana_merge_pair": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
-    "dana_spatial_mean": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dana_merge_pair": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dana_spatial_mean": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "dana_softmax2": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dana_nhwc_pair_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dana_transpose_segments": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p,

@@ -50,6 +50,7 @@ struct ConvGemmParams {
   int sm_ns, sm_pitch;  // SOFTMAX epilogue: keys per segment, column pitch of a segment in the output
   int n_fast;           // tile order: 1 = the N-tiles of an M-tile are consecutive work items, 0 = N is the slow index
   int a_prefetch;       // producer prefetches the next tile's activation boxes into L2
+  int ab_f16;           // operands are IEEE fp16 planes (kind::f16 with F16 formats) instead of bf16
 };
 
 constexpr int kGemmThreads = 320;
@@ -111,10 +112,15 @@ struct SkRange {
 // (dana.py:142-143,273-274): N-tile t is shot t's segment of sm_ns keys (sm_ns <= BLOCK_N), the epilogue takes
 // max / sum over the segment straight from TMEM and writes the normalised probabilities as a bf16 pair at
 // column t*sm_pitch (pad columns zeroed); the fp32 logits never leave the SM.
+// EPI 3: FAST with single-plane fp16 output / residual (out_hi, res_hi are __half planes, no lo plane) whatever the
+// operand planes are: the producer of an fp16-operand layer (the layers that run one MMA per product, see
+// DESIGN.md section 3) writes the plane its consumer feeds to the tensor cores.  Values saturate at +-65504.
 template <int BLOCK_N, int NSPLIT, int EPI, int CM, int KT = 64>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  constexpr bool FAST = (EPI == 1);
+  constexpr bool FAST = (EPI == 1 || EPI == 3);
+  constexpr bool F16IO = (EPI == 3);
+  constexpr bool OUT2 = (NSPLIT == 2) && !F16IO;   // output / residual carry a lo plane
   constexpr bool SOFTMAX = (EPI == 2);
   using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT>;
   constexpr int kTileK = Cfg::kTileK;
@@ -288,7 +294,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BLOCK_N);
+      const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(kTileM, BLOCK_N) : umma_idesc_bf16(kTileM, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -483,7 +489,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               const int cols = min(BLOCK_N / 2, p.n_out - nco * BLOCK_N - (et & 1) * (BLOCK_N / 2));
               for (int c = 0; c < cols; c += 64) {   // 64 bf16 = one 128-byte line
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_hi + off + c));
-                if (NSPLIT == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_lo + off + c));
+                if (OUT2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_lo + off + c));
               }
             }
           }
@@ -509,8 +515,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       // then a compile-time offset of ci*32 elements, the lo plane a uniform delta
       const __nv_bfloat16* rhp[4];
       __nv_bfloat16* ohp[4];
-      const long long d_res = (FAST && res_pair && NSPLIT == 2) ? (p.res_lo - p.res_hi) : 0;
-      const long long d_out = (FAST && NSPLIT == 2) ? (p.out_lo - p.out_hi) : 0;
+      const long long d_res = (FAST && res_pair && OUT2) ? (p.res_lo - p.res_hi) : 0;
+      const long long d_out = (FAST && OUT2) ? (p.out_lo - p.out_hi) : 0;
       if constexpr (FAST) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -527,7 +533,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int i = 0; i < 4; ++i) {
               if (row_ok[i]) {
                 rh[i] = __ldg(reinterpret_cast<const uint4*>(rhp[i] + ofs));
-                if (NSPLIT == 2) rl[i] = __ldg(reinterpret_cast<const uint4*>(rhp[i] + d_res + ofs));
+                if (OUT2) rl[i] = __ldg(reinterpret_cast<const uint4*>(rhp[i] + d_res + ofs));
               }
             }
           }
@@ -719,7 +725,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const float4 bi0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cg);
         const float4 bi1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cg + 4);
         if constexpr (FAST) {
-          const float floor_v = p.relu ? 0.0f : -INFINITY;
+          const float floor_v = p.relu ? 0.0f : (F16IO ? -65504.0f : -INFINITY);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = 8 * i + sub;
@@ -728,6 +734,25 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const float4 b = trow[(2 * (lane & 3) + 1) ^ (r & 7)];
             float f[8] = {a.x * sc0.x + bi0.x, a.y * sc0.y + bi0.y, a.z * sc0.z + bi0.z, a.w * sc0.w + bi0.w,
                           b.x * sc1.x + bi1.x, b.y * sc1.y + bi1.y, b.z * sc1.z + bi1.z, b.w * sc1.w + bi1.w};
+            if constexpr (F16IO) {
+              if (res_pair) {
+                const uint32_t wh[4] = {ch[i].x, ch[i].y, ch[i].z, ch[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&wh[e]));
+                  f[2 * e] += rf.x;
+                  f[2 * e + 1] += rf.y;
+                }
+              }
+              uint32_t ph[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 h2 = __floats2half2_rn(fminf(fmaxf(f[2 * e], floor_v), 65504.0f),
+                                                     fminf(fmaxf(f[2 * e + 1], floor_v), 65504.0f));
+                ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              if (row_ok[i]) *reinterpret_cast<uint4*>(ohp[i] + ci * 32) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            } else {
             if (res_pair) {
               const uint32_t wh[4] = {ch[i].x, ch[i].y, ch[i].z, ch[i].w};
 #pragma unroll
@@ -760,6 +785,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               *reinterpret_cast<uint4*>(ohp[i] + ci * 32) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
               if (NSPLIT == 2) *reinterpret_cast<uint4*>(ohp[i] + d_out + ci * 32) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
+            }  // !F16IO
           }
         } else {
 #pragma unroll

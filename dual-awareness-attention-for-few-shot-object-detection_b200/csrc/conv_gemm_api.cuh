@@ -81,11 +81,16 @@ inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t st
 
 // The fast epilogue needs: bf16 pair output only, full 32-column chunks, 16-byte aligned pointers and
 // strides that are multiples of 8 elements (so every 8-channel group is one aligned 16-byte access).
-inline bool fast_epilogue_ok(const ConvGemmParams& p, int nsplit) {
+inline bool fast_epilogue_ok(const ConvGemmParams& p, int nsplit, bool io_f16 = false) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (p.out_f32 != nullptr || p.res_f32 != nullptr || p.out_hi == nullptr) return false;
   if ((p.n_out % 32) != 0) return false;
   if (!al16(p.out_hi) || (p.so_x % 8) || (p.so_y % 8) || (p.so_n % 8)) return false;
+  if (io_f16) {   // single fp16 plane out (and residual), whatever the operand planes are
+    if (p.out_lo != nullptr || p.res_lo != nullptr) return false;
+    if (p.res_hi != nullptr && (!al16(p.res_hi) || (p.sr_x % 8) || (p.sr_y % 8) || (p.sr_n % 8))) return false;
+    return true;
+  }
   if (nsplit == 2 && (p.out_lo == nullptr || !al16(p.out_lo))) return false;
   if (nsplit == 1 && p.out_lo != nullptr) return false;
   if (p.res_hi != nullptr) {
@@ -97,7 +102,16 @@ inline bool fast_epilogue_ok(const ConvGemmParams& p, int nsplit) {
 }
 
 template <int BLOCK_N, int NSPLIT, int CM, int KT = 64>
-inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stream, bool io_f16 = false) {
+  if (io_f16) {
+    // fp16 single-plane output: the row-contiguous epilogue only (every use of the path has n_out % 32 == 0 and
+    // aligned planes); single-plane operands at every tile width, split operands (the P.V contraction feeding the
+    // fp16 RPN input) at 64 / 128 columns -- the launcher never picks 256-wide split tiles for an fp16 output
+    if constexpr (CM == 1 && KT == 64 && (NSPLIT == 1 || BLOCK_N <= 128)) {
+      if (p.sm_ns == 0 && fast_epilogue_ok(p, NSPLIT, true)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, 3, 1>(p, grid, stream);
+    }
+    return DANA_ENOTSUP;
+  }
   if constexpr (KT == 32) {   // only the plain-epilogue, non-cluster variants are instantiated at KT = 32
     if (fast_epilogue_ok(p, NSPLIT)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, 1, 1, 32>(p, grid, stream);
     return launch_conv_gemm_v<BLOCK_N, NSPLIT, 0, 1, 32>(p, grid, stream);
@@ -126,6 +140,11 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     return DANA_EINVAL;
   const bool batched = a->b_batch_stride != 0;
   const bool softmax = a->softmax_ns > 0;
+  const bool io_f16 = a->io_f16 != 0;
+  if (io_f16 && (softmax || a->out_lo != nullptr || a->res_lo != nullptr || a->out_f32 != nullptr ||
+                 a->res_f32 != nullptr || a->out_hi == nullptr))
+    return DANA_EINVAL;
+  if (a->ab_f16 && a->a_lo != nullptr) return DANA_EINVAL;   // fp16 operands are single planes
   if (softmax) {
     auto al16b = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (a->softmax_ns > 256 || a->softmax_pitch < a->softmax_ns || (a->softmax_pitch % 8) != 0) return DANA_EINVAL;
@@ -179,6 +198,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   p.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
   p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);
   p.out_f32 = a->out_f32;
+  p.ab_f16 = a->ab_f16 ? 1 : 0;
 
   // BLOCK_N: the widest tile that the output fills (wide tiles read A once per 256 columns and keep the MMA off the
   // shared-memory read limit); wave quantisation is handled by stream-K below, not by shrinking tiles
@@ -188,7 +208,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   // Split precision: 256-wide tiles only pay off for long K (tensor-bound: RPN 3x3 0.34 vs 0.41 ms, layer4 3x3 0.18 vs
   // 0.20); up to K = 2304 the 128-wide tile is 13..22 % faster on every trunk layer (three 64 KB stages instead of
   // two 96 KB ones, half-size epilogues, finer wave granularity) -- profiles/r01_gemm_blockn.txt.
-  if (a->a_lo != nullptr && block_n == 256 && static_cast<long long>(taps) * a->a_c <= 2304) block_n = 128;
+  if (a->a_lo != nullptr && block_n == 256 && (io_f16 || static_cast<long long>(taps) * a->a_c <= 2304)) block_n = 128;
   // few M-tiles and a short K loop (the q/k projections of a single episode): narrower tiles spread the work over
   // more SMs at no extra cost -- stream-K's partial-tile exchange costs more than such a launch (measured: q-proj
   // 1900x256x1024 took 50 us as 15 stream-K'd 256-wide tiles)
@@ -211,10 +231,16 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   int cm = 1;
   {
     const long long k_total_ = static_cast<long long>(taps) * a->a_c;
+    const int nsplit_ = (a->a_lo != nullptr) ? 2 : 1;
     // measured on B200 (tools/gemm_bench.py): no gain -- the big layers lose to wave quantisation, not to L2
     // bandwidth -- so the multicast path is opt-in (DANA_CLUSTER=2) and stream-K below is the default remedy
     const char* env = getenv("DANA_CLUSTER");
-    if (env != nullptr && atoi(env) == 2 && block_n == 256 && !batched && k_total_ >= 256 && sp_tiles >= 2) cm = 2;
+    if (env != nullptr && atoi(env) == 2 && block_n == 256 && !batched && !io_f16 && k_total_ >= 256 && sp_tiles >= 2) cm = 2;
+    // experiment (DANA_CLUSTER=3): the 3x3 convolutions of the 64 / 128-channel stages re-stream their weights for every
+    // 128-pixel tile and are bound by L2 -> SM traffic; a CTA pair sharing the weight tile halves that half of it
+    if (env != nullptr && atoi(env) == 3 && nsplit_ == 2 && block_n <= 128 && taps == 9 && !batched && !io_f16 && !softmax &&
+        sp_tiles >= 2 * sms)
+      cm = 2;
   }
 
   // K extent of a pipeline stage (see ConvGemmCfg): 32 for the long-K / wide-N launches of the split mode
@@ -222,11 +248,11 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   int ktile = 64;
   {
     const long long k_total_ = static_cast<long long>(taps) * a->a_c;
-    if (nsplit == 2 && block_n == 256 && cm == 1 && !softmax && (a->a_c % 32) == 0 && k_total_ >= 256 &&
+    if (nsplit == 2 && block_n == 256 && cm == 1 && !softmax && !io_f16 && (a->a_c % 32) == 0 && k_total_ >= 256 &&
         (a->n_out >= 512 || k_total_ >= 2048))
       ktile = 32;
     const char* env = getenv("DANA_KTILE");
-    if (env != nullptr && nsplit == 2 && block_n == 256 && cm == 1 && !softmax && (a->a_c % 32) == 0)
+    if (env != nullptr && nsplit == 2 && block_n == 256 && cm == 1 && !softmax && !io_f16 && (a->a_c % 32) == 0)
       ktile = atoi(env) == 32 ? 32 : 64;
     // (128-wide tiles stay at KT = 64: six 32 KB stages instead of three 64 KB ones measured 7 % slower on the step)
   }
@@ -306,14 +332,14 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     }
   }
   if (nsplit == 1) {
-    if (block_n == 256) return cm == 2 ? launch_conv_gemm<256, 1, 2>(p, grid, stream) : launch_conv_gemm<256, 1, 1>(p, grid, stream);
-    if (block_n == 128) return launch_conv_gemm<128, 1, 1>(p, grid, stream);
-    return launch_conv_gemm<64, 1, 1>(p, grid, stream);
+    if (block_n == 256) return cm == 2 ? launch_conv_gemm<256, 1, 2>(p, grid, stream, io_f16) : launch_conv_gemm<256, 1, 1>(p, grid, stream, io_f16);
+    if (block_n == 128) return launch_conv_gemm<128, 1, 1>(p, grid, stream, io_f16);
+    return launch_conv_gemm<64, 1, 1>(p, grid, stream, io_f16);
   }
-  if (block_n == 256 && ktile == 32) return launch_conv_gemm<256, 2, 1, 32>(p, grid, stream);
-  if (block_n == 256) return cm == 2 ? launch_conv_gemm<256, 2, 2>(p, grid, stream) : launch_conv_gemm<256, 2, 1>(p, grid, stream);
-  if (block_n == 128) return launch_conv_gemm<128, 2, 1>(p, grid, stream);
-  return launch_conv_gemm<64, 2, 1>(p, grid, stream);
+  if (block_n == 256 && ktile == 32) return launch_conv_gemm<256, 2, 1, 32>(p, grid, stream, io_f16);
+  if (block_n == 256) return cm == 2 ? launch_conv_gemm<256, 2, 2>(p, grid, stream, io_f16) : launch_conv_gemm<256, 2, 1>(p, grid, stream, io_f16);
+  if (block_n == 128) return cm == 2 ? launch_conv_gemm<128, 2, 2>(p, grid, stream, io_f16) : launch_conv_gemm<128, 2, 1>(p, grid, stream, io_f16);
+  return cm == 2 ? launch_conv_gemm<64, 2, 2>(p, grid, stream, io_f16) : launch_conv_gemm<64, 2, 1>(p, grid, stream, io_f16);
 }
 
 }  // namespace dana

@@ -449,14 +449,23 @@ __global__ void transpose_segments_kernel(const float* __restrict__ in, int shot
 }
 
 // rbar[set][c] = (unary_gamma / shots) * sum_k r[set*shots + k][c]     (:146 + shot mean :150)
+// optionally also cbar = rbar + mean_k colmean (as a bf16 pair): the row-constant part of the attended value once the
+// values are mean-centred (engine.py, head: V = Vc + 1 m^T and the rows of P sum to one)
 __global__ void support_rbar_kernel(const float* __restrict__ r, int sets, int shots, int c, float unary_gamma,
-                                    float* __restrict__ rbar) {
+                                    float* __restrict__ rbar, const float* __restrict__ colmean,
+                                    __nv_bfloat16* __restrict__ cbar_hi, __nv_bfloat16* __restrict__ cbar_lo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= sets * c) return;
   const int set = i / c, ch = i - set * c;
   float s = 0.0f;
   for (int k = 0; k < shots; ++k) s += r[(static_cast<long long>(set) * shots + k) * c + ch];
-  rbar[i] = s * unary_gamma / static_cast<float>(shots);
+  const float rb = s * unary_gamma / static_cast<float>(shots);
+  rbar[i] = rb;
+  if (cbar_hi != nullptr) {
+    float m = 0.0f;
+    for (int k = 0; k < shots; ++k) m += colmean[(static_cast<long long>(set) * shots + k) * c + ch];
+    st_pair(cbar_hi, cbar_lo, i, rb + m / static_cast<float>(shots));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -603,30 +612,113 @@ __global__ void split_f32_kernel(const float* __restrict__ in, long long n, __nv
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     st_pair(hi, lo, i, in[i]);
 }
-// bf16 pair [rows][c] with row pitch in_pitch -> fp32 contiguous [rows][c]
+// bf16 pair [rows][c] with row pitch in_pitch -> fp32 contiguous [rows][c] and / or one fp16 plane with row pitch
+// f16_pitch (the query half of the fp16 RPN input).  8 channels per thread when VEC (16-byte accesses).
+template <bool VEC>
 __global__ void merge_pair_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                  long long n, int c, long long in_pitch, float* __restrict__ out) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / c;
-    out[i] = ld_pair(hi, lo, row * in_pitch + (i - row * c));
+                                  long long n, int c, long long in_pitch, float* __restrict__ out,
+                                  __half* __restrict__ out16, long long f16_pitch) {
+  if constexpr (VEC) {
+    const int cg = c >> 3;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n / 8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long row = i / cg;
+      const int ch = static_cast<int>(i - row * cg) * 8;
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + row * in_pitch + ch));
+      const uint32_t wh[4] = {h.x, h.y, h.z, h.w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f[2 * e] = __uint_as_float(wh[e] << 16);
+        f[2 * e + 1] = __uint_as_float(wh[e] & 0xFFFF0000u);
+      }
+      if (lo != nullptr) {
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + row * in_pitch + ch));
+        const uint32_t wl[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          f[2 * e] += __uint_as_float(wl[e] << 16);
+          f[2 * e + 1] += __uint_as_float(wl[e] & 0xFFFF0000u);
+        }
+      }
+      if (out != nullptr) {
+        float4* o = reinterpret_cast<float4*>(out + row * c + ch);
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
+      if (out16 != nullptr) {
+        uint32_t ph[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 h2 = __floats2half2_rn(fminf(fmaxf(f[2 * e], -65504.0f), 65504.0f),
+                                               fminf(fmaxf(f[2 * e + 1], -65504.0f), 65504.0f));
+          ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(out16 + row * f16_pitch + ch) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      }
+    }
+  } else {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long row = i / c;
+      const float v = ld_pair(hi, lo, row * in_pitch + (i - row * c));
+      if (out != nullptr) out[i] = v;
+      if (out16 != nullptr) out16[row * f16_pitch + (i - row * c)] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+    }
   }
 }
-// mean over `sp` spatial positions: in pair [items][sp][c] -> fp32 [items][c] and pair
-__global__ void spatial_mean_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+// mean over `sp` spatial positions: in [items][sp][c] (bf16 pair, or one fp16 plane when F16) -> fp32 [items][c] and
+// pair; 8 channels per thread (c % 8 == 0, 16-byte aligned planes: checked by the launcher)
+template <bool F16>
+__global__ void spatial_mean_kernel(const void* __restrict__ hi_v, const __nv_bfloat16* __restrict__ lo,
                                     long long items, int sp, int c, float* __restrict__ out,
                                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-  const long long total = items * c;
+  const int cg = c >> 3;
+  const long long total = items * cg;
+  const __nv_bfloat16* hi = static_cast<const __nv_bfloat16*>(hi_v);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long it = i / c;
-    const int ch = static_cast<int>(i - it * c);
+    const long long it = i / cg;
+    const int ch = static_cast<int>(i - it * cg) * 8;
     // reference: .mean(3).mean(2) -- mean over w first, then over h (sp = h*w, square)
-    float s = 0.0f;
-    for (int p = 0; p < sp; ++p) s += ld_pair(hi, lo, (it * sp + p) * c + ch);
-    const float m = s / static_cast<float>(sp);
-    if (out) out[i] = m;
-    if (out_hi) st_pair(out_hi, out_lo, i, m);
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < sp; ++p) {
+      const long long off = (it * sp + p) * c + ch;
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
+      const uint32_t wh[4] = {h.x, h.y, h.z, h.w};
+      if constexpr (F16) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&wh[e]));
+          s[2 * e] += v.x;
+          s[2 * e + 1] += v.y;
+        }
+      } else {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          f[2 * e] = __uint_as_float(wh[e] << 16);
+          f[2 * e + 1] = __uint_as_float(wh[e] & 0xFFFF0000u);
+        }
+        if (lo != nullptr) {
+          const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+          const uint32_t wl[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            f[2 * e] += __uint_as_float(wl[e] << 16);
+            f[2 * e + 1] += __uint_as_float(wl[e] & 0xFFFF0000u);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += f[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float m = s[e] / static_cast<float>(sp);
+      if (out) out[it * c + ch + e] = m;
+      if (out_hi) st_pair(out_hi, out_lo, it * c + ch + e, m);
+    }
   }
 }
 // 2-class softmax over rows of [rows][2]

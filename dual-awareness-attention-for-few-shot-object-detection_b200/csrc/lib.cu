@@ -14,7 +14,7 @@ using namespace dana;
 
 extern "C" {
 
-int dana_abi_version(void) { return 1; }
+int dana_abi_version(void) { return 2; }
 
 const char* dana_error_string(int code) {
   switch (code) {
@@ -89,9 +89,9 @@ int dana_roi_align_forward(const float* input, const float* rois, int num_rois, 
 
 int dana_roi_align_head(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels, int height,
                         int width, float spatial_scale, int sampling_ratio, float* out, void* out_hi, void* out_lo,
-                        const float* pe, void* qpe_hi, void* qpe_lo, void* stream) {
+                        const float* pe, void* qpe_hi, void* qpe_lo, void* out_f16, void* stream) {
   return roi_align_head_run(feat_nhwc, rois, num_rois, batch, channels, height, width, spatial_scale, sampling_ratio,
-                            out, out_hi, out_lo, pe, qpe_hi, qpe_lo, static_cast<cudaStream_t>(stream));
+                            out, out_hi, out_lo, pe, qpe_hi, qpe_lo, out_f16, static_cast<cudaStream_t>(stream));
 }
 
 int dana_roi_align_backward(const float* grad_out, const float* rois, int num_rois, int batch, int channels,

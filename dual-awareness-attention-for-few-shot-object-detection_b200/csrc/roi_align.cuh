@@ -277,6 +277,7 @@ struct Roi7Out {
   __nv_bfloat16 *hi, *lo;     // MODE 0: bf16 pair (optional)
   const float* pe;            // [49][C]
   __nv_bfloat16 *qhi, *qlo;   // MODE 0: pair of value + pe[bin] (optional)
+  __half* h16;                // MODE 0: one fp16 plane (optional): the layer4 input of the mixed-precision mode
 };
 
 // Accumulators are float2 pairs and every multiply-add is the packed fma.rn.f32x2 (two fp32 FMAs per issue slot:
@@ -335,6 +336,12 @@ __device__ __forceinline__ void roi7_emit(int r, int ph, int c0, int channels, f
       const long long off = (static_cast<long long>(r) * 49 + bin) * channels + c0;
       if (o.out != nullptr) *reinterpret_cast<float4*>(o.out + off) = make_float4(v[0], v[1], v[2], v[3]);
       if (o.hi != nullptr) store4_pair(o.hi, o.lo, off, v);
+      if (o.h16 != nullptr) {
+        const __half2 h0 = __floats2half2_rn(fminf(fmaxf(v[0], -65504.f), 65504.f), fminf(fmaxf(v[1], -65504.f), 65504.f));
+        const __half2 h1 = __floats2half2_rn(fminf(fmaxf(v[2], -65504.f), 65504.f), fminf(fmaxf(v[3], -65504.f), 65504.f));
+        *reinterpret_cast<uint2*>(o.h16 + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0),
+                                                            *reinterpret_cast<const uint32_t*>(&h1));
+      }
       if (o.qhi != nullptr) {
         const float4 p4 = __ldg(reinterpret_cast<const float4*>(o.pe + static_cast<long long>(bin) * channels + c0));
         const float q[4] = {v[0] + p4.x, v[1] + p4.y, v[2] + p4.z, v[3] + p4.w};
@@ -631,14 +638,15 @@ inline bool roi_align7_supported(int channels, int /*height*/, int /*width*/, in
 
 inline int roi_align_head_run(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels,
                               int height, int width, float spatial_scale, int sampling_ratio, float* out, void* out_hi,
-                              void* out_lo, const float* pe, void* qpe_hi, void* qpe_lo, cudaStream_t stream) {
+                              void* out_lo, const float* pe, void* qpe_hi, void* qpe_lo, void* out_f16,
+                              cudaStream_t stream) {
   if (num_rois == 0) return DANA_OK;
   if (!feat_nhwc || !rois || num_rois < 0 || batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return DANA_EINVAL;
-  if (!out && !out_hi && !qpe_hi) return DANA_EINVAL;
+  if (!out && !out_hi && !qpe_hi && !out_f16) return DANA_EINVAL;
   if (qpe_hi && !pe) return DANA_EINVAL;
   if (!roi_align7_supported(channels, height, width, sampling_ratio)) return DANA_ENOTSUP;
   Roi7Out o{out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), pe,
-            static_cast<__nv_bfloat16*>(qpe_hi), static_cast<__nv_bfloat16*>(qpe_lo)};
+            static_cast<__nv_bfloat16*>(qpe_hi), static_cast<__nv_bfloat16*>(qpe_lo), static_cast<__half*>(out_f16)};
   return roi_align7_launch<0>(feat_nhwc, rois, num_rois, channels, height, width, spatial_scale, sampling_ratio, o, stream);
 }
 
@@ -728,7 +736,7 @@ inline int roi_align_forward_run(const float* input, const float* rois, int num_
   } else if (layout == 1) {
     if (!out && !out_hi) return DANA_EINVAL;
     if (pooled_h == 7 && pooled_w == 7 && roi_align7_supported(channels, height, width, sampling_ratio)) {
-      Roi7Out o{out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), nullptr, nullptr, nullptr};
+      Roi7Out o{out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), nullptr, nullptr, nullptr, nullptr};
       return roi_align7_launch<0>(input, rois, num_rois, channels, height, width, spatial_scale, sampling_ratio, o, stream);
     }
     if (channels % 4 != 0) return DANA_ENOTSUP;

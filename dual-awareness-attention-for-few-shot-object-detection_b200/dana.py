@@ -125,9 +125,7 @@ class DAnARCNN(nn.Module):
                 m.weight.data.fill_(1)
                 m.bias.data.zero_()
         if self.pretrained:
-            sd = torch.load(self.model_path)
-            own = dict(self.RCNN_base.named_parameters())
-            raise NotImplementedError("pretrained caffe weights: load them with load_state_dict (%d tensors)" % len(own))
+            self._load_pretrained_resnet(self.model_path)
         # frozen parts (dana.py:350-368): conv1, bn1, the first FIXED_BLOCKS stages and every BatchNorm
         for p in self.RCNN_base[0].parameters():
             p.requires_grad = False
@@ -142,6 +140,37 @@ class DAnARCNN(nn.Module):
             if isinstance(m, nn.BatchNorm2d):
                 for p in m.parameters():
                     p.requires_grad = False
+
+    # torchvision-style resnet key prefix -> position in RCNN_base / RCNN_top (dana.py:344-346)
+    _RESNET_KEY_MAP = (("conv1.", "RCNN_base.0."), ("bn1.", "RCNN_base.1."), ("layer1.", "RCNN_base.4."),
+                       ("layer2.", "RCNN_base.5."), ("layer3.", "RCNN_base.6."), ("layer4.", "RCNN_top.0."))
+
+    def _load_pretrained_resnet(self, path):
+        """dana.py:337-341: `resnet.load_state_dict({k: v for k, v in torch.load(model_path).items() if k in
+        resnet.state_dict()})` -- the caffe-converted resnet checkpoint (conv1 / bn1 / layer1..4 keys; fc is dropped
+        because the trunk has none).  Like the reference, keys the trunk does not have are ignored and a key of the
+        trunk that the file lacks is an error (strict load of the filtered dict)."""
+        print("Loading pretrained weights from %s" % path)
+        state = torch.load(path, map_location="cpu")
+        own = dict(self.RCNN_base.state_dict(prefix="RCNN_base."))
+        own.update(self.RCNN_top.state_dict(prefix="RCNN_top."))
+        mapped = {}
+        for k, v in state.items():
+            for src, dst in self._RESNET_KEY_MAP:
+                if k.startswith(src):
+                    name = dst + k[len(src):]
+                    if name in own:
+                        mapped[name] = v
+                    break
+        missing = [k for k in own if k not in mapped and not k.endswith("num_batches_tracked")]
+        if missing:
+            raise RuntimeError("pretrained resnet checkpoint %s lacks %d trunk tensors (first: %s)"
+                               % (path, len(missing), missing[0]))
+        for name, v in mapped.items():
+            if tuple(own[name].shape) != tuple(v.shape):
+                raise RuntimeError("size mismatch for %s: checkpoint %s vs model %s"
+                                   % (name, tuple(v.shape), tuple(own[name].shape)))
+            own[name].copy_(v)
 
     def _init_weights(self):
         def normal_init(m, mean, stddev, truncated=False):
@@ -183,6 +212,9 @@ class DAnARCNN(nn.Module):
                                       anchor_scales=tuple(cfg.ANCHOR_SCALES), anchor_ratios=tuple(cfg.ANCHOR_RATIOS),
                                       feat_stride=cfg.FEAT_STRIDE[0])
             self._engine_key = key
+            # graphs captured against the previous engine replay kernels that read ITS weight buffers: drop them
+            # (also releases their private memory pools)
+            self._graphs.clear()
         return self._engine
 
     def forward(self, im_data, im_info, gt_boxes, num_boxes, support_ims, all_cls_gt_boxes=None):
@@ -196,8 +228,10 @@ class DAnARCNN(nn.Module):
                   nms_thresh=cfg.TEST.RPN_NMS_THRESH, pooling_size=cfg.POOLING_SIZE)
         rois = None
         if self.use_cuda_graph:
-            key = (id(eng), tuple(im_data.shape), tuple(support_ims.shape), tuple(sorted(kw.items())))
+            key = (tuple(im_data.shape), tuple(support_ims.shape), tuple(sorted(kw.items())))
             g = self._graphs.get(key)
+            if g is not None and g is not False and g.engine is not eng:   # belt and braces: never replay a stale capture
+                g = None
             if g is None:
                 try:
                     from .engine import GraphedForward

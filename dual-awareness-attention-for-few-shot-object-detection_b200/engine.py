@@ -5,6 +5,7 @@ kernels for `_DAnARCNN.forward` in eval mode (lib/model/framework/dana.py:87-220
 Python here is host orchestration only: shapes, buffer allocation (torch caching allocator) and
 kernel order.  Every FLOP runs in libdana_b200.so."""
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -31,10 +32,11 @@ def positional_encoding(max_len, d_model=1024):
 class _Conv:
     """One conv (+ frozen BN) packed for the implicit-GEMM kernel: weight [co, kh*kw*ci] (tap-major)."""
 
-    def __init__(self, w, bn, device, split, conv_bias=None):
+    def __init__(self, w, bn, device, split, conv_bias=None, f16=False):
         co, ci, kh, kw = w.shape
         self.n_out, self.ksize = co, kh
-        self.w = Pair.from_float(w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(device), split)
+        wk = w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(device)
+        self.w = Pair.from_float_f16(wk) if f16 else Pair.from_float(wk, split)
         if bn is not None:
             g, b, m, v = [t.to(device=device, dtype=torch.float32) for t in bn]
             self.scale = (g / torch.sqrt(v + BN_EPS)).contiguous()
@@ -45,15 +47,15 @@ class _Conv:
 
 
 class _Block:
-    def __init__(self, sd, name, device, split):
+    def __init__(self, sd, name, device, split, f16=False):
         def bn(n):
             return (sd[n + ".weight"], sd[n + ".bias"], sd[n + ".running_mean"], sd[n + ".running_var"])
-        self.c1 = _Conv(sd[name + ".conv1.weight"], bn(name + ".bn1"), device, split)
-        self.c2 = _Conv(sd[name + ".conv2.weight"], bn(name + ".bn2"), device, split)
-        self.c3 = _Conv(sd[name + ".conv3.weight"], bn(name + ".bn3"), device, split)
+        self.c1 = _Conv(sd[name + ".conv1.weight"], bn(name + ".bn1"), device, split, f16=f16)
+        self.c2 = _Conv(sd[name + ".conv2.weight"], bn(name + ".bn2"), device, split, f16=f16)
+        self.c3 = _Conv(sd[name + ".conv3.weight"], bn(name + ".bn3"), device, split, f16=f16)
         self.down = None
         if (name + ".downsample.0.weight") in sd:
-            self.down = _Conv(sd[name + ".downsample.0.weight"], bn(name + ".downsample.1"), device, split)
+            self.down = _Conv(sd[name + ".downsample.0.weight"], bn(name + ".downsample.1"), device, split, f16=f16)
 
 
 class GraphedForward:
@@ -63,6 +65,7 @@ class GraphedForward:
     buffers, outputs are cloned out of the graph's private pool."""
 
     def __init__(self, engine, im_data, im_info, support_ims, **kw):
+        self.engine = engine          # the capture is only valid for this engine's buffers (keeps them alive, too)
         self.static_in = [im_data.detach().clone(), im_info.detach().float().clone(), support_ims.detach().clone()]
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -85,14 +88,20 @@ class GraphedForward:
 
 
 class DanaEngine:
-    """precision: 'bf16x3' (hi/lo operands, fp32-equivalent products -- the parity mode) or 'bf16'."""
+    """precision:
+      'mixed'   bf16x3 everywhere except the tensor-bound tail -- the RPN 3x3 conv + its 1x1 heads and layer4 run on
+                single fp16 planes (11 significant bits per operand, one MMA per product, fp32 accumulation); every
+                stage stays within the 1e-3 north-star tolerance (measured 2e-4 .. 6e-4 on those stages)
+      'bf16x3'  hi/lo bf16 operands everywhere: fp32-equivalent products (2e-5 .. 8e-5 on every stage)
+      'bf16'    plain bf16 operands: throughput mode, does not meet 1e-3."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", num_layers=50, n_shot=3,
                  semantic_enhance=True, channel_gamma=0.1, unary_gamma=0.1, precision="bf16x3",
                  anchor_scales=(4, 8, 16, 32), anchor_ratios=(0.5, 1, 2), feat_stride=16):
-        assert precision in ("bf16x3", "bf16")
+        assert precision in ("mixed", "bf16x3", "bf16")
         self.device = torch.device(device)
-        self.split = precision == "bf16x3"
+        self.split = precision in ("bf16x3", "mixed")
+        self.f16 = precision == "mixed"
         self.precision = precision
         self.num_layers = num_layers
         self.n_shot = n_shot
@@ -119,7 +128,7 @@ class DanaEngine:
         self.stages = []
         for prefix, blocks in (("RCNN_base.4", layers[0]), ("RCNN_base.5", layers[1]), ("RCNN_base.6", layers[2])):
             self.stages.append([_Block(sd, "%s.%d" % (prefix, i), dev, split) for i in range(blocks)])
-        self.top = [_Block(sd, "RCNN_top.0.%d" % i, dev, split) for i in range(layers[3])]
+        self.top = [_Block(sd, "RCNN_top.0.%d" % i, dev, split, f16=self.f16) for i in range(layers[3])]
 
         def lin(name):
             return Pair.from_float(f32(sd[name + ".weight"]), split), f32(sd[name + ".bias"])
@@ -133,15 +142,21 @@ class DanaEngine:
             self.ba_w, self.ba_b = f32(sd["rpn_channel_k_layer.weight"]).view(-1), f32(sd["rpn_channel_k_layer.bias"])
         else:
             self.ba_w = self.ba_b = None
-        self.rpn_conv = _Conv(sd["RCNN_rpn.RPN_Conv.weight"], None, dev, split, sd["RCNN_rpn.RPN_Conv.bias"])
+        self.rpn_conv = _Conv(sd["RCNN_rpn.RPN_Conv.weight"], None, dev, split, sd["RCNN_rpn.RPN_Conv.bias"], f16=self.f16)
         w_cb = torch.cat([sd["RCNN_rpn.RPN_cls_score.weight"], sd["RCNN_rpn.RPN_bbox_pred.weight"]], 0)
         b_cb = torch.cat([sd["RCNN_rpn.RPN_cls_score.bias"], sd["RCNN_rpn.RPN_bbox_pred.bias"]], 0)
         assert w_cb.shape[0] == 6 * self.num_a, "RPN head does not match the anchor configuration"
-        self.rpn_out = _Conv(w_cb, None, dev, split, b_cb)
+        self.rpn_out = _Conv(w_cb, None, dev, split, b_cb, f16=self.f16)
         wt = f32(sd["rcnn_transform_layer.weight"])                       # [64, 2048] on cat[query, dense]
         self.tr_wq = Pair.from_float(wt[:, :1024].contiguous(), split)
         self.tr_wd = Pair.from_float(wt[:, 1024:].contiguous(), split)
         self.tr_b = f32(sd["rcnn_transform_layer.bias"])
+        # positional encoding of the head's query side (dana.py:259) folded through the two projections that read it:
+        # (x + PE) W^T = x W^T + PE W^T, a [49, n_out] per-bin bias (built once in fp64), so the RoIAlign output
+        # is written once instead of once plain and once with PE added
+        pe49 = positional_encoding(49).double()
+        self.pe_q = (pe49 @ sd["rcnn_adapt_q_layer.weight"].double().cpu().t()).float().to(dev).contiguous()
+        self.pe_t = (pe49 @ wt[:, :1024].double().cpu().t() + self.tr_b.double().cpu()).float().to(dev).contiguous()
         self.ffn1_w, self.ffn1_b = lin("output_score_layer.linear1")
         self.ffn2_w, self.ffn2_b = lin("output_score_layer.linear2")
         self.bbox_w, self.bbox_b = lin("RCNN_bbox_pred")
@@ -154,7 +169,7 @@ class DanaEngine:
     # ------------------------------------------------------------------ trunk
     def _conv(self, x, c: _Conv, stride=1, relu=True, res=None, out=None):
         return ops.conv_nhwc(x, c.w, c.n_out, ksize=c.ksize, stride=stride, scale=c.scale, bias=c.bias, res=res,
-                             relu=relu, out=out, split=self.split)
+                             relu=relu, out=out, split=self.split, out_f16=x.is_f16)
 
     def _bottleneck(self, x, blk: _Block, stride, out=None):
         y = self._conv(x, blk.c1, stride=stride)
@@ -164,7 +179,21 @@ class DanaEngine:
 
     def trunk(self, im_nchw, out=None):
         """RCNN_base (dana.py:344-345).  NCHW fp32 image batch -> NHWC pair, stride 16, 1024 channels.
-        `out` optionally receives the last block's output (e.g. a channel slice of the RPN input)."""
+        `out` optionally receives the last block's output (e.g. a channel slice of the RPN input).
+        DANA_TRUNK_CHUNK=n (experiment): depth-first over chunks of n images, so that a chunk's layer1/2
+        activations (38 MB per 600x1000 image at 256 channels) stay L2-resident between consecutive layers."""
+        chunk = int(os.environ.get("DANA_TRUNK_CHUNK", "0"))
+        n = im_nchw.shape[0]
+        if chunk > 0 and n > chunk:
+            if out is None:
+                qh, qw = self._trunk_hw(im_nchw.shape[2], im_nchw.shape[3])
+                out = Pair.empty((n, qh, qw, 1024), self.device, self.split)
+            for i0 in range(0, n, chunk):
+                self._trunk(im_nchw[i0:i0 + chunk], out=out[i0:i0 + chunk])
+            return out
+        return self._trunk(im_nchw, out=out)
+
+    def _trunk(self, im_nchw, out=None):
         x = ops.stem(im_nchw, self.stem_w, self.stem_scale, self.stem_bias, split=self.split)
         for si, blocks in enumerate(self.stages):
             for bi, blk in enumerate(blocks):
@@ -220,14 +249,14 @@ class DanaEngine:
                    b_batch_stride=sets * c * pitch, res_f32=res_f32)
         return out
 
-    def rpn_attention(self, corr: Pair, sup: Pair, sets=1):
-        """RPN-level BA + CISA (dana.py:117-151).  corr [B,h,w,2048]: channels [0,1024) hold the query
-        feature, channels [1024,2048) receive the attended support feature (the `cat` of :154 for free).
+    def rpn_attention(self, base2d: Pair, dense_out: Pair, b, nq, sup: Pair, sets=1):
+        """RPN-level BA + CISA (dana.py:117-151).  base2d [B*nq, 1024] (any row pitch): the query feature;
+        dense_out [B*nq, 1024] (any row pitch; bf16 pair or one fp16 plane) receives the attended support feature --
+        when both are channel halves of one [B,h,w,2048] buffer the `cat` of :154 comes for free.
         sup [B*sets*K, hs, ws, 1024]: support maps, image-major; set 0 of every image drives the block."""
         split, k, dev = self.split, self.n_shot, self.device
-        b, qh, qw, _ = corr.hi.shape
         maps, sh, sw, c = sup.hi.shape
-        ns, nq = sh * sw, qh * qw
+        ns = sh * sw
         # support side, all sets*K maps at once (:126-147)
         pitch = (k * self.seg_pitch(ns) + 7) // 8 * 8
         vc, vt, rbar = ops.support_prepare(sup.view(maps, ns, c), self.pe(ns), k, ba_w=self.ba_w, ba_b=self.ba_b,
@@ -236,13 +265,10 @@ class DanaEngine:
                                            split=split)
         kc = ops.linear(vc, self.rpn_k_w, 256, split=split)
         # query side (:118,124-125)
-        x2d = Pair(corr.hi.view(b * nq, 2048)[:, :1024], None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, :1024])
         q = torch.empty((b * nq, 256), dtype=torch.float32, device=dev)
-        ops.linear(x2d, self.rpn_q_w, 256, out_f32=q)
+        ops.linear(base2d, self.rpn_q_w, 256, out_f32=q)
         qc = ops.center_rows(q, b, nq, split=split)
-        dense_view = Pair(corr.hi.view(b * nq, 2048)[:, 1024:],
-                          None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, 1024:])
-        self._attention(qc, kc, vt, rbar, 0, sets, b, ns, dense_view)
+        self._attention(qc, kc, vt, rbar, 0, sets, b, ns, dense_out)
 
     @torch.no_grad()
     def ba_cisa_block(self, base_feat_nchw, support_feat_nchw):
@@ -251,15 +277,12 @@ class DanaEngine:
         b, c, h, w = base_feat_nchw.shape
         k = support_feat_nchw.shape[1]
         assert k == self.n_shot and c == 1024
-        corr = Pair.zeros((b, h, w, 2048), self.device, self.split)
         base = ops.split_f32(base_feat_nchw.permute(0, 2, 3, 1).contiguous(), self.split)
-        corr.hi[..., :1024].copy_(base.hi)
-        if self.split:
-            corr.lo[..., :1024].copy_(base.lo)
+        dense = Pair.empty((b * h * w, 1024), self.device, self.split)
         hs, ws = support_feat_nchw.shape[3], support_feat_nchw.shape[4]
         sup = ops.split_f32(support_feat_nchw.reshape(b * k, c, hs, ws).permute(0, 2, 3, 1).contiguous(), self.split)
-        self.rpn_attention(corr, sup, 1)
-        return ops.merge_pair(corr).permute(0, 3, 1, 2)[:, 1024:]
+        self.rpn_attention(base.view(b * h * w, 1024), dense, b, h * w, sup, 1)
+        return ops.merge_pair(dense).view(b, h, w, 1024).permute(0, 3, 1, 2)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -286,12 +309,25 @@ class DanaEngine:
 
         # ---- trunk over the query and the support crops (dana.py:98,111)
         qh, qw = self._trunk_hw(im_data.shape[2], im_data.shape[3])
-        corr = Pair.empty((b, qh, qw, 2048), dev, split)             # [base | dense]: removes the cat (:154)
-        base = self.trunk(im_data.float().contiguous(), out=corr[..., :1024])
+        nq = qh * qw
+        if self.f16:
+            # the RPN input [base | dense] is one fp16 plane; the trunk keeps its own bf16-pair output (the q-projection
+            # and RoIAlign read it at full precision)
+            corr16 = torch.empty((b, qh, qw, 2048), dtype=torch.float16, device=dev)
+            corr = None
+            base = self.trunk(im_data.float().contiguous())
+            dense_out = Pair(corr16.view(b * nq, 2048)[:, 1024:])
+        else:
+            corr = Pair.empty((b, qh, qw, 2048), dev, split)         # [base | dense]: removes the cat (:154)
+            base = self.trunk(im_data.float().contiguous(), out=corr[..., :1024])
+            dense_out = Pair(corr.hi.view(b * nq, 2048)[:, 1024:],
+                             None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, 1024:])
         sup = support_feats if support_feats is not None else self.encode_supports(support_ims)
         maps, sh, sw, c = sup.hi.shape
+        if sh != sw:
+            raise ValueError("support feature maps must be square (got %dx%d): AvgPool2d(%d) of dana.py:42 assumes "
+                             "20x20 maps" % (sh, sw, sh - pooling_size + 1))
         ns = sh * sw
-        nq = qh * qw
         if "base_feat" in want:
             extra["base_feat"] = ops.merge_pair(base).permute(0, 3, 1, 2)
         if "support_feat" in want:
@@ -304,17 +340,37 @@ class DanaEngine:
         if teacher and "support_feat" in teacher:
             sup = ops.split_f32(teacher["support_feat"].reshape(maps, c, sh, sw).permute(0, 2, 3, 1).contiguous(), split)
 
-        self.rpn_attention(corr, sup, sets)
+        if self.f16:
+            base2d = base.view(b * nq, 1024)
+        else:
+            base2d = Pair(corr.hi.view(b * nq, 2048)[:, :1024], None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, :1024])
+        self.rpn_attention(base2d, dense_out, b, nq, sup, sets)
         if "dense" in want:
-            extra["dense"] = ops.merge_pair(corr).permute(0, 3, 1, 2)[:, 1024:]
+            if self.f16:        # export at full precision: the same contractions once more into a bf16 pair (tests only)
+                dpair = Pair.empty((b * nq, 1024), dev, split)
+                self.rpn_attention(base2d, dpair, b, nq, sup, sets)
+                extra["dense"] = ops.merge_pair(dpair).view(b, qh, qw, 1024).permute(0, 3, 1, 2)
+            else:
+                extra["dense"] = ops.merge_pair(corr).permute(0, 3, 1, 2)[:, 1024:]
         if teacher and "dense" in teacher:
-            td = ops.split_f32(teacher["dense"].permute(0, 2, 3, 1).contiguous(), split)
-            corr.hi[..., 1024:].copy_(td.hi)
-            if split:
-                corr.lo[..., 1024:].copy_(td.lo)
+            if self.f16:
+                corr16[..., 1024:].copy_(teacher["dense"].permute(0, 2, 3, 1))
+            else:
+                td = ops.split_f32(teacher["dense"].permute(0, 2, 3, 1).contiguous(), split)
+                corr.hi[..., 1024:].copy_(td.hi)
+                if split:
+                    corr.lo[..., 1024:].copy_(td.lo)
+
+        # ---- RoIAlign input (fp32 NHWC) -- and, in the mixed mode, the query half of the fp16 RPN input
+        if self.f16:
+            base_f32 = ops.merge_pair(base, out16=corr16[..., :1024])
+            rpn_in = Pair(corr16)
+        else:
+            base_f32 = ops.merge_pair(Pair(corr.hi[..., :1024], None if corr.lo is None else corr.lo[..., :1024]))
+            rpn_in = corr
 
         # ---- RPN head + proposal layer (rpn.py:58-78)
-        r1 = self._conv(corr, self.rpn_conv, relu=True)
+        r1 = self._conv(rpn_in, self.rpn_conv, relu=True)
         rpn_raw = torch.empty((b, qh, qw, 6 * self.num_a), dtype=torch.float32, device=dev)
         ops.conv_nhwc(r1, self.rpn_out.w, 6 * self.num_a, ksize=1, bias=self.rpn_out.bias, out_f32=rpn_raw)
         fg, deltas = ops.rpn_fg_prob(rpn_raw, self.num_a)
@@ -331,26 +387,29 @@ class DanaEngine:
             rois = teacher["rois"].to(dev).float().contiguous()
 
         # ---- RoIAlign on the query feature (dana.py:183)
-        base_f32 = ops.merge_pair(Pair(corr.hi[..., :1024], None if corr.lo is None else corr.lo[..., :1024]))
         r = b * post_nms_top_n
         bins = pooling_size * pooling_size
         need_f32 = "pooled" in want
-        if pooling_size == 7:   # fused: pooled pair (layer4 input) + positional-encoded query pair (dana.py:259)
-            pooled_f32, pooled, qpe4 = ops.roi_align_head(base_f32, rois.view(-1, 5), 1.0 / 16.0, 0, pe=self.pe(bins),
-                                                          want_f32=need_f32, want_pair=True, want_qpe=True, split=split)
-            qpe = qpe4.view(r * bins, 1024)
+        pooled16 = None
+        if pooling_size == 7:   # one pass: pooled bf16 pair (head CISA) [+ fp16 plane (layer4 input, mixed mode)]
+            res4 = ops.roi_align_head(base_f32, rois.view(-1, 5), 1.0 / 16.0, 0, want_f32=need_f32, want_pair=True,
+                                      split=split, want_f16=self.f16)
+            pooled_f32, pooled = res4[0], res4[1]
+            if self.f16:
+                pooled16 = res4[3]
         else:
             pooled_f32, pooled = ops.roi_align_nhwc(base_f32, rois.view(-1, 5), 1.0 / 16.0, pooling_size, 0, split=split)
-            qpe = None
         if need_f32:
             extra["pooled"] = pooled_f32.permute(0, 3, 1, 2)
         if teacher and "pooled" in teacher:
             pooled_f32 = teacher["pooled"].permute(0, 2, 3, 1).contiguous()
             pooled = ops.split_f32(pooled_f32, split)
-            qpe = None
+            pooled16 = None
+        if self.f16 and pooled16 is None:
+            pooled16 = Pair.from_float_f16(pooled_f32 if pooled_f32 is not None else ops.merge_pair(pooled))
 
         # ---- head: box regression (dana.py:246,387-389)
-        top = self.layer4(pooled)
+        top = self.layer4(pooled16 if self.f16 else pooled)
         fc7_f32, fc7 = ops.spatial_mean(top.view(r, top.hi.shape[1] * top.hi.shape[2], top.hi.shape[3]), split=split)
         bbox_pred = torch.empty((r, 4), dtype=torch.float32, device=dev)
         ops.linear(fc7, self.bbox_w, 4, bias=self.bbox_b, out_f32=bbox_pred)
@@ -364,29 +423,33 @@ class DanaEngine:
             extra["support_pooled"] = s_pooled.permute(0, 3, 1, 2)
         pitch_h = (k * self.seg_pitch(bins) + 7) // 8 * 8
         sp_h = self.seg_pitch(bins)
-        vc_h, _vt_h, rbar_h, cm_h = ops.support_prepare(s_pooled.view(maps, bins, c), self.pe(bins), k,
+        vc_h, _vt_h, rbar_h, cbar = ops.support_prepare(s_pooled.view(maps, bins, c), self.pe(bins), k,
                                                         un_w=self.rcnn_un_w, un_b=self.rcnn_un_b,
                                                         unary_gamma=self.unary_gamma, vt_pitch=pitch_h, seg_pitch=sp_h,
-                                                        split=split, want_colmean=True)
+                                                        split=split, want_cbar=True)
         kc_h = ops.linear(vc_h, self.rcnn_k_w, 256, split=split)
         # (P V) W^T = P (V W^T): the dense half of the 2048 -> 64 transform (:288) is applied to the support values
         # BEFORE the attention-weighted sum (:281), so the [R*49, 1024] attended feature (241 MB per support set) is
         # never materialised.  V = Vc + 1 m^T (m = column mean) and the rows of P sum to one, hence
-        #   dense W_d^T = (1/K) sum_k P_k (Vc_k W_d^T) + (rbar + mean_k m_k) W_d^T.
+        #   dense W_d^T = (1/K) sum_k P_k (Vc_k W_d^T) + (rbar + mean_k m_k) W_d^T      (cbar = rbar + mean_k m_k)
         z = torch.empty((maps * bins, 64), dtype=torch.float32, device=dev)
         ops.linear(vc_h, self.tr_wd, 64, out_f32=z)
         zt = ops.transpose_segments(z.view(maps, bins, 64), k, sp_h, pitch_h, split=split)   # [B*sets, 64, pitch]
-        cbar = rbar_h + cm_h.view(b * sets, k, c).mean(1)
         c64 = torch.empty((b * sets, 64), dtype=torch.float32, device=dev)
-        ops.linear(ops.split_f32(cbar.contiguous(), split), self.tr_wd, 64, out_f32=c64)
-        if qpe is None:
-            qpe = Pair.empty((r * bins, c), dev, split)
-            ops.add_pe_split(pooled_f32, self.pe(bins), bins, qpe, c)     # :259
+        ops.linear(cbar, self.tr_wd, 64, out_f32=c64)
+        # query side: the positional encoding of :259 enters as the per-bin bias PE W^T of the two projections
+        pooled2d = pooled.view(r * bins, c)
         q_h = torch.empty((r * bins, 256), dtype=torch.float32, device=dev)
-        ops.linear(qpe, self.rcnn_q_w, 256, out_f32=q_h)                  # :266
-        qc_h = ops.center_rows(q_h, r, bins, split=split)                 # :267
         t_q = torch.empty((r * bins, 64), dtype=torch.float32, device=dev)
-        ops.linear(qpe, self.tr_wq, 64, bias=self.tr_b, out_f32=t_q)      # query half of :288 (shared by all sets)
+        if bins == 49:
+            ops.linear(pooled2d, self.rcnn_q_w, 256, out_f32=q_h, row_bias=self.pe_q)          # :259,266
+            ops.linear(pooled2d, self.tr_wq, 64, out_f32=t_q, row_bias=self.pe_t)             # query half of :288
+        else:
+            qpe = Pair.empty((r * bins, c), dev, split)
+            ops.add_pe_split(pooled_f32 if pooled_f32 is not None else ops.merge_pair(pooled), self.pe(bins), bins, qpe, c)
+            ops.linear(qpe, self.rcnn_q_w, 256, out_f32=q_h)
+            ops.linear(qpe, self.tr_wq, 64, bias=self.tr_b, out_f32=t_q)
+        qc_h = ops.center_rows(q_h, r, bins, split=split)                 # :267
         cls_scores = torch.empty((sets * r, 2), dtype=torch.float32, device=dev)
         for s in range(sets):
             t = Pair.empty((r * bins, 64), dev, split)

@@ -37,6 +37,7 @@ class BucketedGradAllReduce:
         self._work = [None] * len(self.buckets)
         self._hooks = []
         self._armed = False
+        self._next = 0
 
     # ---- overlap mode: call arm() before backward, finish() after it
     def arm(self):
@@ -45,6 +46,7 @@ class BucketedGradAllReduce:
         self.disarm()
         self._pending = [len(b) for b in self.buckets]
         self._work = [None] * len(self.buckets)
+        self._next = 0                      # buckets [0, _next) have been launched
         for p in self.params:
             self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self._armed = True
@@ -58,8 +60,15 @@ class BucketedGradAllReduce:
     def _on_grad(self, p):
         bi = self._bucket_of[id(p)]
         self._pending[bi] -= 1
-        if self._pending[bi] == 0:
-            self._launch(bi)
+        if self._pending[bi] < 0:
+            raise RuntimeError("BucketedGradAllReduce: a gradient arrived twice after one arm() -- call arm() before "
+                               "every backward pass")
+        # Collectives must be issued in the same order on every rank, and hook completion order is not that: a
+        # parameter unused on one rank never fires its hook there.  Buckets are therefore launched strictly in index
+        # order (as DDP does): bucket i goes out once it is complete AND buckets 0..i-1 have gone out.
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
 
     def _launch(self, bi):
         bucket = self.buckets[bi]
@@ -79,9 +88,10 @@ class BucketedGradAllReduce:
         """Wait for every bucket (launching those whose hooks never fired, e.g. parameters without a gradient this
         step) and write the averaged gradients back into `.grad`."""
         world = dist.get_world_size(self.group)
-        for bi, bucket in enumerate(self.buckets):
+        for bi, bucket in enumerate(self.buckets):      # the rest, still in index order
             if self._work[bi] is None:
                 self._launch(bi)
+        self._next = len(self.buckets)
         for bi, bucket in enumerate(self.buckets):
             self._work[bi].wait()
             flat = self._flat[bi]

@@ -21,15 +21,17 @@ def _count(n):
     LAUNCHES += n
 
 
-# stream-K scratch of the GEMM kernel: one zero-initialised buffer per device (single-stream use), and a
-# launch counter that serves as the epoch of the ready flags
+# stream-K scratch of the GEMM kernel: one zero-initialised buffer per (device, stream) -- launches on different
+# streams may overlap, and the partial tiles / ready flags of two concurrent launches must not share storage --
+# and a launch counter that serves as the epoch of the ready flags
 _SK_WS = {}
 _SK_EPOCH = 0
 
 
 def _sk_workspace(device):
     global _SK_EPOCH
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (device.type, index, torch.cuda.current_stream(index).cuda_stream)
     ws = _SK_WS.get(key)
     if ws is None:
         nbytes = _lib.load().dana_conv_gemm_workspace_bytes()
@@ -54,11 +56,26 @@ def _need_cuda(*ts):
 
 
 class Pair:
-    """bf16 (hi, lo) planes of an activation / weight: x ~= hi + lo.  lo is None in plain-bf16 mode."""
+    """bf16 (hi, lo) planes of an activation / weight: x ~= hi + lo.  lo is None in plain-bf16 mode.
+    A single IEEE fp16 plane (hi.dtype == float16, lo None) is the operand format of the layers that run one
+    MMA per product in the mixed-precision mode."""
     __slots__ = ("hi", "lo")
 
     def __init__(self, hi, lo=None):
         self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty_f16(shape, device):
+        return Pair(torch.empty(shape, dtype=torch.float16, device=device))
+
+    @staticmethod
+    def from_float_f16(x):
+        """Host-side (torch) fp16 rounding, saturating: weights at load time and tests."""
+        return Pair(x.clamp(-65504.0, 65504.0).to(torch.float16).contiguous())
+
+    @property
+    def is_f16(self):
+        return self.hi.dtype == torch.float16
 
     @staticmethod
     def empty(shape, device, split=True):
@@ -122,6 +139,12 @@ def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strid
     args.r_sx, args.r_sy, args.r_sn = [int(v) for v in r_strides]
     args.alpha = float(alpha)
     args.relu = 1 if relu else 0
+    if a.is_f16 != w.is_f16:
+        raise _lib.DanaError("dana_conv_gemm: A and B must both be fp16 planes or both bf16 planes")
+    args.ab_f16 = 1 if a.is_f16 else 0
+    args.io_f16 = 1 if (out is not None and out.is_f16) else 0
+    if res is not None and res.is_f16 != bool(args.io_f16):
+        raise _lib.DanaError("dana_conv_gemm: the residual must have the output's plane format")
     ws, epoch = _sk_workspace(a.hi.device)
     args.workspace, args.workspace_bytes, args.sk_epoch = _p(ws), ws.numel(), epoch
     args.softmax_ns, args.softmax_pitch = int(softmax_ns), int(softmax_pitch)
@@ -139,7 +162,7 @@ def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strid
 
 
 def conv_nhwc(x: Pair, w: Pair, n_out: int, *, ksize=1, stride=1, scale=None, bias=None, res: Optional[Pair] = None,
-              relu=False, out: Optional[Pair] = None, out_f32=None, out_channel_offset=0, split=True):
+              relu=False, out: Optional[Pair] = None, out_f32=None, out_channel_offset=0, split=True, out_f16=False):
     """Conv2d (1x1 any stride, or 3x3 stride 1 pad 1) + per-channel scale/bias (+residual) (+ReLU) on an NHWC
     activation pair [N,H,W,C] (resnet.py:71-76 Bottleneck convs + frozen BN).  Returns the output pair."""
     n, h, wd, c = x.hi.shape
@@ -157,7 +180,8 @@ def conv_nhwc(x: Pair, w: Pair, n_out: int, *, ksize=1, stride=1, scale=None, bi
         a_strides = (sx, sy, sn)
         taps = (3, 3, 1, 1)
     if out is None and out_f32 is None:
-        out = Pair.empty((n, oh, ow, n_out), x.hi.device, split=split)
+        out = Pair.empty_f16((n, oh, ow, n_out), x.hi.device) if out_f16 else \
+            Pair.empty((n, oh, ow, n_out), x.hi.device, split=split)
     ref = out.hi if out is not None else out_f32
     osn, osy, osx, osc = ref.stride()
     assert osc == 1
@@ -177,9 +201,12 @@ def conv_nhwc(x: Pair, w: Pair, n_out: int, *, ksize=1, stride=1, scale=None, bi
 
 def linear(x: Pair, w: Pair, n_out: int, *, bias=None, scale=None, relu=False, alpha=1.0, out: Optional[Pair] = None,
            out_f32=None, split=True, batch=1, b_batch_stride=0, bias_sn=0, res_f32=None, softmax_ns=0,
-           softmax_pitch=0):
+           softmax_pitch=0, row_bias=None):
     """y = alpha * x @ w.T (* scale) + bias on a row-major pair x [batch*rows, K] (nn.Linear / torch.bmm,
-    dana.py:124,140,142,147).  With batch > 1 the rows are split evenly and w / bias may differ per batch."""
+    dana.py:124,140,142,147).  With batch > 1 the rows are split evenly and w / bias may differ per batch.
+    row_bias: fp32 [period, n_out] added to row i as row_bias[i % period] (the positional-encoding term of a
+    projection, (x + PE) W^T = x W^T + PE W^T): the rows are presented to the kernel as a (period x rows/period)
+    grid and the table as a residual with a zero stride over the second index."""
     rows_total, k = x.hi.shape
     pitch = x.hi.stride(0)
     assert rows_total % batch == 0
@@ -188,6 +215,14 @@ def linear(x: Pair, w: Pair, n_out: int, *, bias=None, scale=None, relu=False, a
         out = Pair.empty((rows_total, n_out), x.hi.device, split=split)
     ref = out.hi if out is not None else out_f32
     opitch = ref.stride(0)
+    if row_bias is not None:
+        period = row_bias.shape[0]
+        assert batch == 1 and res_f32 is None and rows % period == 0 and row_bias.shape[1] == n_out
+        groups = rows // period
+        conv_gemm(x, (k, period, groups, 1), (pitch, pitch * period, pitch * rows), w, n_out, (period, groups, 1),
+                  (opitch, opitch * period, opitch * rows), out=out, out_f32=out_f32, scale=scale, bias=bias, relu=relu,
+                  alpha=alpha, res_f32=row_bias, r_strides=(row_bias.stride(0), 0, 0))
+        return out if out is not None else out_f32
     r_strides = (0, 0, 0)
     if res_f32 is not None:
         rp = res_f32.stride(0)
@@ -293,9 +328,10 @@ def roi_align_nhwc(feat_nhwc, rois, spatial_scale, pooled, sampling_ratio, *, wa
 
 
 def roi_align_head(feat_nhwc, rois, spatial_scale, sampling_ratio, *, pe=None, want_f32=False, want_pair=True,
-                   want_qpe=False, split=True):
+                   want_qpe=False, split=True, want_f16=False):
     """Head RoIAlign (7x7): NHWC fp32 map [B,H,W,C] -> [R,7,7,C] as fp32 / bf16 pair / pair of value + pe[bin]
-    (dana.py:183 and the positional-encoded query of :259 in one pass).  Returns (f32, pair, qpe_pair)."""
+    (dana.py:183 and the positional-encoded query of :259 in one pass) / one fp16 plane.
+    Returns (f32, pair, qpe_pair) -- and the fp16 plane as a fourth item when want_f16."""
     _need_cuda(feat_nhwc, rois)
     b, h, w, c = feat_nhwc.shape
     r = rois.shape[0]
@@ -303,13 +339,17 @@ def roi_align_head(feat_nhwc, rois, spatial_scale, sampling_ratio, *, pe=None, w
     out = torch.empty((r, 7, 7, c), dtype=torch.float32, device=dev) if want_f32 else None
     pair = Pair.empty((r, 7, 7, c), dev, split=split) if want_pair else None
     qpe = Pair.empty((r, 7, 7, c), dev, split=split) if want_qpe else None
+    h16 = Pair.empty_f16((r, 7, 7, c), dev) if want_f16 else None
     _count(1)
     check(_lib.load().dana_roi_align_head(_p(feat_nhwc), _p(rois), r, b, c, h, w, float(spatial_scale),
                                           int(sampling_ratio), _p(out), _p(pair.hi) if pair else None,
                                           _p(pair.lo) if (pair and pair.lo is not None) else None, _p(pe),
                                           _p(qpe.hi) if qpe else None,
-                                          _p(qpe.lo) if (qpe and qpe.lo is not None) else None, _stream()),
+                                          _p(qpe.lo) if (qpe and qpe.lo is not None) else None,
+                                          _p(h16.hi) if h16 else None, _stream()),
           "dana_roi_align_head")
+    if want_f16:
+        return out, pair, qpe, h16
     return out, pair, qpe
 
 
@@ -376,9 +416,10 @@ def avgpool(x: Pair, k: int):
 
 
 def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b, unary_gamma=0.1, vt_pitch,
-                    seg_pitch=None, split=True, want_colmean=False):
+                    seg_pitch=None, split=True, want_cbar=False):
     """Support side of BA+CISA.  x: Pair or fp32 tensor [maps, ns, c].  Returns (vc pair [maps*ns, c],
-    vt pair [sets, c, vt_pitch], rbar fp32 [sets, c])."""
+    vt pair [sets, c, vt_pitch], rbar fp32 [sets, c]) and, with want_cbar, the pair [sets, c] of
+    rbar + mean over shots of the column means."""
     if isinstance(x, Pair):
         maps, ns, c = x.hi.shape
         dev = x.hi.device
@@ -397,14 +438,17 @@ def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b
     vc = Pair.empty((maps * ns, c), dev, split=split)
     vt = Pair.zeros((sets, c, vt_pitch), dev, split=split)
     rbar = torch.empty((sets, c), **f)
+    cbar = Pair.empty((sets, c), dev, split=split) if want_cbar else None
     _count(4)                                  # logits, weighted sums, finalize, rbar
     check(_lib.load().dana_support_prepare(in_hi, in_lo, in_f32, _p(pe), maps, shots, ns, c, _p(ba_w), _p(ba_b),
                                            float(gamma), _p(un_w), _p(un_b), float(unary_gamma), _p(v), _p(logit),
                                            _p(g), _p(r), _p(colmean), _p(vc.hi), _p(vc.lo), _p(vt.hi), _p(vt.lo),
                                            int(vt_pitch), int(seg_pitch if seg_pitch is not None else ns), _p(rbar),
+                                           _p(cbar.hi) if cbar else None,
+                                           _p(cbar.lo) if (cbar and cbar.lo is not None) else None,
                                            _stream()), "dana_support_prepare")
-    if want_colmean:
-        return vc, vt, rbar, colmean
+    if want_cbar:
+        return vc, vt, rbar, cbar
     return vc, vt, rbar
 
 
@@ -469,26 +513,33 @@ def split_f32(x_f32, split=True):
     return out
 
 
-def merge_pair(x: Pair):
-    """pair [..., c] (last dim contiguous, uniform row pitch) -> contiguous fp32 of the same shape."""
+def merge_pair(x: Pair, out16=None, want_f32=True):
+    """pair [..., c] (last dim contiguous, uniform row pitch) -> contiguous fp32 of the same shape; `out16`
+    (an fp16 tensor view [..., c] with a uniform row pitch) also receives the values as one fp16 plane."""
     shape = tuple(x.hi.shape)
     c = shape[-1]
     rows = x.hi.numel() // c
     pitch = x.hi.stride(-2) if x.hi.dim() > 1 else c
-    out = torch.empty(shape, dtype=torch.float32, device=x.hi.device)
+    out = torch.empty(shape, dtype=torch.float32, device=x.hi.device) if want_f32 else None
+    p16 = 0
+    if out16 is not None:
+        assert out16.dtype == torch.float16 and out16.shape == x.hi.shape and out16.stride(-1) == 1
+        p16 = out16.stride(-2) if out16.dim() > 1 else c
     _count(1)
-    check(_lib.load().dana_merge_pair(_p(x.hi), _p(x.lo), rows, c, pitch, _p(out), _stream()), "dana_merge_pair")
+    check(_lib.load().dana_merge_pair(_p(x.hi), _p(x.lo), rows, c, pitch, _p(out), _p(out16), p16, _stream()),
+          "dana_merge_pair")
     return out
 
 
 def spatial_mean(x: Pair, split=True):
+    """[items, sp, c] (bf16 pair or one fp16 plane) -> (fp32 [items, c], bf16 pair [items, c])."""
     items, sp, c = x.hi.shape
     dev = x.hi.device
     out = torch.empty((items, c), dtype=torch.float32, device=dev)
     pair = Pair.empty((items, c), dev, split=split)
     _count(1)
-    check(_lib.load().dana_spatial_mean(_p(x.hi), _p(x.lo), items, sp, c, _p(out), _p(pair.hi), _p(pair.lo),
-                                        _stream()), "dana_spatial_mean")
+    check(_lib.load().dana_spatial_mean(_p(x.hi), _p(x.lo), 1 if x.is_f16 else 0, items, sp, c, _p(out), _p(pair.hi),
+                                        _p(pair.lo), _stream()), "dana_spatial_mean")
     return out, pair
 
 

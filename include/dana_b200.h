@@ -92,11 +92,12 @@ int dana_roi_align_forward(const float* input, const float* rois, int num_rois, 
                            float* out, void* out_hi, void* out_lo, void* workspace, int64_t workspace_bytes,
                            void* stream);
 /* Head variant of the forward (7x7 bins): NHWC fp32 map -> [R,7,7,C] written as any of fp32 (out), bf16 pair
- * (out_hi/out_lo) and bf16 pair of value + pe[bin][c] (qpe_*; the positional-encoded query of rcnn_head,
- * lib/model/framework/dana.py:259).  pe is fp32 [49, C]. */
+ * (out_hi/out_lo), bf16 pair of value + pe[bin][c] (qpe_*; the positional-encoded query of rcnn_head,
+ * lib/model/framework/dana.py:259) and one fp16 plane (out_f16; the layer4 input of the mixed-precision mode).
+ * pe is fp32 [49, C]. */
 int dana_roi_align_head(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels, int height,
                         int width, float spatial_scale, int sampling_ratio, float* out, void* out_hi, void* out_lo,
-                        const float* pe, void* qpe_hi, void* qpe_lo, void* stream);
+                        const float* pe, void* qpe_hi, void* qpe_lo, void* out_f16, void* stream);
 /* grad_input [B,C,H,W] fp32 is ZEROED by the call and then accumulated (NCHW only). */
 int dana_roi_align_backward(const float* grad_out, const float* rois, int num_rois, int batch, int channels,
                             int height, int width, int pooled_h, int pooled_w, float spatial_scale,
@@ -169,6 +170,12 @@ typedef struct dana_conv_gemm_args {
    * as a bf16 pair at column segment * softmax_pitch (softmax_pitch % 8 == 0, pad columns zeroed). */
   int32_t softmax_ns;
   int32_t softmax_pitch;
+  /* fp16 planes (ABI 2).  ab_f16: a_hi / b_hi are IEEE fp16 planes (a_lo / b_lo must be NULL): one MMA per product,
+   * 11 significant bits per operand -- the tensor-bound layers of the mixed-precision mode (layer4, RPN conv).
+   * io_f16: out_hi (and res_hi, when given) are single fp16 planes, whatever the operand planes are (out_lo, res_lo,
+   * out_f32, res_f32 must be NULL; n_out % 32 == 0, 16-byte aligned planes, strides % 8 == 0; saturates at 65504). */
+  int32_t ab_f16;
+  int32_t io_f16;
 } dana_conv_gemm_args;
 int64_t dana_conv_gemm_workspace_bytes(void);
 int dana_conv_gemm(const dana_conv_gemm_args* args, void* stream);
@@ -189,12 +196,13 @@ int dana_avgpool(const void* in_hi, const void* in_lo, int maps, int h, int w, i
 /* Support side of BA + CISA (dana.py:126-147; rcnn_head :255-276 with ba_w == NULL): positional
  * encoding, background-attenuation gate, unary term r, mean-centred k-projection input (vc) and the
  * transposed values vt[set][c][shot*seg_pitch + n] (row pitch vt_pitch, seg_pitch >= ns) for the P.V
- * contraction. */
+ * contraction.  cbar_hi/lo (optional, [sets][c] pair): rbar + mean over shots of the column means -- the row-constant
+ * part of the attended value when the head contracts P with the centred values. */
 int dana_support_prepare(const void* in_hi, const void* in_lo, const float* in_f32, const float* pe, int maps,
                          int shots, int ns, int c, const float* ba_w, const float* ba_b, float gamma,
                          const float* un_w, const float* un_b, float unary_gamma, float* v, float* logit, float* g,
                          float* r, float* colmean, void* vc_hi, void* vc_lo, void* vt_hi, void* vt_lo,
-                         int64_t vt_pitch, int seg_pitch, float* rbar, void* stream);
+                         int64_t vt_pitch, int seg_pitch, float* rbar, void* cbar_hi, void* cbar_lo, void* stream);
 /* x - x.mean(1, keepdim=True) over groups of rows (dana.py:125,141,267,272) -> pair.
  * sums: fp32 scratch of groups*c*(1 + ceil(group_rows/64)) elements, needed when group_rows > 256 (column sums are
  * reduced in a fixed order, no float atomics: results are bit-reproducible); may be NULL for small groups. */
@@ -208,12 +216,14 @@ int dana_rpn_fg_prob(const float* in, int64_t pixels, int num_a, int pitch, floa
 int dana_add_pe_split(const float* in, const float* pe, int64_t rows, int c, int period, int64_t out_pitch,
                       void* out_hi, void* out_lo, void* stream);
 int dana_split_f32(const float* in, int64_t n, void* out_hi, void* out_lo, void* stream);
-/* pair [rows][c] (row pitch in_pitch elements) -> contiguous fp32 [rows][c] */
+/* pair [rows][c] (row pitch in_pitch elements) -> contiguous fp32 [rows][c] (out, may be NULL) and / or one fp16
+ * plane with row pitch f16_pitch (out_f16, may be NULL; saturating) */
 int dana_merge_pair(const void* in_hi, const void* in_lo, int64_t rows, int c, int64_t in_pitch, float* out,
-                    void* stream);
-/* .mean(3).mean(2) of the layer4 output (dana.py:387-389): pair [items][sp][c] -> [items][c]. */
-int dana_spatial_mean(const void* in_hi, const void* in_lo, int64_t items, int sp, int c, float* out, void* out_hi,
-                      void* out_lo, void* stream);
+                    void* out_f16, int64_t f16_pitch, void* stream);
+/* .mean(3).mean(2) of the layer4 output (dana.py:387-389): [items][sp][c] -> [items][c] fp32 and / or pair.
+ * Input: bf16 pair, or (in_is_f16) one fp16 plane in in_hi.  c % 8 == 0, 16-byte aligned planes. */
+int dana_spatial_mean(const void* in_hi, const void* in_lo, int in_is_f16, int64_t items, int sp, int c, float* out,
+                      void* out_hi, void* out_lo, void* stream);
 int dana_softmax2(const float* in, int64_t rows, float* out, void* stream);
 int dana_nhwc_pair_to_nchw(const void* in_hi, const void* in_lo, int batch, int c, int hw, float* out, void* stream);
 /* Key-major relayout: in fp32 [maps][ns][c] -> pair out[maps/shots][c][vt_pitch], element (set, ch, slot*seg_pitch + n),

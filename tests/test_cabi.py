@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libdana_b200.so does not export %s" % n
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
-    assert lib.dana_abi_version() == 1
+    assert lib.dana_abi_version() == 2
     assert lib.dana_error_string(-1).decode() == "invalid argument"
 
 

@@ -68,7 +68,7 @@ def test_forward_vs_reference_golden(small_case, golden_dir):
     assert relerr(cls_prob, g["cls_prob"]) <= TOL
 
 
-@pytest.mark.parametrize("precision,tol", [("bf16x3", TOL), ("bf16", 5e-2)])
+@pytest.mark.parametrize("precision,tol", [("mixed", TOL), ("bf16x3", TOL), ("bf16", 5e-2)])
 def test_forward_stages_vs_oracle(precision, tol):
     """2 support sets x 2 shots, every stage against the oracle (free-running trunk, teacher-forced rois)."""
     import dana_b200  # noqa: F401
@@ -89,6 +89,8 @@ def test_forward_stages_vs_oracle(precision, tol):
     assert relerr(ex["rpn_deltas"], ref["rpn_bbox_pred"].permute(0, 2, 3, 1).reshape(2, -1, 4)) <= tol
     if precision == "bf16x3":
         assert roi_set_match(rois, ref["rois"]) >= 0.97
+    if precision == "mixed":    # fp16 RPN scores move a few NMS decisions: the set is compared a little looser
+        assert roi_set_match(rois, ref["rois"]) >= 0.95
     rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want,
                                            teacher={"rois": ref["rois"].cuda()})
     assert relerr(ex["pooled"], ref["pooled"]) <= tol
@@ -101,23 +103,26 @@ def test_forward_stages_vs_oracle(precision, tol):
 
 @pytest.mark.parametrize("nq_hw,ns_hw,shots", [((38, 50), (20, 20), 1), ((38, 50), (20, 20), 3), ((38, 50), (14, 14), 1),
                                                ((38, 50), (14, 14), 3), ((38, 63), (20, 20), 6), ((38, 50), (14, 14), 6)])
-@pytest.mark.parametrize("attn_std", [0.01, 0.05])
-def test_ba_cisa_block_vs_oracle(nq_hw, ns_hw, shots, attn_std):
+@pytest.mark.parametrize("attn_std,feat_scale", [(0.01, 1.0), (0.05, 1.0), (0.05, 4.0)])
+def test_ba_cisa_block_vs_oracle(nq_hw, ns_hw, shots, attn_std, feat_scale):
     """The lifted BA+CISA block (BASELINE.json configs 1/5): (Nq, Ns) in {(1900,400),(1900,196),(2394,400)} x
-    units in {1,3,6}; post-ReLU N(0,1) features; logits up to |6| at attn_std 0.05 (stated with the tolerance)."""
+    units in {1,3,6}; post-ReLU N(0,1) features.  Logit range, stated with the tolerance:
+    |logit| <= 0.3 at attn_std 0.01, <= ~6 at 0.05, and ~75 with the features scaled x4 (trained-like scale, where
+    plain bf16 operands are off by 3e-2 and only the split operands hold 1e-3)."""
     import dana_b200  # noqa: F401
     from dana_b200.engine import DanaEngine
     p = O.make_params(11, attn_std=attn_std)
     rs = np.random.RandomState(shots * 100 + ns_hw[0])
-    base = torch.from_numpy(np.maximum(rs.standard_normal((1, 1024) + nq_hw), 0).astype(np.float32))
-    sup = torch.from_numpy(np.maximum(rs.standard_normal((1, shots, 1024) + ns_hw), 0).astype(np.float32))
+    base = torch.from_numpy(np.maximum(rs.standard_normal((1, 1024) + nq_hw), 0).astype(np.float32)) * feat_scale
+    sup = torch.from_numpy(np.maximum(rs.standard_normal((1, shots, 1024) + ns_hw), 0).astype(np.float32)) * feat_scale
     with torch.no_grad():
         want = O.ba_cisa_rpn(base, sup, p, True)
     eng = DanaEngine(p, n_shot=shots, precision="bf16x3")
     got = eng.ba_cisa_block(base.cuda(), sup.cuda())
     assert relerr(got, want) <= TOL
-    eng16 = DanaEngine(p, n_shot=shots, precision="bf16")
-    assert relerr(eng16.ba_cisa_block(base.cuda(), sup.cuda()), want) <= 2e-2
+    if feat_scale == 1.0:
+        eng16 = DanaEngine(p, n_shot=shots, precision="bf16")
+        assert relerr(eng16.ba_cisa_block(base.cuda(), sup.cuda()), want) <= 2e-2
 
 
 def test_module_boundary_eval_forward():
@@ -180,24 +185,33 @@ def test_res101_five_sets_vs_oracle():
     assert tuple(cls_prob.shape) == (sets * 300, 2)
 
 
-def test_full_size_query_vs_oracle():
-    """The headline configuration itself (BASELINE.json configs[1], one episode of it): a 600x1000 query with 2 support
-    sets x 3 shots of 320x320 crops, every stage against the oracle at the north-star tolerance (1e-3, max-norm)."""
-    import dana_b200  # noqa: F401
-    from dana_b200.engine import DanaEngine
+@pytest.fixture(scope="module")
+def full_size_ref():
     k, sets = 3, 2
     p = O.make_params(1996, attn_std=0.05)
     im, info, sup = O.synth_inputs(21, 1, 600, 1000, k * sets)
     with torch.no_grad():
         ref = O.dana_forward_eval(p, im, info, sup, k)
-    eng = DanaEngine(p, n_shot=k, precision="bf16x3")
+    return p, im, info, sup, ref
+
+
+@pytest.mark.parametrize("precision", ["mixed", "bf16x3"])
+def test_full_size_query_vs_oracle(full_size_ref, precision):
+    """The headline configuration itself (BASELINE.json configs[1], one episode of it): a 600x1000 query with 2 support
+    sets x 3 shots of 320x320 crops, every stage against the oracle at the north-star tolerance (1e-3, max-norm), in
+    both parity modes (the benchmarked mixed mode and the all-bf16x3 mode)."""
+    import dana_b200  # noqa: F401
+    from dana_b200.engine import DanaEngine
+    k, sets = 3, 2
+    p, im, info, sup, ref = full_size_ref
+    eng = DanaEngine(p, n_shot=k, precision=precision)
     want = ("base_feat", "dense", "pooled", "fc7", "rpn_fg")
     rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want)
     assert tuple(ex["base_feat"].shape) == (1, 1024, 38, 63)
     assert relerr(ex["base_feat"], ref["base_feat"]) <= TOL
     assert relerr(ex["dense"], ref["dense"]) <= TOL
     assert relerr(ex["rpn_fg"], ref["rpn_cls_prob"][:, 12:].permute(0, 2, 3, 1).reshape(1, -1)) <= TOL
-    assert roi_set_match(rois, ref["rois"]) >= 0.97
+    assert roi_set_match(rois, ref["rois"]) >= (0.97 if precision == "bf16x3" else 0.95)
     rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want,
                                            teacher={"rois": ref["rois"].cuda()})
     assert relerr(ex["pooled"], ref["pooled"]) <= TOL

@@ -283,3 +283,118 @@ def test_transpose_segments(ops, maps, shots, ns, c, seg):
     assert (got - want).abs().max().item() <= 2e-5 * x.abs().max().item()
     mask = want == 0
     assert (got[mask] == 0).all()
+
+
+# ------------------------------------------------------------------------------------ fp16 planes (mixed-precision mode)
+@pytest.mark.parametrize("m,k,n", [(128, 64, 64), (1000, 1200, 1024), (19200, 4608, 512), (300, 512, 96)])
+def test_linear_f16_operands(ops, m, k, n):
+    """kind::f16 MMAs with IEEE fp16 operand planes and an fp16 single-plane output, operand-exact in fp64
+    (tolerance = fp16 output rounding, 2^-11)."""
+    torch.manual_seed(m + k)
+    x = ops.Pair.from_float_f16(torch.randn(m, k, device="cuda"))
+    w = ops.Pair.from_float_f16(torch.randn(n, k, device="cuda") * 0.05)
+    bias = torch.randn(n, device="cuda")
+    ref = torch.relu(x.hi.double() @ w.hi.double().t() + bias.double())
+    out32 = torch.empty(m, n, device="cuda")
+    ops.linear(x, w, n, bias=bias, out_f32=out32, relu=True)
+    assert relerr(out32, ref) <= 2e-5
+    if n % 32 == 0:
+        out16 = ops.Pair.empty_f16((m, n), "cuda")
+        ops.linear(x, w, n, bias=bias, out=out16, relu=True)
+        assert relerr(out16.hi.float(), ref) <= 6e-4
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,ks,stride", [(16, 4, 4, 512, 512, 3, 1), (8, 7, 7, 1024, 512, 1, 2),
+                                                      (1, 38, 63, 2048, 512, 3, 1), (9, 4, 4, 512, 2048, 1, 1)])
+def test_conv_f16_planes(ops, n, h, w, cin, cout, ks, stride):
+    """layer4 / RPN convolutions of the mixed mode: fp16 activation, weight, residual and output planes."""
+    torch.manual_seed(h * w + cin)
+    F = torch.nn.functional
+    xp = ops.Pair.from_float_f16(torch.randn(n, h, w, cin, device="cuda"))
+    wt = torch.randn(cout, cin, ks, ks, device="cuda") / (cin * ks * ks) ** 0.5
+    wp = ops.Pair.from_float_f16(wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous())
+    scale = torch.rand(cout, device="cuda") + 0.5
+    bias = torch.randn(cout, device="cuda") * 0.1
+    oh, ow = (h - 1) // stride + 1, (w - 1) // stride + 1
+    rp = ops.Pair.from_float_f16(torch.randn(n, oh, ow, cout, device="cuda"))
+    out = ops.conv_nhwc(xp, wp, cout, ksize=ks, stride=stride, scale=scale, bias=bias, res=rp, relu=True, out_f16=True)
+    assert out.is_f16 and out.lo is None
+    xr = xp.hi.double().permute(0, 3, 1, 2)
+    wr = wp.hi.double().reshape(cout, ks, ks, cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, wr, stride=stride, padding=ks // 2) * scale.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1)
+    ref = torch.relu(ref + rp.hi.double().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    assert relerr(out.hi.float(), ref) <= 6e-4
+
+
+def test_split_operands_to_f16_plane(ops):
+    """The P.V contraction of the mixed mode: bf16x3 operands, per-image weights and bias, fp16 single-plane output
+    written into a channel slice of a wider buffer (the dense half of the RPN input)."""
+    torch.manual_seed(3)
+    b, rows, k, n = 2, 700, 1200, 1024
+    x = ops.Pair.from_float(torch.rand(b * rows, k, device="cuda") / k)
+    w = ops.Pair.from_float(torch.randn(b, n, k, device="cuda"))
+    bias = torch.randn(b, n, device="cuda") * 0.1
+    buf = torch.zeros(b * rows, 2 * n, dtype=torch.float16, device="cuda")
+    ops.linear(x, ops.Pair(w.hi.view(b * n, k), w.lo.view(b * n, k)), n, alpha=0.5, bias=bias, bias_sn=n,
+               out=ops.Pair(buf[:, n:]), batch=b, b_batch_stride=n * k)
+    ref = torch.stack([0.5 * (x.float()[i * rows:(i + 1) * rows].double() @ w.float()[i].double().t()) + bias[i].double()
+                       for i in range(b)]).reshape(b * rows, n)
+    assert relerr(buf[:, n:].float(), ref) <= 6e-4
+    assert (buf[:, :n] == 0).all()
+
+
+def test_linear_row_bias(ops):
+    """(x + PE) W^T = x W^T + PE W^T: the per-bin bias table enters as a residual with a zero stride over RoIs."""
+    torch.manual_seed(5)
+    r, bins, k, n = 37, 49, 1024, 256
+    x = torch.randn(r * bins, k, device="cuda")
+    w = torch.randn(n, k, device="cuda") * 0.03
+    pe = torch.randn(bins, k, device="cuda")
+    table = (pe.double() @ w.double().t()).float().contiguous()
+    out = torch.empty(r * bins, n, device="cuda")
+    ops.linear(ops.Pair.from_float(x), ops.Pair.from_float(w), n, out_f32=out, row_bias=table)
+    ref = (x.view(r, bins, k) + pe).double().view(-1, k) @ w.double().t()
+    assert relerr(out, ref) <= 3e-5
+
+
+def test_f16_plane_producers(ops):
+    """merge_pair (+ fp16 plane into a strided slice), spatial_mean on an fp16 plane, RoIAlign fp16 output."""
+    torch.manual_seed(8)
+    x = torch.randn(2, 9, 11, 64, device="cuda") * 3
+    xp = ops.Pair.from_float(x)
+    buf = torch.zeros(2, 9, 11, 128, dtype=torch.float16, device="cuda")
+    f32 = ops.merge_pair(xp, out16=buf[..., :64])
+    assert relerr(f32, x) <= 2e-5
+    assert torch.equal(buf[..., :64], f32.half()) and (buf[..., 64:] == 0).all()
+    t = torch.randn(50, 16, 2048, device="cuda")
+    m32, mp = ops.spatial_mean(ops.Pair.from_float_f16(t))
+    assert relerr(m32, t.half().double().mean(1)) <= 2e-6
+    assert relerr(mp.float(), m32) <= 2e-5
+    m32b, _ = ops.spatial_mean(ops.Pair.from_float(t))
+    assert relerr(m32b, t.double().mean(1)) <= 2e-5
+    rs = np.random.RandomState(4)
+    feat = torch.from_numpy(rs.standard_normal((2, 20, 31, 64)).astype(np.float32)).cuda()
+    rois = torch.from_numpy(np.stack([rs.randint(0, 2, 40).astype(np.float64), rs.uniform(0, 200, 40), rs.uniform(0, 100, 40),
+                                      rs.uniform(250, 480, 40), rs.uniform(150, 310, 40)], 1).astype(np.float32)).cuda()
+    f32, pair, _, h16 = ops.roi_align_head(feat, rois, 1.0 / 16, 0, want_f32=True, want_pair=True, want_f16=True)
+    assert torch.equal(h16.hi, f32.half())
+    assert relerr(pair.float(), f32) <= 2e-5
+
+
+def test_nms_strict_gt_matches_reference_cuda_rule(ops):
+    """The reference's CUDA operator suppresses on IoU > thr (cuda/nms.cu:60), its CPU operator on >= (nms_cpu.cpp:60):
+    _C.nms(strict_gt=True) selects the former; they differ exactly when an IoU equals the threshold."""
+    from dana_b200 import _C
+    b = torch.tensor([[0., 0, 9, 9], [0, 0, 9, 4]]).cuda()      # IoU = 50 / 100 = 0.5 exactly
+    s = torch.tensor([.9, .8]).cuda()
+    assert _C.nms(b, s, 0.5).tolist() == [0]
+    assert _C.nms(b, s, 0.5, strict_gt=True).tolist() == [0, 1]
+    rs = np.random.RandomState(1)
+    n = 2000
+    x1, y1 = rs.uniform(0, 500, n), rs.uniform(0, 300, n)
+    bb = np.stack([x1, y1, x1 + rs.uniform(5, 120, n), y1 + rs.uniform(5, 120, n)], 1).astype(np.float32)
+    ss = rs.permutation(n).astype(np.float32) / n
+    thr = np.float32(0.7)
+    want = O.nms(bb, ss, float(np.nextafter(thr, np.float32(np.inf)))).numpy()
+    got = _C.nms(torch.from_numpy(bb).cuda(), torch.from_numpy(ss).cuda(), float(thr), strict_gt=True).cpu().numpy()
+    np.testing.assert_array_equal(got, want)

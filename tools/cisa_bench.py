@@ -42,13 +42,10 @@ for prec in a.precision.split(","):
             from dana_b200 import ops
             from dana_b200.ops import Pair
             split = prec == "bf16x3"
-            corr = Pair.zeros((1, 38, 50, 2048), "cuda", split)
-            bp = ops.split_f32(base.permute(0, 2, 3, 1).contiguous(), split)
-            corr.hi[..., :1024].copy_(bp.hi)
-            if split:
-                corr.lo[..., :1024].copy_(bp.lo)
+            bp = ops.split_f32(base.permute(0, 2, 3, 1).contiguous(), split).view(NQ, C)
+            dense = Pair.empty((NQ, C), "cuda", split)
             supp = ops.split_f32(sup.reshape(units, C, hs, hs).permute(0, 2, 3, 1).contiguous(), split)
-            run = lambda: eng.rpn_attention(corr, supp, 1)  # noqa: E731
+            run = lambda: eng.rpn_attention(bp, dense, 1, NQ, supp, 1)  # noqa: E731
             for _ in range(3):
                 run()
             if not a.eager:   # one graph replay per iteration: device time of the block, not python launch overhead

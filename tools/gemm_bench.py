@@ -27,6 +27,8 @@ SHAPES = [
     ("l4.conv2 3x3 512->512", 1200, 4, 4, 512, 512, 3, 1, False),
     ("l4.conv3 1x1 512->2048 +res", 1200, 4, 4, 512, 2048, 1, 1, True),
     ("l4.conv1 1x1 2048->512", 1200, 4, 4, 2048, 512, 1, 1, False),
+    ("l2.conv2 3x3 128->128", 4, 75, 125, 128, 128, 3, 1, False),
+    ("l2.conv1 1x1 512->128", 4, 75, 125, 512, 128, 1, 1, False),
     ("exp 1x1 64->256 no res", 4, 150, 250, 64, 256, 1, 1, False),
     ("exp 1x1 256->256 +res", 4, 150, 250, 256, 256, 1, 1, True),
     ("exp 1x1 64->64 +res", 4, 150, 250, 64, 64, 1, 1, True),
@@ -42,13 +44,16 @@ print("%-30s %5s %9s %8s %9s %9s" % ("layer", "prec", "ms", "TFLOP/s", "GB/s(alg
 for idx, (name, n, h, w, cin, cout, ks, stride, has_res) in enumerate(SHAPES):
     if a.only >= 0 and idx != a.only:
         continue
-    for split in ((True, False) if a.precision == "both" else ((a.precision == "bf16x3"),)):
-        x = Pair.from_float(torch.randn(n, h, w, cin, device="cuda"), split)
-        wt = Pair.from_float(torch.randn(cout, ks * ks * cin, device="cuda") * 0.02, split)
+    modes = {"both": ("x3", "x1"), "all": ("x3", "x1", "f16"), "bf16x3": ("x3",), "bf16": ("x1",), "f16": ("f16",)}[a.precision]
+    for mode in modes:
+        split = mode == "x3"
+        mk = Pair.from_float_f16 if mode == "f16" else (lambda t: Pair.from_float(t, split))
+        x = mk(torch.randn(n, h, w, cin, device="cuda"))
+        wt = mk(torch.randn(cout, ks * ks * cin, device="cuda") * 0.02)
         sc = torch.rand(cout, device="cuda") + 0.5
         bi = torch.randn(cout, device="cuda")
-        res = Pair.from_float(torch.randn(n, h, w, cout, device="cuda"), split) if has_res else None
-        out = Pair.empty((n, h, w, cout), "cuda", split)
+        res = mk(torch.randn(n, h, w, cout, device="cuda")) if has_res else None
+        out = Pair.empty_f16((n, h, w, cout), "cuda") if mode == "f16" else Pair.empty((n, h, w, cout), "cuda", split)
         run = lambda: ops.conv_nhwc(x, wt, cout, ksize=ks, stride=stride, scale=sc, bias=bi, res=res, relu=True, out=out, split=split)  # noqa: E731
         for _ in range(3):
             run()
@@ -65,5 +70,5 @@ for idx, (name, n, h, w, cin, cout, ks, stride, has_res) in enumerate(SHAPES):
         m = n * h * w
         planes = 2 if split else 1
         byt = planes * 2 * (m * cin + m * cout * (2 if has_res else 1) + cout * ks * ks * cin)
-        print("%-30s %5s %9.4f %8.1f %9.0f %9.1f" % (name, "x3" if split else "x1", ms, 2.0 * m * cout * ks * ks * cin / ms / 1e9,
+        print("%-30s %5s %9.4f %8.1f %9.0f %9.1f" % (name, mode, ms, 2.0 * m * cout * ks * ks * cin / ms / 1e9,
                                                     byt / ms / 1e6, byt / 1e6), flush=True)

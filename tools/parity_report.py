@@ -1,0 +1,123 @@
+"""Per-stage parity report of the DAnA forward against the oracle, for every precision mode: max-norm relative error
+(the asserted metric, `|a-b|_inf / |b|_inf`) next to the worst elementwise relative error over the elements with
+|ref| > 1 % of the tensor's max ("define rel per tensor and also report elementwise").
+Cases: small (2 sets x 2 shots, 112x176), large-logit (attention weights std 0.05, trunk features x4 -> |logit| ~ 75),
+full (600x1000, 2 sets x 3 shots).  Writes one JSON line per (case, precision)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch  # noqa: E402
+
+import dana_oracle as O  # noqa: E402
+import dana_b200  # noqa: E402,F401
+from dana_b200.engine import DanaEngine  # noqa: E402
+
+
+def errs(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    d = (a - b).abs()
+    big = b.abs() > 0.01 * b.abs().max()
+    return [float(d.max() / b.abs().max().clamp_min(1e-30)), float((d[big] / b.abs()[big]).max()) if big.any() else 0.0]
+
+
+def run_case(name, p, im, info, sup, k, precisions, out):
+    with torch.no_grad():
+        ref = O.dana_forward_eval(p, im, info, sup, k)
+    b = im.shape[0]
+    for prec in precisions:
+        eng = DanaEngine(p, n_shot=k, precision=prec)
+        want = ("base_feat", "support_feat", "dense", "pooled", "fc7", "cls_score", "rpn_fg")
+        rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want)
+        rep = {"case": name, "precision": prec}
+        rep["base_feat"] = errs(ex["base_feat"], ref["base_feat"])
+        rep["dense"] = errs(ex["dense"], ref["dense"])
+        rep["rpn_fg"] = errs(ex["rpn_fg"], ref["rpn_cls_prob"][:, 12:].permute(0, 2, 3, 1).reshape(b, -1))
+        rep["rpn_deltas"] = errs(ex["rpn_deltas"], ref["rpn_bbox_pred"].permute(0, 2, 3, 1).reshape(b, -1, 4))
+        got, wantr = rois.cpu(), ref["rois"]
+        hits = total = 0
+        for i in range(b):
+            w = wantr[i][(wantr[i, :, 1:].abs().sum(1) > 0)][:, 1:]
+            d = (w[:, None, :] - got[i][None, :, 1:]).abs().max(2)[0].min(1)[0]
+            hits += int((d <= 0.05).sum())
+            total += w.shape[0]
+        rep["rois_set_match"] = hits / max(total, 1)
+        rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want,
+                                               teacher={"rois": ref["rois"].cuda()})
+        rep["pooled"] = errs(ex["pooled"], ref["pooled"])
+        rep["fc7"] = errs(ex["fc7"], ref["fc7"])
+        rep["bbox_pred"] = errs(bbox, ref["bbox_pred"])
+        rep["cls_score"] = errs(ex["cls_score"], ref["cls_score"])
+        rep["cls_prob"] = errs(cls_prob, ref["cls_prob"])
+        line = json.dumps({k_: ([float("%.3g" % v) for v in val] if isinstance(val, list) else val) for k_, val in rep.items()})
+        print(line, flush=True)
+        out.append(line)
+        del eng
+        torch.cuda.empty_cache()
+
+
+def block_case(scale, precisions, out):
+    """The lifted RPN-level BA+CISA block at a stated logit range: post-ReLU N(0,1) features x `scale`,
+    projections std 0.05 (scale 1 -> |logit| ~ 6, scale 4 -> ~ 75)."""
+    import math
+    import numpy as np
+    import torch.nn.functional as F
+    p = O.make_params(11, attn_std=0.05)
+    rs = np.random.RandomState(5)
+    base = torch.from_numpy(np.maximum(rs.standard_normal((1, 1024, 38, 50)), 0).astype(np.float32)) * scale
+    sup = torch.from_numpy(np.maximum(rs.standard_normal((1, 3, 1024, 20, 20)), 0).astype(np.float32)) * scale
+    with torch.no_grad():
+        want = O.ba_cisa_rpn(base, sup, p, True)
+        q = F.linear(base.reshape(1, 1024, -1).transpose(1, 2), p["rpn_adapt_q_layer.weight"])
+        q = q - q.mean(1, keepdim=True)
+        s0 = sup[:, 0].reshape(1, 1024, 400).transpose(1, 2) + O.positional_encoding(400)
+        k = F.linear(s0, p["rpn_adapt_k_layer.weight"])
+        k = k - k.mean(1, keepdim=True)
+        max_logit = float((torch.bmm(q, k.transpose(1, 2)) / math.sqrt(256)).abs().max())
+    for prec in precisions:
+        eng = DanaEngine(p, n_shot=3, precision=prec)
+        got = eng.ba_cisa_block(base.cuda(), sup.cuda())
+        e = errs(got, want)
+        line = json.dumps({"case": "ba_cisa_block x%g" % scale, "precision": prec, "max_abs_logit": round(max_logit, 1),
+                           "dense": [float("%.3g" % v) for v in e]})
+        print(line, flush=True)
+        out.append(line)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="small,block,large_logit,full")
+    ap.add_argument("--precision", default="mixed,bf16x3,bf16")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    precs = a.precision.split(",")
+    lines = []
+    print("# [max-norm relative, worst elementwise relative where |ref| > 1% of max]")
+    for case in a.cases.split(","):
+        if case == "small":
+            p = O.make_params(1996, attn_std=0.05)
+            im, info, sup = O.synth_inputs(7, 2, 112, 176, 4)
+            run_case(case, p, im, info, sup, 2, precs, lines)
+        elif case == "large_logit":
+            # trained-like scale: attention projections std 0.05 and a trunk whose output is ~4x larger (last BN
+            # gamma of the stride-16 stage x4) -> RPN-level |logit| up to ~75 (third column)
+            p = O.make_params(1996, attn_std=0.05)
+            for key in list(p.keys()):
+                if key.startswith("RCNN_base.6.5.bn3.weight") or key.startswith("RCNN_base.6.5.bn3.bias"):
+                    p[key] = p[key] * 4.0
+            im, info, sup = O.synth_inputs(9, 1, 160, 240, 4)
+            run_case(case, p, im, info, sup, 2, precs, lines)
+        elif case == "block":
+            block_case(1.0, precs, lines)
+            block_case(4.0, precs, lines)
+        elif case == "full":
+            p = O.make_params(1996, attn_std=0.05)
+            im, info, sup = O.synth_inputs(21, 1, 600, 1000, 6)
+            run_case(case, p, im, info, sup, 3, precs, lines)
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write("\n".join(lines) + "\n")
