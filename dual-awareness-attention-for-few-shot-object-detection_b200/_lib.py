@@ -44,6 +44,22 @@ class ConvGemmArgs(Structure):
     ]
 
 
+class CisaArgs(Structure):
+    """Mirror of `dana_cisa_args` (include/dana_b200.h)."""
+    _fields_ = [
+        ("q_hi", c_void_p), ("q_lo", c_void_p), ("q_pitch", c_int64),
+        ("s_hi", c_void_p), ("s_lo", c_void_p),
+        ("batch", c_int32), ("nq", c_int32), ("sets", c_int32), ("shots", c_int32), ("ns", c_int32), ("c", c_int32),
+        ("d", c_int32),
+        ("pe", c_void_p),
+        ("wq_hi", c_void_p), ("wq_lo", c_void_p), ("wk_hi", c_void_p), ("wk_lo", c_void_p),
+        ("un_w", c_void_p), ("un_b", c_void_p), ("unary_gamma", c_float),
+        ("ba_w", c_void_p), ("ba_b", c_void_p), ("gamma", c_float),
+        ("out_hi", c_void_p), ("out_lo", c_void_p), ("out_pitch", c_int64), ("out_f16", c_int32),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
+    ]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header.
 SIGNATURES = {
     "dana_abi_version": (c_int, []),
@@ -69,6 +85,8 @@ SIGNATURES = {
                                     c_int, c_int, c_float, c_float, c_float, c_void_p, c_int, c_int, c_void_p]),
     "dana_conv_gemm_workspace_bytes": (c_int64, []),
     "dana_conv_gemm": (c_int, [POINTER(ConvGemmArgs), c_void_p]),
+    "dana_cisa_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "dana_cisa_fwd": (c_int, [POINTER(CisaArgs), c_void_p]),
     "dana_stem_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dana_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dana_avgpool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

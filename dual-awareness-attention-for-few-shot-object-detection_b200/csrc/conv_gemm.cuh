@@ -527,7 +527,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint4 rh[4], rl[4];
       auto prefetch = [&](int c) {
         if constexpr (FAST) {
-          if (res_pair) {
+          if (res_pair && co0 + c * 32 < p.n_out) {
             const int ofs = (c - c_begin) * 32;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -691,6 +691,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       for (int ci = 0; ci < kCpw; ++ci) {
         const int c = c_begin + ci;
         if (c >= kChunks) break;
+        // the last N-tile may be partial; FAST launches have n_out % 32 == 0, so a chunk is either whole or absent
+        // (the generic path predicates per element)
+        if (FAST && co0 + c * 32 >= p.n_out) break;
         // ---- phase A: accumulator row -> scale/bias -> swizzled smem tile
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +

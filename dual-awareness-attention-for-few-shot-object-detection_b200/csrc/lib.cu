@@ -1,4 +1,5 @@
 // libdana_b200.so -- single translation unit: kernels + extern "C" entry points (include/dana_b200.h).
+#include <math.h>
 #include <string.h>
 
 #include "api_common.cuh"
@@ -116,5 +117,6 @@ int dana_episode_resize(const void* src, int src_is_f32, int src_h, int src_w, i
 }
 
 #include "dana_ops_api.inc"
+#include "cisa_api.inc"
 
 }  // extern "C"

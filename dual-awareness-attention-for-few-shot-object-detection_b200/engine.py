@@ -254,6 +254,15 @@ class DanaEngine:
         dense_out [B*nq, 1024] (any row pitch; bf16 pair or one fp16 plane) receives the attended support feature --
         when both are channel halves of one [B,h,w,2048] buffer the `cat` of :154 comes for free.
         sup [B*sets*K, hs, ws, 1024]: support maps, image-major; set 0 of every image drives the block."""
+        maps, sh, sw, c = sup.hi.shape
+        ns = sh * sw
+        if os.environ.get("DANA_CISA_PY") == "1":      # the same stages sequenced from Python (debugging aid)
+            return self._rpn_attention_py(base2d, dense_out, b, nq, sup, sets)
+        ops.cisa_fwd(base2d, sup.view(maps, ns, c), self.pe(ns), self.n_shot, sets, b, wq=self.rpn_q_w, wk=self.rpn_k_w,
+                     un_w=self.rpn_un_w, un_b=self.rpn_un_b, unary_gamma=self.unary_gamma, ba_w=self.ba_w, ba_b=self.ba_b,
+                     gamma=self.channel_gamma, out=dense_out)
+
+    def _rpn_attention_py(self, base2d: Pair, dense_out: Pair, b, nq, sup: Pair, sets=1):
         split, k, dev = self.split, self.n_shot, self.device
         maps, sh, sw, c = sup.hi.shape
         ns = sh * sw

@@ -35,7 +35,8 @@ def _sk_workspace(device):
     ws = _SK_WS.get(key)
     if ws is None:
         nbytes = _lib.load().dana_conv_gemm_workspace_bytes()
-        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        ws[:4096].zero_()      # only the ready flags need a defined start; the kernel hands them back as zero
         _SK_WS[key] = ws
     _SK_EPOCH = _SK_EPOCH % 0x7FFFFFF0 + 1
     return ws, _SK_EPOCH
@@ -450,6 +451,46 @@ def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b
     if want_cbar:
         return vc, vt, rbar, cbar
     return vc, vt, rbar
+
+
+# scratch of dana_cisa_fwd, one per (device, stream, size)
+_CISA_WS = {}
+
+
+def cisa_fwd(q: Pair, sup: Pair, pe, shots, sets, batch, *, wq: Pair, wk: Pair, un_w, un_b, unary_gamma=0.1, ba_w=None,
+             ba_b=None, gamma=0.1, out: Pair):
+    """RPN-level BA + CISA block in ONE C call (dana_cisa_fwd; dana.py:117-151).
+    q [batch*nq, c] query feature (any row pitch); sup [batch*sets*shots, ns, c] support maps (set 0 of every image
+    drives the block); out [batch*nq, c] (any row pitch): bf16 pair, or one fp16 plane."""
+    _need_cuda(q.hi, sup.hi, out.hi)
+    rows, c = q.hi.shape
+    maps, ns, c2 = sup.hi.shape
+    d = wq.hi.shape[0]
+    assert c2 == c and rows % batch == 0 and maps == batch * sets * shots
+    assert sup.hi.is_contiguous() and (sup.lo is None or sup.lo.is_contiguous())
+    nq = rows // batch
+    lib = _lib.load()
+    dev = q.hi.device
+    nbytes = lib.dana_cisa_workspace_bytes(batch, nq, sets, shots, ns, c, d)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(index).cuda_stream, nbytes)
+    ws = _CISA_WS.get(key)
+    if ws is None:
+        ws = _CISA_WS[key] = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    a = _lib.CisaArgs()
+    a.q_hi, a.q_lo, a.q_pitch = _p(q.hi), _p(q.lo), q.hi.stride(0)
+    a.s_hi, a.s_lo = _p(sup.hi), _p(sup.lo)
+    a.batch, a.nq, a.sets, a.shots, a.ns, a.c, a.d = batch, nq, sets, shots, ns, c, d
+    a.pe = _p(pe)
+    a.wq_hi, a.wq_lo, a.wk_hi, a.wk_lo = _p(wq.hi), _p(wq.lo), _p(wk.hi), _p(wk.lo)
+    a.un_w, a.un_b, a.unary_gamma = _p(un_w), _p(un_b), float(unary_gamma)
+    a.ba_w, a.ba_b, a.gamma = _p(ba_w), _p(ba_b), float(gamma)
+    a.out_hi, a.out_lo, a.out_pitch = _p(out.hi), _p(out.lo), out.hi.stride(0)
+    a.out_f16 = 1 if out.is_f16 else 0
+    a.workspace, a.workspace_bytes = _p(ws), nbytes
+    _count(15 if ns > 256 else 14)     # 4 support kernels, 4 GEMMs, 3 centring kernels (1 for small groups), softmax, memsets
+    check(lib.dana_cisa_fwd(ctypes.byref(a), _stream()), "dana_cisa_fwd")
+    return out
 
 
 def transpose_segments(x_f32, shots, seg_pitch, vt_pitch, split=True):

@@ -181,6 +181,47 @@ int64_t dana_conv_gemm_workspace_bytes(void);
 int dana_conv_gemm(const dana_conv_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------
+ * BA + CISA block, RPN level -- replaces the inline PyTorch of lib/model/framework/dana.py:117-151 (there is no such
+ * operator in the reference; SURVEY.md section 8b introduces it behind the module boundary): positional encoding of
+ * the support maps, background-attenuation gate, q / k projections with mean-centring, softmax(Q K^T / sqrt(d)) per
+ * shot plus the unary term, attention-weighted values, mean over shots.
+ *
+ * q: the query feature, bf16 pair [batch*nq][c], row pitch q_pitch (e.g. the first channel half of the RPN input).
+ * s: support maps, bf16 pair [batch*sets*shots][ns][c], image-major; set 0 of every image drives the block.
+ * pe fp32 [ns][c]; wq / wk bf16 pairs [d][c] (the Linear biases cancel under the centring); un_w [c], un_b [1] the
+ * unary Linear; ba_w [c], ba_b [1] the BA Linear (NULL: no BA block, semantic_enhance=False).
+ * out: attended support feature [batch*nq][c] with row pitch out_pitch, as a bf16 pair (out_hi/out_lo) or, with
+ * out_f16, as one fp16 plane in out_hi (out_lo NULL).  lo planes all NULL = plain-bf16 operands.
+ * workspace: dana_cisa_workspace_bytes(...) bytes, 256-byte aligned, uninitialised, private to one stream.  ns <= 512. */
+typedef struct dana_cisa_args {
+  const void* q_hi;
+  const void* q_lo;
+  int64_t q_pitch;
+  const void* s_hi;
+  const void* s_lo;
+  int32_t batch, nq, sets, shots, ns, c, d;
+  const float* pe;
+  const void* wq_hi;
+  const void* wq_lo;
+  const void* wk_hi;
+  const void* wk_lo;
+  const float* un_w;
+  const float* un_b;
+  float unary_gamma;
+  const float* ba_w;
+  const float* ba_b;
+  float gamma;
+  void* out_hi;
+  void* out_lo;
+  int64_t out_pitch;
+  int32_t out_f16;
+  void* workspace;
+  int64_t workspace_bytes;
+} dana_cisa_args;
+int64_t dana_cisa_workspace_bytes(int batch, int nq, int sets, int shots, int ns, int c, int d);
+int dana_cisa_fwd(const dana_cisa_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
  * CUDA-core stages of the path (each replaces the torch ops named).
  * bf16 "pairs" are (hi, lo) planes with x ~= hi + lo; lo may be NULL.
  * ------------------------------------------------------------------------ */

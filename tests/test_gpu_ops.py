@@ -398,3 +398,21 @@ def test_nms_strict_gt_matches_reference_cuda_rule(ops):
     want = O.nms(bb, ss, float(np.nextafter(thr, np.float32(np.inf)))).numpy()
     got = _C.nms(torch.from_numpy(bb).cuda(), torch.from_numpy(ss).cuda(), float(thr), strict_gt=True).cpu().numpy()
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("m,k,n", [(300, 512, 96), (1000, 192, 160), (4000, 64, 320)])
+def test_linear_pair_output_partial_last_tile(ops, m, k, n):
+    """Row-contiguous (FAST) epilogue with n_out a multiple of 32 but not of the tile width: the chunks of the last
+    N-tile that lie past n_out must not be written (they would land in the next row)."""
+    torch.manual_seed(n)
+    x = ops.Pair.from_float(torch.randn(m, k, device="cuda"))
+    w = ops.Pair.from_float(torch.randn(n, k, device="cuda") * 0.05)
+    res = ops.Pair.from_float(torch.randn(m, n, device="cuda"))
+    buf = ops.Pair.zeros((m + 1, n), "cuda")                      # one guard row behind the output
+    out = ops.Pair(buf.hi[:m], buf.lo[:m])
+    rows_total = m
+    ops.conv_gemm(x, (k, rows_total, 1, 1), (k, k * m, k * m), w, n, (rows_total, 1, 1), (n, n * m, n * m), out=out,
+                  res=res, r_strides=(n, n * m, n * m), relu=True)
+    ref = torch.relu(x.float().double() @ w.float().double().t() + res.float().double())
+    assert relerr(out.float(), ref) <= 2e-5
+    assert (buf.hi[m] == 0).all() and (buf.lo[m] == 0).all()
