@@ -51,6 +51,7 @@ struct ConvGemmParams {
   int n_fast;           // tile order: 1 = the N-tiles of an M-tile are consecutive work items, 0 = N is the slow index
   int a_prefetch;       // producer prefetches the next tile's activation boxes into L2
   int ab_f16;           // operands are IEEE fp16 planes (kind::f16 with F16 formats) instead of bf16
+  int dx_box_bytes;     // DX3: bytes of one window box per plane, bw * (bh + 2) rows of the K-tile
 };
 
 constexpr int kGemmThreads = 320;
@@ -59,12 +60,22 @@ constexpr int kTileM = 128;
 // has two planes per operand, i.e. only two 96 KB stages; its long-K launches use KT = 32 (64-byte swizzle rows,
 // four 48 KB stages), which covers the TMA latency better (measured: RPN 3x3 conv 0.406 -> 0.357 ms).  Narrow tiles
 // already have >= 3 stages and lose with the halved boxes (twice the TMA / barrier traffic), so they stay at 64.
-template <int BLOCK_N, int NSPLIT, int KT = 64>
+// DX3: 3x3 stride-1 pad-1 convolution with the input window loaded ONCE PER COLUMN SHIFT instead of once per tap.
+// The output tile is bw x bh pixels (bw = 8 or 16, bw * bh = 128, row m = y * bw + x).  For dx in {0,1,2} one TMA box
+// of bw x (bh + 2) pixels starting at (x0 + dx - 1, y0 - 1) lands in shared memory as (bh + 2) * bw rows; the A
+// operand of tap (dy, dx) is that box from row dy * bw on -- 128 consecutive rows whose start is a whole number of
+// 8-row swizzle atoms, so the UMMA descriptor needs nothing special.  A pipeline stage holds one such box and the
+// three weight tiles of its taps: 3 window loads per channel block instead of 9, i.e. 1.1x instead of 9x the
+// activation bytes through L2 -> SM (ncu on layer1's 3x3: 530 MB pulled through TMA for 77 MB of operands).
+template <int BLOCK_N, int NSPLIT, int KT = 64, bool DX3 = false>
 struct ConvGemmCfg {
   static constexpr int kTileK = KT;
-  static constexpr int kATileBytes = kTileM * kTileK * 2;   // per plane
-  static constexpr int kBTileBytes = BLOCK_N * kTileK * 2;
-  static constexpr int kStageBytes = NSPLIT * (kATileBytes + kBTileBytes);
+  static constexpr int kARows = DX3 ? 160 : kTileM;          // 8 x 18 = 144 or 16 x 10 = 160 window rows
+  static constexpr int kBTaps = DX3 ? 3 : 1;
+  static constexpr int kATileBytes = kARows * kTileK * 2;   // per plane
+  static constexpr int kBTileBytes = BLOCK_N * kTileK * 2;  // per plane and tap
+  static constexpr int kBGroupBytes = kBTaps * kBTileBytes;
+  static constexpr int kStageBytes = NSPLIT * (kATileBytes + kBGroupBytes);
   static constexpr int kBudget = 200 * 1024;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -115,14 +126,15 @@ struct SkRange {
 // EPI 3: FAST with single-plane fp16 output / residual (out_hi, res_hi are __half planes, no lo plane) whatever the
 // operand planes are: the producer of an fp16-operand layer (the layers that run one MMA per product, see
 // DESIGN.md section 3) writes the plane its consumer feeds to the tensor cores.  Values saturate at +-65504.
-template <int BLOCK_N, int NSPLIT, int EPI, int CM, int KT = 64>
+template <int BLOCK_N, int NSPLIT, int EPI, int CM, int KT = 64, bool DX3 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  static_assert(!DX3 || (CM == 1 && EPI != 2), "DX3: single-CTA clusters, no softmax epilogue");
   constexpr bool FAST = (EPI == 1 || EPI == 3);
   constexpr bool F16IO = (EPI == 3);
   constexpr bool OUT2 = (NSPLIT == 2) && !F16IO;   // output / residual carry a lo plane
   constexpr bool SOFTMAX = (EPI == 2);
-  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT>;
+  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT, DX3>;
   constexpr int kTileK = Cfg::kTileK;
   constexpr int kATileBytes = Cfg::kATileBytes;
   constexpr int kStages = Cfg::kStages;
@@ -149,7 +161,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_kb = p.taps_r * p.taps_s * p.c_blocks;
+  const int num_kb = (DX3 ? 3 : p.taps_r * p.taps_s) * p.c_blocks;
   const int sp_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   // work item w -> (N-tile, group of CM consecutive M-tiles); this CTA takes M-tile group*CM + rank, which may
   // lie past the end (phantom tile: TMA zero-fills, the epilogue masks every row) so that all CTAs of a cluster
@@ -260,12 +272,27 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           const int tap = kb / p.c_blocks;
           const int cb = kb - tap * p.c_blocks;
-          const int r = tap / p.taps_s;
-          const int s = tap - r * p.taps_s;
           mbar_wait(&empty_bar[stage], phase ^ 1, 101);
           uint8_t* st = tiles + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int ka = cb * kTileK;
+          if constexpr (DX3) {
+            // `tap` is the column shift dx: one window box (all three row shifts) + the weight tiles of taps (dy, dx)
+            mbar_arrive_expect_tx(&full_bar[stage], NSPLIT * (p.dx_box_bytes + Cfg::kBGroupBytes));
+            tma_load_4d(st, &p.tm_a_hi, &full_bar[stage], ka, x0 + tap - 1, y0 - 1, n0);
+            if (NSPLIT == 2) tma_load_4d(st + kATileBytes, &p.tm_a_lo, &full_bar[stage], ka, x0 + tap - 1, y0 - 1, n0);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const int kbk = (dy * 3 + tap) * p.c_in + ka;
+              tma_load_3d(st + NSPLIT * kATileBytes + dy * Cfg::kBTileBytes, &p.tm_b_hi, &full_bar[stage], kbk,
+                          co_t * BLOCK_N, 0);
+              if (NSPLIT == 2)
+                tma_load_3d(st + NSPLIT * kATileBytes + Cfg::kBGroupBytes + dy * Cfg::kBTileBytes, &p.tm_b_lo,
+                            &full_bar[stage], kbk, co_t * BLOCK_N, 0);
+            }
+          } else {
+          const int r = tap / p.taps_s;
+          const int s = tap - r * p.taps_s;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int kbk = tap * p.c_in + cb * kTileK;
           tma_load_4d(st, &p.tm_a_hi, &full_bar[stage], ka, x0 + s - p.pad_x, y0 + r - p.pad_y, n0);
           if (CM == 1) {
@@ -283,6 +310,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               tma_load_3d_mc(st + 2 * kATileBytes + Cfg::kBTileBytes + cm_rank * (Cfg::kBTileBytes / CM), &p.tm_b_lo,
                              &full_bar[stage], kbk, co_t * BLOCK_N + cm_rank * (BLOCK_N / CM), 0, kMcMask);
             }
+          }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -311,22 +339,28 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint32_t a_hi = smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint32_t b_hi = a_hi + NSPLIT * kATileBytes;
 #pragma unroll
+          for (int dy = 0; dy < Cfg::kBTaps; ++dy) {
+            // DX3: tap (dy, dx) reads the window box from row dy * bw on (a whole number of 8-row swizzle atoms)
+            const uint32_t a_t = a_hi + (DX3 ? static_cast<uint32_t>(dy * p.bw * (kTileK * 2)) : 0u);
+            const uint32_t b_t = b_hi + static_cast<uint32_t>(dy * Cfg::kBTileBytes);
+#pragma unroll
           for (int k = 0; k < kTileK / 16; ++k) {
             const uint32_t koff = k * 32;  // 16 bf16 = 32 B inside the swizzled row
-            const uint64_t da = (kTileK == 64) ? umma_desc_sw128(a_hi + koff) : umma_desc_sw64(a_hi + koff);
-            const uint64_t db = (kTileK == 64) ? umma_desc_sw128(b_hi + koff) : umma_desc_sw64(b_hi + koff);
+            const uint64_t da = (kTileK == 64) ? umma_desc_sw128(a_t + koff) : umma_desc_sw64(a_t + koff);
+            const uint64_t db = (kTileK == 64) ? umma_desc_sw128(b_t + koff) : umma_desc_sw64(b_t + koff);
             if (NSPLIT == 2) {
-              const uint64_t dal = (kTileK == 64) ? umma_desc_sw128(a_hi + kATileBytes + koff)
-                                                  : umma_desc_sw64(a_hi + kATileBytes + koff);
-              const uint64_t dbl = (kTileK == 64) ? umma_desc_sw128(b_hi + Cfg::kBTileBytes + koff)
-                                                  : umma_desc_sw64(b_hi + Cfg::kBTileBytes + koff);
+              const uint64_t dal = (kTileK == 64) ? umma_desc_sw128(a_t + kATileBytes + koff)
+                                                  : umma_desc_sw64(a_t + kATileBytes + koff);
+              const uint64_t dbl = (kTileK == 64) ? umma_desc_sw128(b_t + Cfg::kBGroupBytes + koff)
+                                                  : umma_desc_sw64(b_t + Cfg::kBGroupBytes + koff);
               // small cross terms first, leading term last
-              umma_bf16(d_addr, dal, db, idesc, ((kb - kb_lo) | k) != 0);
+              umma_bf16(d_addr, dal, db, idesc, ((kb - kb_lo) | k | dy) != 0);
               umma_bf16(d_addr, da, dbl, idesc, 1);
               umma_bf16(d_addr, da, db, idesc, 1);
             } else {
-              umma_bf16(d_addr, da, db, idesc, ((kb - kb_lo) | k) != 0);
+              umma_bf16(d_addr, da, db, idesc, ((kb - kb_lo) | k | dy) != 0);
             }
+          }
           }
           if (CM == 1) {
             umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire

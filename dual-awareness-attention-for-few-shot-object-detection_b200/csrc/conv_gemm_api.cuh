@@ -32,13 +32,13 @@ inline TileChoice choose_tile(int w, int h, int n, bool batched_b) {
   return best;
 }
 
-template <int BLOCK_N, int NSPLIT, int EPI, int CM, int KT = 64>
+template <int BLOCK_N, int NSPLIT, int EPI, int CM, int KT = 64, bool DX3 = false>
 inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT>;
+  using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT, DX3>;
   static bool configured_dev[kMaxDevices] = {};
   bool& configured = configured_dev[current_device()];
   if (!configured) {
-    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM, KT>,
+    DANA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM, KT, DX3>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
@@ -74,7 +74,7 @@ inline int launch_conv_gemm_v(const ConvGemmParams& p, int grid, cudaStream_t st
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  DANA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM, KT>, p));
+  DANA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, NSPLIT, EPI, CM, KT, DX3>, p));
   DANA_LAUNCH_CHECK();
   return DANA_OK;
 }
@@ -157,6 +157,30 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   TileChoice tc{a->tile_w, a->tile_h, a->tile_n};
+  // 3x3 stride-1 pad-1 convolutions with split operands can take the window-per-column-shift schedule (ConvGemmCfg:
+  // DX3; output tiles of 8 x 16 or 16 x 8 pixels, whichever pads the map less).  Measured on B200 (round 2,
+  // tools/gemm_bench.py / bench.py): 64 channels (layer1) 0.0605 -> 0.0537 ms and +0.7 % on the step; 128 / 256 channels
+  // LOSE (0.0455 -> 0.0477, 0.0395 -> 0.0433 ms: only two 68 KB stages fit, and these layers were never bound by the
+  // L2 -> SM bytes the schedule saves -- ncu shows the tensor pipe, at 40 % efficiency for 64-column MMAs, as the
+  // busiest unit).  Default: 64-channel layers only; DANA_DX3=<max channels> overrides (0 = off).
+  bool dx3 = false;
+  {
+    static int dx3_env = -1;
+    if (dx3_env < 0) {
+      const char* env = getenv("DANA_DX3");   // largest input-channel count that takes the schedule (0 = off)
+      dx3_env = (env != nullptr) ? atoi(env) : 64;
+    }
+    dx3 = a->a_c <= dx3_env && a->taps_r == 3 && a->taps_s == 3 && a->pad_y == 1 && a->pad_x == 1 && a->a_lo != nullptr && !batched &&
+          !softmax && !io_f16 && a->bias_sn == 0 && (a->a_c == 64 || a->a_c == 128 || a->a_c == 256) &&
+          (a->n_out == 64 || a->n_out % 128 == 0) && a->tile_w <= 0 && a->out_w == a->a_w && a->out_h == a->a_h;
+    if (dx3) {
+      auto cost = [&](int bw) {
+        const int bh = 128 / bw;
+        return static_cast<long long>((a->out_w + bw - 1) / bw) * ((a->out_h + bh - 1) / bh);
+      };
+      tc = (cost(16) < cost(8)) ? TileChoice{16, 8, 1} : TileChoice{8, 16, 1};
+    }
+  }
   if (tc.bw <= 0 || tc.bh <= 0 || tc.bn <= 0)
     tc = choose_tile(a->out_w, a->out_h, a->out_n, batched || a->bias_sn != 0);
   if (tc.bw * tc.bh * tc.bn != 128 || (batched && tc.bn != 1)) return DANA_EINVAL;
@@ -216,9 +240,10 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     while (block_n > 64 && sp_tiles * ((a->n_out + block_n - 1) / block_n) * 2 <= sms) block_n >>= 1;
   }
   if (softmax) block_n = a->softmax_ns <= 64 ? 64 : 256;   // one N-tile per shot segment
+  if (dx3) block_n = a->n_out == 64 ? 64 : 128;
   {
     const char* env = getenv("DANA_BLOCK_N");
-    if (env != nullptr && !softmax) {
+    if (env != nullptr && !softmax && !dx3) {
       const int v = atoi(env);
       if (v == 64 || v == 128 || v == 256) block_n = v;
     }
@@ -255,6 +280,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     if (env != nullptr && nsplit == 2 && block_n == 256 && cm == 1 && !softmax && !io_f16 && (a->a_c % 32) == 0)
       ktile = atoi(env) == 32 ? 32 : 64;
     // (128-wide tiles stay at KT = 64: six 32 KB stages instead of three 64 KB ones measured 7 % slower on the step)
+    if (dx3) ktile = (block_n == 64) ? 64 : 32;   // two stages of 88 KB / 68 KB (window box + three weight tiles, two planes)
   }
   p.c_blocks = static_cast<int>((a->a_c + ktile - 1) / ktile);
   // tensor maps
@@ -263,8 +289,9 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
                               static_cast<uint64_t>(a->a_h), static_cast<uint64_t>(a->a_n)};
     const uint64_t str[3] = {static_cast<uint64_t>(a->a_sx) * 2, static_cast<uint64_t>(a->a_sy) * 2,
                              static_cast<uint64_t>(a->a_sn) * 2};
-    const uint32_t box[4] = {static_cast<uint32_t>(ktile), static_cast<uint32_t>(tc.bw), static_cast<uint32_t>(tc.bh),
-                             static_cast<uint32_t>(tc.bn)};
+    const uint32_t box[4] = {static_cast<uint32_t>(ktile), static_cast<uint32_t>(tc.bw),
+                             static_cast<uint32_t>(dx3 ? tc.bh + 2 : tc.bh), static_cast<uint32_t>(tc.bn)};
+    p.dx_box_bytes = dx3 ? tc.bw * (tc.bh + 2) * ktile * 2 : 0;
     int rc = encode_bf16_map(&p.tm_a_hi, a->a_hi, 4, dims, str, box, ktile == 32);
     if (rc != DANA_OK) return rc;
     if (nsplit == 2) {
@@ -309,7 +336,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   // stream-K when whole-tile scheduling would leave SMs idle (partial last round or fewer tiles than SMs)
   p.sk_epoch = 0;
   {
-    const long long num_kb = static_cast<long long>(taps) * p.c_blocks;
+    const long long num_kb = static_cast<long long>(dx3 ? 3 : taps) * p.c_blocks;   // DX3: a k-block is a column shift (3 taps)
     const long long total_it = num_work * num_kb;
     const long long rounds = (num_work + sms - 1) / sms;
     const double eff = static_cast<double>(num_work) / static_cast<double>(rounds * sms);
@@ -318,7 +345,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     const bool allowed = (env == nullptr) || atoi(env) != 0;
     // cost model (microseconds): a k-block costs ~0.8 us in x3 / ~0.27 us in bf16 at BLOCK_N = 256; stream-K pays
     // ~4 us for publishing / collecting partial tiles
-    const double kb_us = (nsplit == 2 ? 0.8 : 0.27) * block_n / 256.0 * ktile / 64.0;
+    const double kb_us = (nsplit == 2 ? 0.8 : 0.27) * block_n / 256.0 * ktile / 64.0 * (dx3 ? 3.0 : 1.0);
     const double plain_us = static_cast<double>(rounds * num_kb) * kb_us;
     const double sk_us = static_cast<double>((total_it + sms - 1) / sms) * kb_us + 4.0;
     if (allowed && !softmax && cm == 1 && a->workspace != nullptr && a->workspace_bytes >= need && a->sk_epoch != 0 && eff < 0.9 &&
@@ -330,6 +357,11 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
       const long long cap = num_work * 4;
       grid = static_cast<int>(cap < sms ? cap : sms);
     }
+  }
+  if (dx3) {
+    if (!fast_epilogue_ok(p, 2)) return DANA_ENOTSUP;   // checked before choosing the schedule would be nicer; trunk layers always pass
+    if (block_n == 64) return launch_conv_gemm_v<64, 2, 1, 1, 64, true>(p, grid, stream);
+    return launch_conv_gemm_v<128, 2, 1, 1, 32, true>(p, grid, stream);
   }
   if (nsplit == 1) {
     if (block_n == 256) return cm == 2 ? launch_conv_gemm<256, 1, 2>(p, grid, stream, io_f16) : launch_conv_gemm<256, 1, 1>(p, grid, stream, io_f16);

@@ -186,7 +186,12 @@ def test_linear(ops, split, m, k, n):
 @pytest.mark.parametrize("n,h,w,cin,cout,ks,stride", [(2, 38, 63, 256, 256, 3, 1), (3, 20, 20, 128, 128, 3, 1),
                                                       (16, 4, 4, 512, 512, 3, 1), (2, 75, 125, 256, 128, 1, 2),
                                                       (8, 7, 7, 1024, 512, 1, 2), (1, 150, 250, 64, 256, 1, 1),
-                                                      (1, 38, 63, 2048, 512, 3, 1), (5, 9, 11, 64, 72, 1, 1)])
+                                                      (1, 38, 63, 2048, 512, 3, 1), (5, 9, 11, 64, 72, 1, 1),
+                                                      # window-per-column-shift schedule (DX3): 64 / 128 / 256 channels,
+                                                      # maps that do and do not divide the 8x16 / 16x8 tiles
+                                                      (2, 150, 250, 64, 64, 3, 1), (1, 37, 29, 64, 64, 3, 1),
+                                                      (2, 75, 125, 128, 128, 3, 1), (3, 40, 40, 128, 128, 3, 1),
+                                                      (1, 5, 3, 256, 256, 3, 1), (4, 80, 80, 64, 64, 3, 1)])
 def test_conv(ops, split, n, h, w, cin, cout, ks, stride):
     torch.manual_seed(h * w + cin)
     F = torch.nn.functional
