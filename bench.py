@@ -42,20 +42,26 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
-def gemm_traffic():
-    """DRAM bytes per launch of the GEMM kernel (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 116
-    launches of one step), from the committed ncu launch list of this round; None when the file is absent."""
-    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        return round(json.load(f)["dram_bytes_per_launch"])
+def gemm_traffic(precision):
+    """DRAM bytes per launch of the GEMM kernel (dram__bytes_read.sum + dram__bytes_write.sum averaged over the GEMM
+    launches of one step).  ncu cannot run inside a timed bench, so this is the figure of the newest committed ncu
+    launch list of the same step and precision (profiles/rNN_gemm_traffic_<precision>.json, written by
+    tools/gemm_traffic.py from the capture, stamped with its commit); None when there is none for this precision.
+    The run's own algorithmic bytes are printed beside it (roofline.algorithmic_bytes_per_launch)."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic_%s.json" % precision)))
+    if not cands:
+        return None, None
+    with open(cands[-1]) as f:
+        d = json.load(f)
+    return round(d["dram_bytes_per_launch"]), {"file": os.path.relpath(cands[-1], ROOT), "commit": d.get("commit"),
+                                               "launches_per_step": d.get("launches_per_step")}
 
 
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -79,8 +85,15 @@ class ClockSampler(threading.Thread):
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+               "reasons": reasons, "samples": len(self.samples)}
+        try:
+            pw = [float(s[6]) for s in self.samples if len(s) > 6]
+            if pw:
+                out["power_w_median"], out["power_w_max"] = round(statistics.median(pw), 1), round(max(pw), 1)
+        except ValueError:
+            pass
+        return out
 
 
 def dist_setup(n_gpus):
@@ -188,15 +201,43 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in (im_h, info_h, gt_h, nb_h, sup_h))
     d2h = sum(t.numel() * t.element_size() for t in res)
 
-    # ---- roofline of the dominant kernel: one extra instrumented step, CUDA events around every
-    # tensor-core GEMM launch on the launching stream; algorithmic FLOPs = 2*M*N*K from the launch shapes
+    # ---- roofline of the dominant kernel + per-stage breakdown: one extra instrumented eager step, CUDA events around
+    # every tensor-core GEMM launch and at every stage boundary, on the launching stream; algorithmic FLOPs =
+    # 2*M*N*K and algorithmic bytes (every operand / output element once) from the launch shapes
     ops.GEMM_TRACE = []
+    eng.stage_events = []
     eng.forward(im_d, info_d, sup_d)          # eager launches: events around every GEMM on the launching stream
     torch.cuda.synchronize()
     trace, ops.GEMM_TRACE = ops.GEMM_TRACE, None
+    marks, eng.stage_events = eng.stage_events, None
+    ops.STAGE = ""
     g_ms = sum(t[0].elapsed_time(t[1]) for t in trace)
     g_flops = sum(t[2] for t in trace)
+    g_issued = sum(t[2] * t[4]["mma_per_product"] for t in trace)
+    g_bytes = sum(t[4]["bytes"] for t in trace)
     peaks = load_peaks()
+    stage_ms = {marks[i + 1][0]: marks[i][1].elapsed_time(marks[i + 1][1]) for i in range(len(marks) - 1)}
+    eager_ms = sum(stage_ms.values())
+    r_rois = b * 300
+    hbm_stage_bytes = {"roi_align": r_rois * 49 * 1024 * (6 if args.precision == "mixed" else 4 if args.precision == "bf16x3" else 2)
+                       + b * 38 * 63 * 1024 * 4}
+    stages = []
+    for name, ms in stage_ms.items():
+        tr = [t for t in trace if t[4]["stage"] == name]
+        fl = sum(t[2] for t in tr)
+        ent = {"stage": name, "ms_eager": round(ms, 3), "share": round(ms / eager_ms, 4),
+               "gemm_launches": len(tr), "gemm_ms": round(sum(t[0].elapsed_time(t[1]) for t in tr), 3),
+               "algorithmic_gflop": round(fl / 1e9, 1)}
+        if name in hbm_stage_bytes:
+            ent.update(bound="hbm", algorithmic_mb=round(hbm_stage_bytes[name] / 1e6, 1),
+                       achieved_gbs=round(hbm_stage_bytes[name] / (ms * 1e-3) / 1e9, 1),
+                       frac=round(hbm_stage_bytes[name] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4))
+        elif fl > 0:
+            ent.update(bound="tensor", achieved_tflops=round(fl / (ms * 1e-3) / 1e12, 1),
+                       frac=round(fl / (ms * 1e-3) / 1e12 / peaks["tf_sustained"], 4),
+                       issued_frac=round(sum(t[2] * t[4]["mma_per_product"] for t in tr) / (ms * 1e-3) / 1e12 / peaks["tf_sustained"], 4))
+        stages.append(ent)
+    traffic, traffic_src = gemm_traffic(args.precision)
 
     value, t_max, units = aggregate_throughput(units=b * args.steps, seconds=dev_s, device=dev)
     e2e_value, _, _ = aggregate_throughput(units=b * args.steps, seconds=e2e_s, device=dev)
@@ -225,10 +266,20 @@ def run_ours(args):
                      "achieved": round(g_flops / (g_ms * 1e-3) / 1e12, 1) if g_ms > 0 else None,
                      "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": round(g_flops / (g_ms * 1e-3) / 1e12 / peaks["tf_sustained"], 4) if g_ms > 0 else None,
-                     "traffic": gemm_traffic(), "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a step)",
-                     "launches_per_step": len(trace), "gemm_ms_per_step": round(g_ms, 3),
+                     "issued_frac": round(g_issued / (g_ms * 1e-3) / 1e12 / peaks["tf_sustained"], 4) if g_ms > 0 else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": round(g_bytes / max(len(trace), 1)),
+                     "algorithmic_bytes_per_step": round(g_bytes),
+                     "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a step)",
+                     "launches_per_step": len(trace),
+                     "gemm_ms_per_step": round(g_ms, 3),
+                     "gemm_ms_note": "sum of CUDA-event intervals around each GEMM launch of one EAGER step",
                      "algorithmic_gflop_per_step": round(g_flops / 1e9, 1),
+                     "issued_gflop_per_step": round(g_issued / 1e9, 1),
                      "step_gflop_model": GF_PER_QUERY * b},
+        "stages": {"timing": "one eager step, CUDA events at the stage boundaries (host launch gaps included: %.3f ms "
+                             "eager vs ms_per_step under graph replay); shares are the comparable quantity" % eager_ms,
+                   "list": stages},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sample_batch=1)
@@ -342,8 +393,10 @@ def run_reference(args):
         return
     sample_batch = 1
     step, kind = cpu_forward_fn(sample_batch)
-    warm = min(args.warmup, 1)
-    steps = max(1, min(args.steps, 5))          # bounded: one 600x1000 query per step, a few seconds each
+    # one 600x1000 query + its 6 support crops per step (~0.7 s on 16 cores): --steps / --warmup are honoured as given
+    # up to 60 steps / 10 warm-ups (a bound, so that a sustained-run request of the GPU arm does not run for hours here)
+    warm = max(0, min(args.warmup, 10))
+    steps = max(1, min(args.steps, 60))
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -355,7 +408,9 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
             "ms_per_step": round(1e3 * dt / steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "1 query + 6 supports per step on the host cores"},
+            "config": {"workload": WORKLOAD, "sample": "1 query + 6 supports per step on the host cores",
+                       "steps_requested": args.steps, "warmup_requested": args.warmup,
+                       "process": "one CPU process on rank 0 whatever --gpus is (the reference path does not shard)"},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "cpu": cpu_model(), "kind": "port",
                              "detail": kind,
                              "sample": "%d steps x 1 query 600x1000 (2-way 3-shot), torch CPU fp32, %d threads" % (steps, os.cpu_count() or 1)},
@@ -369,7 +424,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["mixed", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()

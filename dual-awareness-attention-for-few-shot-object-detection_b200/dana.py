@@ -58,7 +58,7 @@ class _RPNParams(nn.Module):
 class DAnARCNN(nn.Module):
     def __init__(self, classes, attention_type, rpn_reduce_dim=256, rcnn_reduce_dim=256, gamma=0.1,
                  semantic_enhance=False, num_layers=50, pretrained=False, num_way=2, num_shot=5, pos_encoding=True,
-                 precision="bf16x3", use_cuda_graph=False):
+                 precision="mixed", use_cuda_graph=False):
         super().__init__()
         if attention_type != "concat":
             raise NotImplementedError("only attention_type='concat' (the shipped configuration, utils.py:119) is built")

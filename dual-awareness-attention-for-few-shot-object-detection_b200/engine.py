@@ -113,6 +113,7 @@ class DanaEngine:
         self.num_a = self.base_anchors.shape[0]
         self._pe = {}
         self._prop_ws = None
+        self.stage_events = None      # bench.py: list receiving (stage name, CUDA event) at the stage boundaries
         self.load_state_dict(state_dict)
 
     # ------------------------------------------------------------------ weights
@@ -160,6 +161,18 @@ class DanaEngine:
         self.ffn1_w, self.ffn1_b = lin("output_score_layer.linear1")
         self.ffn2_w, self.ffn2_b = lin("output_score_layer.linear2")
         self.bbox_w, self.bbox_b = lin("RCNN_bbox_pred")
+
+    # stage boundaries of forward(), in order; _mark(name) closes stage `name`
+    STAGES = ("trunk", "cisa_rpn", "rpn_proposals", "roi_align", "layer4_bbox", "head_cisa")
+
+    def _mark(self, name):
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
+            order = ("start",) + self.STAGES
+            i = order.index(name)
+            ops.STAGE = order[i + 1] if i + 1 < len(order) else ""
 
     def pe(self, n):
         if n not in self._pe:
@@ -256,7 +269,9 @@ class DanaEngine:
         sup [B*sets*K, hs, ws, 1024]: support maps, image-major; set 0 of every image drives the block."""
         maps, sh, sw, c = sup.hi.shape
         ns = sh * sw
-        if os.environ.get("DANA_CISA_PY") == "1":      # the same stages sequenced from Python (debugging aid)
+        # the same kernels sequenced from Python: debugging aid, and the path bench.py's per-launch GEMM trace uses
+        # (the events of the trace sit around the Python-level launches)
+        if os.environ.get("DANA_CISA_PY") == "1" or ops.GEMM_TRACE is not None:
             return self._rpn_attention_py(base2d, dense_out, b, nq, sup, sets)
         ops.cisa_fwd(base2d, sup.view(maps, ns, c), self.pe(ns), self.n_shot, sets, b, wq=self.rpn_q_w, wk=self.rpn_k_w,
                      un_w=self.rpn_un_w, un_b=self.rpn_un_b, unary_gamma=self.unary_gamma, ba_w=self.ba_w, ba_b=self.ba_b,
@@ -317,6 +332,7 @@ class DanaEngine:
         extra = {}
 
         # ---- trunk over the query and the support crops (dana.py:98,111)
+        self._mark("start")
         qh, qw = self._trunk_hw(im_data.shape[2], im_data.shape[3])
         nq = qh * qw
         if self.f16:
@@ -349,6 +365,7 @@ class DanaEngine:
         if teacher and "support_feat" in teacher:
             sup = ops.split_f32(teacher["support_feat"].reshape(maps, c, sh, sw).permute(0, 2, 3, 1).contiguous(), split)
 
+        self._mark("trunk")
         if self.f16:
             base2d = base.view(b * nq, 1024)
         else:
@@ -370,6 +387,7 @@ class DanaEngine:
                 if split:
                     corr.lo[..., 1024:].copy_(td.lo)
 
+        self._mark("cisa_rpn")
         # ---- RoIAlign input (fp32 NHWC) -- and, in the mixed mode, the query half of the fp16 RPN input
         if self.f16:
             base_f32 = ops.merge_pair(base, out16=corr16[..., :1024])
@@ -395,6 +413,7 @@ class DanaEngine:
         if teacher and "rois" in teacher:
             rois = teacher["rois"].to(dev).float().contiguous()
 
+        self._mark("rpn_proposals")
         # ---- RoIAlign on the query feature (dana.py:183)
         r = b * post_nms_top_n
         bins = pooling_size * pooling_size
@@ -417,6 +436,7 @@ class DanaEngine:
         if self.f16 and pooled16 is None:
             pooled16 = Pair.from_float_f16(pooled_f32 if pooled_f32 is not None else ops.merge_pair(pooled))
 
+        self._mark("roi_align")
         # ---- head: box regression (dana.py:246,387-389)
         top = self.layer4(pooled16 if self.f16 else pooled)
         fc7_f32, fc7 = ops.spatial_mean(top.view(r, top.hi.shape[1] * top.hi.shape[2], top.hi.shape[3]), split=split)
@@ -425,6 +445,7 @@ class DanaEngine:
         if "fc7" in want:
             extra["fc7"] = fc7_f32
 
+        self._mark("layer4_bbox")
         # ---- head: per-RoI CISA (dana.py:247-290); support projections hoisted out of the RoI loop
         sp_k = sh - pooling_size + 1
         s_pooled = ops.avgpool(sup, sp_k)                                 # dana.py:114  [maps,7,7,C] fp32
@@ -466,6 +487,7 @@ class DanaEngine:
             hid = ops.linear(t.view(r, bins * 64), self.ffn1_w, 1024, bias=self.ffn1_b, relu=True, split=split)
             ops.linear(hid, self.ffn2_w, 2, bias=self.ffn2_b, out_f32=cls_scores[s * r:(s + 1) * r])
         cls_prob = ops.softmax2(cls_scores)                               # :290
+        self._mark("head_cisa")
         if "cls_score" in want:
             extra["cls_score"] = cls_scores
         if want:

@@ -14,6 +14,7 @@ from ._lib import ConvGemmArgs, check
 # (bench.py's roofline: list of (start_event, end_event, algorithmic_flops) on the launching stream).
 LAUNCHES = 0
 GEMM_TRACE = None
+STAGE = ""          # set by DanaEngine._mark while a trace is recorded: the forward stage the next launches belong to
 
 
 def _count(n):
@@ -156,8 +157,16 @@ def conv_gemm(a: Pair, a_dims, a_strides, w: Pair, n_out: int, out_dims, o_strid
         check(_lib.load().dana_conv_gemm(ctypes.byref(args), _stream()), "dana_conv_gemm")
         e1.record()
         m = args.out_w * args.out_h * args.out_n
-        GEMM_TRACE.append((e0, e1, 2.0 * m * args.n_out * args.taps_r * args.taps_s * args.a_c,
-                           (m, args.n_out, args.taps_r * args.taps_s * args.a_c, args.taps_r * args.taps_s)))
+        kk = args.taps_r * args.taps_s * args.a_c
+        planes = 2 if a.lo is not None else 1
+        # algorithmic bytes: every operand element once (activation, weights, residual) + the output once
+        nb = args.out_n if b_batch_stride else 1
+        out_b = (4 if out_f32 is not None else 0) + ((2 * (2 if out.lo is not None else 1)) if out is not None else 0)
+        res_b = (4 if res_f32 is not None else 0) + ((2 * (2 if res.lo is not None else 1)) if res is not None else 0)
+        a_elems = args.a_w * args.a_h * args.a_n * args.a_c          # the (strided) input view, each pixel once
+        byts = 2.0 * planes * (a_elems + nb * args.n_out * kk) + m * args.n_out * (out_b + res_b)
+        GEMM_TRACE.append((e0, e1, 2.0 * m * args.n_out * kk, (m, args.n_out, kk, args.taps_r * args.taps_s),
+                           {"stage": STAGE, "mma_per_product": 3 if planes == 2 else 1, "bytes": byts}))
         return
     check(_lib.load().dana_conv_gemm(ctypes.byref(args), _stream()), "dana_conv_gemm")
 

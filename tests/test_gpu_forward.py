@@ -89,8 +89,8 @@ def test_forward_stages_vs_oracle(precision, tol):
     assert relerr(ex["rpn_deltas"], ref["rpn_bbox_pred"].permute(0, 2, 3, 1).reshape(2, -1, 4)) <= tol
     if precision == "bf16x3":
         assert roi_set_match(rois, ref["rois"]) >= 0.97
-    if precision == "mixed":    # fp16 RPN scores move a few NMS decisions: the set is compared a little looser
-        assert roi_set_match(rois, ref["rois"]) >= 0.95
+    if precision == "mixed":    # fp16 RPN deltas (4e-4 relative) move the boxes of the large anchors by up to ~0.2 px
+        assert roi_set_match(rois, ref["rois"], tol=0.5) >= 0.97
     rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want,
                                            teacher={"rois": ref["rois"].cuda()})
     assert relerr(ex["pooled"], ref["pooled"]) <= tol
@@ -146,7 +146,7 @@ def test_module_boundary_eval_forward():
     assert len(out) == 8 and out[3:7] == (0, 0, 0, 0) and out[7] is None
     g = np.load(os.path.join(root, "tests", "golden", "forward_small.npz"))
     assert tuple(out[0].shape) == tuple(g["rois"].shape)
-    assert roi_set_match(out[0], torch.from_numpy(g["rois"])) >= 0.97
+    assert roi_set_match(out[0], torch.from_numpy(g["rois"]), tol=0.5) >= 0.97     # default precision: mixed
     with pytest.raises(NotImplementedError):
         net.train()(im.cuda(), info.cuda(), torch.zeros(1, 1, 5).cuda(), torch.zeros(1).cuda(), sup.cuda())
 
@@ -211,7 +211,7 @@ def test_full_size_query_vs_oracle(full_size_ref, precision):
     assert relerr(ex["base_feat"], ref["base_feat"]) <= TOL
     assert relerr(ex["dense"], ref["dense"]) <= TOL
     assert relerr(ex["rpn_fg"], ref["rpn_cls_prob"][:, 12:].permute(0, 2, 3, 1).reshape(1, -1)) <= TOL
-    assert roi_set_match(rois, ref["rois"]) >= (0.97 if precision == "bf16x3" else 0.95)
+    assert roi_set_match(rois, ref["rois"], tol=0.05 if precision == "bf16x3" else 0.5) >= 0.97
     rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want,
                                            teacher={"rois": ref["rois"].cuda()})
     assert relerr(ex["pooled"], ref["pooled"]) <= TOL

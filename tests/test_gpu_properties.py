@@ -20,12 +20,12 @@ def _iou_matrix(b):
     return inter / (area[:, None] + area[None, :] - inter)
 
 
-@pytest.fixture(scope="module")
-def full_case():
+@pytest.fixture(scope="module", params=["mixed", "bf16x3"])
+def full_case(request):
     import dana_b200  # noqa: F401
     from dana_b200.engine import DanaEngine
     from dana_b200.synthetic import synthetic_episode, synthetic_state_dict
-    eng = DanaEngine(synthetic_state_dict(1996), n_shot=3, precision="bf16x3")
+    eng = DanaEngine(synthetic_state_dict(1996), n_shot=3, precision=request.param)
     im, info, sup = synthetic_episode(77, 4, 600, 1000, 6)
     return eng, im.cuda(), info.cuda(), sup.cuda()
 

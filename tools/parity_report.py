@@ -45,7 +45,7 @@ def run_case(name, p, im, info, sup, k, precisions, out):
             d = (w[:, None, :] - got[i][None, :, 1:]).abs().max(2)[0].min(1)[0]
             hits += int((d <= 0.05).sum())
             total += w.shape[0]
-        rep["rois_set_match"] = hits / max(total, 1)
+        rep["rois_set_match_0.05px"] = hits / max(total, 1)
         rois, cls_prob, bbox, ex = eng.forward(im.cuda(), info.cuda(), sup.cuda(), want=want,
                                                teacher={"rois": ref["rois"].cuda()})
         rep["pooled"] = errs(ex["pooled"], ref["pooled"])
