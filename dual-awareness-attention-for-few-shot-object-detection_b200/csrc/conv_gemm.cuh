@@ -48,6 +48,7 @@ struct ConvGemmParams {
   int* sk_flags;        // [grid]
   int sk_epoch;         // value a flag takes when this launch's partial is published; 0 = stream-K off
   int sm_ns, sm_pitch;  // SOFTMAX epilogue: keys per segment, column pitch of a segment in the output
+  int sm_half;          // wide softmax tile (EPI 4): columns per MMA = rows per key box = ceil32(sm_ns) / 2
   int n_fast;           // tile order: 1 = the N-tiles of an M-tile are consecutive work items, 0 = N is the slow index
   int a_prefetch;       // producer prefetches the next tile's activation boxes into L2
   int ab_f16;           // operands are IEEE fp16 planes (kind::f16 with F16 formats) instead of bf16
@@ -76,10 +77,12 @@ struct ConvGemmCfg {
   static constexpr int kBTileBytes = BLOCK_N * kTileK * 2;  // per plane and tap
   static constexpr int kBGroupBytes = kBTaps * kBTileBytes;
   static constexpr int kStageBytes = NSPLIT * (kATileBytes + kBGroupBytes);
-  static constexpr int kBudget = 200 * 1024;
+  static constexpr int kBudget = (BLOCK_N > 256 ? 184 : 200) * 1024;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulators
+  // two accumulators; the 512-column tile (wide softmax epilogue) owns all of TMEM with a single one
+  static constexpr int kAccBufs = BLOCK_N > 256 ? 1 : 2;
+  static constexpr int kTmemCols = BLOCK_N > 256 ? 512 : (2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
   static constexpr int kXposeBytes = 8 * 4096;  // one 32x32 fp32 transposition buffer per epilogue warp
   // softmax epilogue: (row max, row sum) exchange, 8 warps x 64 floats; it overlays the scale/bias arrays (unused
   // by that epilogue) when they are large enough -- the <256, 2> budget has no 2 KB to spare
@@ -133,12 +136,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr bool FAST = (EPI == 1 || EPI == 3);
   constexpr bool F16IO = (EPI == 3);
   constexpr bool OUT2 = (NSPLIT == 2) && !F16IO;   // output / residual carry a lo plane
-  constexpr bool SOFTMAX = (EPI == 2);
+  constexpr bool SOFTMAX = (EPI == 2 || EPI == 4);
+  // EPI 4: the same fused attention softmax for segments of 257..512 keys (the reference's 20 x 20 supports: 400).  A
+  // segment does not fit one 256-column MMA, nor two accumulators TMEM: the tile is ONE accumulator of up to 512
+  // columns written by two MMAs of sm_half = ceil32(ns) / 2 columns per k-step, and the epilogue makes three passes
+  // over it straight from TMEM (row max, sum of exponentials, normalised probabilities) instead of holding the
+  // segment in registers.  No fp32 logits in HBM, no separate softmax kernel.
+  constexpr bool SOFTMAXW = (EPI == 4);
+  static_assert(!SOFTMAXW || (BLOCK_N == 512 && KT == 32 && CM == 1 && !DX3), "wide softmax: 512-column tile, 32-wide K stages");
+  constexpr int kAccBufs = ConvGemmCfg<BLOCK_N, NSPLIT, KT, DX3>::kAccBufs;
   using Cfg = ConvGemmCfg<BLOCK_N, NSPLIT, KT, DX3>;
   constexpr int kTileK = Cfg::kTileK;
   constexpr int kATileBytes = Cfg::kATileBytes;
   constexpr int kStages = Cfg::kStages;
-  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && (BLOCK_N <= 256 || SOFTMAXW), "BLOCK_N");
   static_assert(kStages >= 2, "pipeline too shallow");
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared-memory budget");
 
@@ -289,6 +300,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 tma_load_3d(st + NSPLIT * kATileBytes + Cfg::kBGroupBytes + dy * Cfg::kBTileBytes, &p.tm_b_lo,
                             &full_bar[stage], kbk, co_t * BLOCK_N, 0);
             }
+          } else if constexpr (SOFTMAXW) {
+            // A k-block + the segment's keys as two boxes of sm_half rows (a TMA box has at most 256 rows)
+            const int hb = p.sm_half * (kTileK * 2);
+            mbar_arrive_expect_tx(&full_bar[stage], NSPLIT * (kATileBytes + 2 * hb));
+            tma_load_4d(st, &p.tm_a_hi, &full_bar[stage], ka, x0, y0, n0);
+            if (NSPLIT == 2) tma_load_4d(st + kATileBytes, &p.tm_a_lo, &full_bar[stage], ka, x0, y0, n0);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              tma_load_3d(st + NSPLIT * kATileBytes + hf * hb, &p.tm_b_hi, &full_bar[stage], ka,
+                          co_t * p.sm_ns + hf * p.sm_half, bcoord);
+              if (NSPLIT == 2)
+                tma_load_3d(st + NSPLIT * kATileBytes + Cfg::kBGroupBytes + hf * hb, &p.tm_b_lo, &full_bar[stage], ka,
+                            co_t * p.sm_ns + hf * p.sm_half, bcoord);
+            }
           } else {
           const int r = tap / p.taps_s;
           const int s = tap - r * p.taps_s;
@@ -322,7 +347,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(kTileM, BLOCK_N) : umma_idesc_bf16(kTileM, BLOCK_N);
+      const int mma_n = SOFTMAXW ? p.sm_half : BLOCK_N;
+      const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(kTileM, mma_n) : umma_idesc_bf16(kTileM, mma_n);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -346,19 +372,25 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
           for (int k = 0; k < kTileK / 16; ++k) {
             const uint32_t koff = k * 32;  // 16 bf16 = 32 B inside the swizzled row
+#pragma unroll
+            for (int hf = 0; hf < (SOFTMAXW ? 2 : 1); ++hf) {
+            // wide softmax tile: columns [hf * sm_half, (hf + 1) * sm_half) from the hf-th box of keys
+            const uint32_t d_h = d_addr + (SOFTMAXW ? static_cast<uint32_t>(hf * p.sm_half) : 0u);
+            const uint32_t b_h = b_t + (SOFTMAXW ? static_cast<uint32_t>(hf * p.sm_half * (kTileK * 2)) : 0u);
             const uint64_t da = (kTileK == 64) ? umma_desc_sw128(a_t + koff) : umma_desc_sw64(a_t + koff);
-            const uint64_t db = (kTileK == 64) ? umma_desc_sw128(b_t + koff) : umma_desc_sw64(b_t + koff);
+            const uint64_t db = (kTileK == 64) ? umma_desc_sw128(b_h + koff) : umma_desc_sw64(b_h + koff);
             if (NSPLIT == 2) {
               const uint64_t dal = (kTileK == 64) ? umma_desc_sw128(a_t + kATileBytes + koff)
                                                   : umma_desc_sw64(a_t + kATileBytes + koff);
-              const uint64_t dbl = (kTileK == 64) ? umma_desc_sw128(b_t + Cfg::kBGroupBytes + koff)
-                                                  : umma_desc_sw64(b_t + Cfg::kBGroupBytes + koff);
+              const uint64_t dbl = (kTileK == 64) ? umma_desc_sw128(b_h + Cfg::kBGroupBytes + koff)
+                                                  : umma_desc_sw64(b_h + Cfg::kBGroupBytes + koff);
               // small cross terms first, leading term last
-              umma_bf16(d_addr, dal, db, idesc, ((kb - kb_lo) | k | dy) != 0);
-              umma_bf16(d_addr, da, dbl, idesc, 1);
-              umma_bf16(d_addr, da, db, idesc, 1);
+              umma_bf16(d_h, dal, db, idesc, ((kb - kb_lo) | k | dy) != 0);
+              umma_bf16(d_h, da, dbl, idesc, 1);
+              umma_bf16(d_h, da, db, idesc, 1);
             } else {
-              umma_bf16(d_addr, da, db, idesc, ((kb - kb_lo) | k | dy) != 0);
+              umma_bf16(d_h, da, db, idesc, ((kb - kb_lo) | k | dy) != 0);
+            }
             }
           }
           }
@@ -373,7 +405,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         umma_commit(&acc_full[acc]);  // accumulator ready for the epilogue
-        if (++acc == 2) {
+        if (++acc == kAccBufs) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -438,7 +470,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        if (++acc == 2) {
+        if (++acc == kAccBufs) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -604,7 +636,116 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
       mbar_wait(&acc_full[acc], acc_phase, 104);
       tc_fence_after();
-      if constexpr (SOFTMAX) {
+      if constexpr (SOFTMAXW) {
+        // Three passes over the single wide accumulator, 32 columns at a time (the two warps of a TMEM lane quarter
+        // split the chunks): row max -> exchange -> sum of exponentials -> exchange -> normalised probabilities.
+        // Nothing but one chunk lives in registers, the logits stay in TMEM until the last pass has read them.
+        const int ns = p.sm_ns;
+        const int used = (ns + 31) >> 5;                       // chunks that hold keys (<= 16)
+        const int n_first = (used + 1) >> 1;
+        const int my_c0 = half ? n_first : 0;
+        const int my_n = half ? used - n_first : n_first;
+        const uint32_t trow0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        float* xs_mine = s_xchg + (warp - 2) * 64;
+        const float* xs_peer = s_xchg + ((warp - 2) ^ 4) * 64;
+        const float sc = p.alpha * 1.4426950408889634f;
+        uint32_t v[32];
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int ci = 0; ci < my_n; ++ci) {
+          const int c = my_c0 + ci;
+          tmem_ld32(trow0 + c * 32, v);
+          tmem_ld_wait();
+          const int nv = ns - c * 32;
+          if (nv >= 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+        }
+        xs_mine[lane] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        mx = fmaxf(mx, xs_peer[lane]);
+        const float mb = mx * sc;
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int ci = 0; ci < my_n; ++ci) {
+          const int c = my_c0 + ci;
+          tmem_ld32(trow0 + c * 32, v);
+          tmem_ld_wait();
+          const int nv = ns - c * 32;
+          float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e;
+            const float t = fmaf(__uint_as_float(v[j]), sc, -mb);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+            if (j >= nv) e = 0.0f;
+            part[j & 3] += e;
+          }
+          sum += (part[0] + part[1]) + (part[2] + part[3]);
+        }
+        xs_mine[32 + lane] = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        sum += xs_peer[32 + lane];
+        const float inv = 1.0f / sum;
+        const long long seg_col = static_cast<long long>(co_t) * p.sm_pitch;
+#pragma unroll 1
+        for (int ci = 0; ci < my_n; ++ci) {
+          const int c = my_c0 + ci;
+          tmem_ld32(trow0 + c * 32, v);
+          tmem_ld_wait();
+          const int nv = ns - c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e;
+            const float t = fmaf(__uint_as_float(v[j]), sc, -mb);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+            v[j] = __float_as_uint(j < nv ? e * inv : 0.0f);
+          }
+          uint4* trow = reinterpret_cast<uint4*>(tb + lane * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) trow[g ^ (lane & 7)] = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          __syncwarp();
+          const int col = c * 32 + cg;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + sub;
+            const float4* tr = reinterpret_cast<const float4*>(tb + r * 32);
+            const float4 a = tr[(2 * (lane & 3)) ^ (r & 7)];
+            const float4 b = tr[(2 * (lane & 3) + 1) ^ (r & 7)];
+            if (row_ok[i] && col < p.sm_pitch) {
+              const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+              uint32_t ph[4], pl[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                ph[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * e] - __uint_as_float(ph[e] << 16),
+                                                                f[2 * e + 1] - __uint_as_float(ph[e] & 0xFFFF0000u));
+                pl[e] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              *reinterpret_cast<uint4*>(p.out_hi + o_off[i] + seg_col + col) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              if (NSPLIT == 2)
+                *reinterpret_cast<uint4*>(p.out_lo + o_off[i] + seg_col + col) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+          }
+          __syncwarp();
+        }
+        // every tcgen05.ld of this warp has completed: hand the (only) accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        if (++acc == kAccBufs) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
+      if constexpr (SOFTMAX && !SOFTMAXW) {
         static_assert(!SOFTMAX || Cfg::kXchgBytes > 0 || 2 * BLOCK_N * 4 >= 8 * 64 * 4, "no room for the softmax exchange");
         // The segment's 32-column chunks are split between the two warps of the TMEM lane quarter.  Each warp
         // pulls its chunks into registers with one tcgen05.ld burst and hands the accumulator back to the MMA
@@ -625,7 +766,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc]);           // the logits live in registers from here on
-        if (++acc == 2) {
+        if (++acc == kAccBufs) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -928,7 +1069,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (++acc == 2) {
+      if (++acc == kAccBufs) {
         acc = 0;
         acc_phase ^= 1;
       }

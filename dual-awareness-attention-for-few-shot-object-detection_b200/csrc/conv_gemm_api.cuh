@@ -147,7 +147,8 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   if (a->ab_f16 && a->a_lo != nullptr) return DANA_EINVAL;   // fp16 operands are single planes
   if (softmax) {
     auto al16b = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    if (a->softmax_ns > 256 || a->softmax_pitch < a->softmax_ns || (a->softmax_pitch % 8) != 0) return DANA_EINVAL;
+    if (a->softmax_ns > 512 || a->softmax_pitch < a->softmax_ns || (a->softmax_pitch % 8) != 0) return DANA_EINVAL;
+    if (a->softmax_ns > 256 && ((a->a_c % 32) != 0 || taps != 1)) return DANA_ENOTSUP;   // wide tile: 32-wide K stages
     if (a->out_hi == nullptr || a->out_f32 != nullptr || a->scale || a->bias || a->res_hi || a->res_f32) return DANA_EINVAL;
     if (!al16b(a->out_hi) || (a->out_lo && !al16b(a->out_lo)) || (a->o_sx % 8) || (a->o_sy % 8) || (a->o_sn % 8))
       return DANA_EINVAL;
@@ -239,7 +240,9 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   if (static_cast<long long>(taps) * a->a_c <= 2048) {
     while (block_n > 64 && sp_tiles * ((a->n_out + block_n - 1) / block_n) * 2 <= sms) block_n >>= 1;
   }
-  if (softmax) block_n = a->softmax_ns <= 64 ? 64 : 256;   // one N-tile per shot segment
+  if (softmax) block_n = a->softmax_ns <= 64 ? 64 : (a->softmax_ns <= 256 ? 256 : 512);   // one N-tile per shot segment
+  const bool wide = softmax && block_n == 512;
+  const int sm_half = wide ? ((a->softmax_ns + 31) / 32 * 32) / 2 : 0;   // % 16 == 0, <= 256
   if (dx3) block_n = a->n_out == 64 ? 64 : 128;
   {
     const char* env = getenv("DANA_BLOCK_N");
@@ -251,6 +254,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   p.tiles_co = softmax ? (a->n_out + a->softmax_ns - 1) / a->softmax_ns : (a->n_out + block_n - 1) / block_n;
   p.sm_ns = softmax ? a->softmax_ns : 0;
   p.sm_pitch = softmax ? a->softmax_pitch : 0;
+  p.sm_half = sm_half;
   // cluster of 2 CTAs along M sharing (multicasting) the weight tile: only where weights are shared across
   // tiles (not the per-image attention operands), the K loop is long enough to matter and tiles are 256 wide
   int cm = 1;
@@ -281,6 +285,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
       ktile = atoi(env) == 32 ? 32 : 64;
     // (128-wide tiles stay at KT = 64: six 32 KB stages instead of three 64 KB ones measured 7 % slower on the step)
     if (dx3) ktile = (block_n == 64) ? 64 : 32;   // two stages of 88 KB / 68 KB (window box + three weight tiles, two planes)
+    if (wide) ktile = 32;                         // two stages of (8 + 32) KB per plane
   }
   p.c_blocks = static_cast<int>((a->a_c + ktile - 1) / ktile);
   // tensor maps
@@ -306,7 +311,7 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     const uint64_t bs = batched ? static_cast<uint64_t>(a->b_batch_stride)
                                 : static_cast<uint64_t>(a->b_pitch) * static_cast<uint64_t>(a->n_out);
     const uint64_t str[2] = {static_cast<uint64_t>(a->b_pitch) * 2, ((bs * 2 + 15) / 16) * 16};
-    const uint32_t box[3] = {static_cast<uint32_t>(ktile), static_cast<uint32_t>(block_n / cm), 1};
+    const uint32_t box[3] = {static_cast<uint32_t>(ktile), static_cast<uint32_t>(wide ? sm_half : block_n / cm), 1};
     int rc = encode_bf16_map(&p.tm_b_hi, a->b_hi, 3, dims, str, box, ktile == 32);
     if (rc != DANA_OK) return rc;
     if (nsplit == 2) {
@@ -357,6 +362,9 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
       const long long cap = num_work * 4;
       grid = static_cast<int>(cap < sms ? cap : sms);
     }
+  }
+  if (wide) {
+    return nsplit == 2 ? launch_conv_gemm_v<512, 2, 4, 1, 32>(p, grid, stream) : launch_conv_gemm_v<512, 1, 4, 1, 32>(p, grid, stream);
   }
   if (dx3) {
     if (!fast_epilogue_ok(p, 2)) return DANA_ENOTSUP;   // checked before choosing the schedule would be nicer; trunk layers always pass

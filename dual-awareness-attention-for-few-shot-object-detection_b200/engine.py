@@ -114,6 +114,7 @@ class DanaEngine:
         self._pe = {}
         self._prop_ws = None
         self.stage_events = None      # bench.py: list receiving (stage name, CUDA event) at the stage boundaries
+        self._side = None             # side stream of forward()'s support-side branch
         self.load_state_dict(state_dict)
 
     # ------------------------------------------------------------------ weights
@@ -222,17 +223,20 @@ class DanaEngine:
         return x
 
     # ------------------------------------------------------------------ attention
-    @staticmethod
-    def seg_pitch(ns):
-        """Column pitch of one shot's key segment in P / V^T: 8-aligned where the fused softmax epilogue is used."""
-        return (ns + 7) // 8 * 8 if ns <= 256 else ns
+    FUSED_SOFTMAX_MAX_NS = 256 if os.environ.get("DANA_WIDE_SOFTMAX") == "0" else 512
+
+    @classmethod
+    def seg_pitch(cls, ns):
+        """Column pitch of one shot's key segment in P / V^T: 8-aligned where the fused softmax epilogue is used
+        (up to 256 keys: one 256-column tile; 257..512 keys: the wide single-accumulator tile)."""
+        return (ns + 7) // 8 * 8 if ns <= cls.FUSED_SOFTMAX_MAX_NS else ns
 
     def _attention(self, qc: Pair, kc_all: Pair, vt_all: Pair, rbar_all, set_index, sets, batch, ns, out: Pair,
                    res_f32=None):
         """CISA contractions for one support set (dana.py:142-150 / :273-281).
         qc [batch*rows, 256] centred queries; kc_all [batch*sets*K*ns, 256]; vt_all [batch*sets, C, pitch];
         rbar_all [batch*sets, C].  Writes the attended feature into `out` [batch*rows, C] (any row pitch).
-        ns <= 256: the logits GEMM carries the softmax in its epilogue (no fp32 logits in HBM);
+        ns <= 512: the logits GEMM carries the softmax in its epilogue (no fp32 logits in HBM);
         larger segments: logits GEMM -> attn_softmax kernel."""
         k = self.n_shot
         d = qc.hi.shape[1]
@@ -242,7 +246,7 @@ class DanaEngine:
         kn = k * ns
         rows_total = qc.hi.shape[0]
         kc = kc_all[set_index * kn:]
-        if ns <= 256:
+        if ns <= self.FUSED_SOFTMAX_MAX_NS:
             p = Pair.empty((rows_total, pitch), self.device, self.split)
             if pitch > k * sp:                       # row-pitch padding beyond the last segment must be finite
                 p.hi[:, k * sp:].zero_()
@@ -308,6 +312,35 @@ class DanaEngine:
         self.rpn_attention(base.view(b * h * w, 1024), dense, b, h * w, sup, 1)
         return ops.merge_pair(dense).view(b, h, w, 1024).permute(0, 3, 1, 2)
 
+    def _head_support_side(self, sup: Pair, b, sets, pooling_size, want, extra):
+        """Support side of the per-RoI CISA head (dana.py:114,255-276,288): depends on the support maps only, so
+        forward() runs it on a side stream while the RPN / proposal stages occupy the main one.
+        Returns (kc_h centred k-projections, zt key-major transformed values, c64 row-constant term)."""
+        split, k, dev = self.split, self.n_shot, self.device
+        maps, sh, sw, c = sup.hi.shape
+        bins = pooling_size * pooling_size
+        sp_k = sh - pooling_size + 1
+        s_pooled = ops.avgpool(sup, sp_k)                                 # dana.py:114  [maps,7,7,C] fp32
+        if "support_pooled" in want:
+            extra["support_pooled"] = s_pooled.permute(0, 3, 1, 2)
+        pitch_h = (k * self.seg_pitch(bins) + 7) // 8 * 8
+        sp_h = self.seg_pitch(bins)
+        vc_h, _vt_h, rbar_h, cbar = ops.support_prepare(s_pooled.view(maps, bins, c), self.pe(bins), k,
+                                                        un_w=self.rcnn_un_w, un_b=self.rcnn_un_b,
+                                                        unary_gamma=self.unary_gamma, vt_pitch=pitch_h, seg_pitch=sp_h,
+                                                        split=split, want_cbar=True)
+        kc_h = ops.linear(vc_h, self.rcnn_k_w, 256, split=split)
+        # (P V) W^T = P (V W^T): the dense half of the 2048 -> 64 transform (:288) is applied to the support values
+        # BEFORE the attention-weighted sum (:281), so the [R*49, 1024] attended feature (241 MB per support set) is
+        # never materialised.  V = Vc + 1 m^T (m = column mean) and the rows of P sum to one, hence
+        #   dense W_d^T = (1/K) sum_k P_k (Vc_k W_d^T) + (rbar + mean_k m_k) W_d^T      (cbar = rbar + mean_k m_k)
+        z = torch.empty((maps * bins, 64), dtype=torch.float32, device=dev)
+        ops.linear(vc_h, self.tr_wd, 64, out_f32=z)
+        zt = ops.transpose_segments(z.view(maps, bins, 64), k, sp_h, pitch_h, split=split)   # [B*sets, 64, pitch]
+        c64 = torch.empty((b * sets, 64), dtype=torch.float32, device=dev)
+        ops.linear(cbar, self.tr_wd, 64, out_f32=c64)
+        return kc_h, zt, c64
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def encode_supports(self, support_ims):
@@ -366,6 +399,18 @@ class DanaEngine:
             sup = ops.split_f32(teacher["support_feat"].reshape(maps, c, sh, sw).permute(0, 2, 3, 1).contiguous(), split)
 
         self._mark("trunk")
+        # Two branches from here: the head's support side needs only the support maps, the RPN-level attention /
+        # RPN conv / proposal layer only the query side -- the former (a dozen small launches) runs on a side stream
+        # under the latter (captured as parallel branches of the CUDA graph).  Single stream while bench.py's
+        # instrumented step records per-launch / per-stage events, or with DANA_SIDE_STREAM=0.
+        head_sup, side = None, None
+        if self.stage_events is None and ops.GEMM_TRACE is None and os.environ.get("DANA_SIDE_STREAM", "1") != "0":
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                head_sup = self._head_support_side(sup, b, sets, pooling_size, want, extra)
         if self.f16:
             base2d = base.view(b * nq, 1024)
         else:
@@ -447,26 +492,11 @@ class DanaEngine:
 
         self._mark("layer4_bbox")
         # ---- head: per-RoI CISA (dana.py:247-290); support projections hoisted out of the RoI loop
-        sp_k = sh - pooling_size + 1
-        s_pooled = ops.avgpool(sup, sp_k)                                 # dana.py:114  [maps,7,7,C] fp32
-        if "support_pooled" in want:
-            extra["support_pooled"] = s_pooled.permute(0, 3, 1, 2)
-        pitch_h = (k * self.seg_pitch(bins) + 7) // 8 * 8
-        sp_h = self.seg_pitch(bins)
-        vc_h, _vt_h, rbar_h, cbar = ops.support_prepare(s_pooled.view(maps, bins, c), self.pe(bins), k,
-                                                        un_w=self.rcnn_un_w, un_b=self.rcnn_un_b,
-                                                        unary_gamma=self.unary_gamma, vt_pitch=pitch_h, seg_pitch=sp_h,
-                                                        split=split, want_cbar=True)
-        kc_h = ops.linear(vc_h, self.rcnn_k_w, 256, split=split)
-        # (P V) W^T = P (V W^T): the dense half of the 2048 -> 64 transform (:288) is applied to the support values
-        # BEFORE the attention-weighted sum (:281), so the [R*49, 1024] attended feature (241 MB per support set) is
-        # never materialised.  V = Vc + 1 m^T (m = column mean) and the rows of P sum to one, hence
-        #   dense W_d^T = (1/K) sum_k P_k (Vc_k W_d^T) + (rbar + mean_k m_k) W_d^T      (cbar = rbar + mean_k m_k)
-        z = torch.empty((maps * bins, 64), dtype=torch.float32, device=dev)
-        ops.linear(vc_h, self.tr_wd, 64, out_f32=z)
-        zt = ops.transpose_segments(z.view(maps, bins, 64), k, sp_h, pitch_h, split=split)   # [B*sets, 64, pitch]
-        c64 = torch.empty((b * sets, 64), dtype=torch.float32, device=dev)
-        ops.linear(cbar, self.tr_wd, 64, out_f32=c64)
+        if head_sup is None:
+            head_sup = self._head_support_side(sup, b, sets, pooling_size, want, extra)
+        elif side is not None:
+            torch.cuda.current_stream().wait_stream(side)                # join the side branch
+        kc_h, zt, c64 = head_sup
         # query side: the positional encoding of :259 enters as the per-bin bias PE W^T of the two projections
         pooled2d = pooled.view(r * bins, c)
         q_h = torch.empty((r * bins, 256), dtype=torch.float32, device=dev)

@@ -497,7 +497,7 @@ def cisa_fwd(q: Pair, sup: Pair, pe, shots, sets, batch, *, wq: Pair, wk: Pair, 
     a.out_hi, a.out_lo, a.out_pitch = _p(out.hi), _p(out.lo), out.hi.stride(0)
     a.out_f16 = 1 if out.is_f16 else 0
     a.workspace, a.workspace_bytes = _p(ws), nbytes
-    _count(15 if ns > 256 else 14)     # 4 support kernels, 4 GEMMs, 3 centring kernels (1 for small groups), softmax, memsets
+    _count(14)     # 4 support kernels, 4 GEMMs (softmax fused), 3 centring kernels, 3 memsets
     check(lib.dana_cisa_fwd(ctypes.byref(a), _stream()), "dana_cisa_fwd")
     return out
 

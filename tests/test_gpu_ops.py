@@ -421,3 +421,29 @@ def test_linear_pair_output_partial_last_tile(ops, m, k, n):
     ref = torch.relu(x.float().double() @ w.float().double().t() + res.float().double())
     assert relerr(out.float(), ref) <= 2e-5
     assert (buf.hi[m] == 0).all() and (buf.lo[m] == 0).all()
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("rows,ns,shots,batch", [(1900, 400, 3, 1), (300, 400, 1, 2), (777, 324, 2, 1), (130, 512, 2, 1),
+                                                 (500, 260, 5, 1)])
+def test_fused_softmax_wide_segments(ops, split, rows, ns, shots, batch):
+    """Attention logits + softmax in one launch for segments of 257..512 keys (the reference's 20x20 supports: 400):
+    single 512-column TMEM accumulator, three-pass epilogue.  Against softmax_j(alpha * q k^T) of the same rounded
+    operands in fp64, per shot segment; pad columns zero."""
+    torch.manual_seed(ns + rows)
+    d = 256
+    q = ops.Pair.from_float(torch.randn(batch * rows, d, device="cuda"), split)
+    k = ops.Pair.from_float(torch.randn(batch * shots * ns, d, device="cuda") * 1.5, split)
+    sp = (ns + 7) // 8 * 8
+    pitch = (shots * sp + 7) // 8 * 8 + 8
+    p = ops.Pair.zeros((batch * rows, pitch), "cuda", split)
+    ops.linear(q, k, shots * ns, alpha=1.0 / 16.0, out=p, batch=batch, b_batch_stride=shots * ns * d, softmax_ns=ns,
+               softmax_pitch=sp)
+    qf, kf = q.float().double().view(batch, rows, d), k.float().double().view(batch, shots, ns, d)
+    got = p.float().view(batch, rows, pitch)
+    for s in range(shots):
+        ref = torch.softmax(torch.einsum("brd,bnd->brn", qf, kf[:, s]) / 16.0, dim=2)
+        seg = got[:, :, s * sp:s * sp + ns]
+        assert relerr(seg, ref) <= (3e-5 if split else 8e-3)
+        assert (got[:, :, s * sp + ns:(s + 1) * sp] == 0).all()
+    assert (got[:, :, shots * sp:] == 0).all()

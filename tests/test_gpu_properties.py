@@ -48,13 +48,16 @@ def test_full_size_forward_batch_equivariance(full_case):
     the outputs.  Tile boundaries move with the position in the batch, so equality is to fp32 rounding, and the
     proposals (discontinuous in the scores) are compared as sets."""
     eng, im, info, sup = full_case
+    # mixed mode: an fp32 accumulation-order difference can flip the fp16 rounding of an RPN activation (2^-11 relative),
+    # which moves the decoded boxes of the large anchors by ~0.1 px
+    tol = 0.5 if eng.precision == "mixed" else 0.05
     perm = [2, 0, 3, 1]
     rois, cls_prob, bbox = eng.forward(im, info, sup)
     rois_p, cls_p, bbox_p = eng.forward(im[perm].contiguous(), info[perm].contiguous(), sup[perm].contiguous())
     for j, i in enumerate(perm):
         a, b = rois[i, :, 1:], rois_p[j, :, 1:]
         d = (a[:, None, :] - b[None, :, :]).abs().max(2)[0].min(1)[0]
-        assert (d <= 0.05).float().mean().item() >= 0.97
+        assert (d <= tol).float().mean().item() >= 0.97
         assert (rois_p[j, :, 0] == j).all()
 
 
