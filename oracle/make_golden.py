@@ -66,6 +66,38 @@ def proposal_case():
 
 
 FORWARD_CASE = dict(seed=1996, height=128, width=192, n_shot=2, attn_std=0.05)
+# the headline shape itself (BASELINE.json configs[1], one episode): 600x1000 query, 3 shots (the reference's eval
+# forward uses the positive set only)
+FORWARD_FULL_CASE = dict(seed=2024, height=600, width=1000, n_shot=3, attn_std=0.05)
+
+
+def postprocess_case():
+    """Detections input for the post-processing pin (inference.py:108-142 / utils.py:312-317): 300 boxes with
+    clustered overlaps and scores around the 0.05 threshold."""
+    rs = np.random.RandomState(31)
+    n = 300
+    cx, cy = rs.uniform(50, 950, n), rs.uniform(50, 550, n)
+    cx[100:] = cx[:200] + rs.normal(0, 6, 200)
+    cy[100:] = cy[:200] + rs.normal(0, 6, 200)
+    w, h = rs.uniform(20, 300, n), rs.uniform(20, 300, n)
+    boxes = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
+    scores = rs.uniform(0, 1, n).astype(np.float32) ** 2
+    return boxes, scores
+
+
+def reference_NMS_function(ref_c, nms_thresh):
+    """utils.py cannot be imported (it pulls the dataset stack), so its NMS() is exec'd from the source text,
+    lines 312-317, with the names it uses bound to the reference's own objects."""
+    import easydict  # noqa: F401  (shim installed by ref_loader)
+    src = open("/root/reference/utils.py").read().splitlines()
+    start = next(i for i, l in enumerate(src) if l.startswith("def NMS("))
+    body = "\n".join(src[start:start + 6])
+    from model.roi_layers import nms as ref_nms
+    from model.utils.config import cfg
+    cfg.TEST.NMS = nms_thresh
+    ns = {"torch": torch, "nms": ref_nms, "cfg": cfg}
+    exec(compile(body, "utils.py:NMS", "exec"), ns)
+    return ns["NMS"]
 
 
 def sample(t, step=7):
@@ -131,6 +163,32 @@ def main():
              support_feat_sample=sample(sup_feat, 97), dense_sample=sample(dense),
              dense_abs_sum=float(dense.abs().sum()), pooled_sample=sample(cap["pooled"], 101),
              base_shape=np.array(base_feat.shape), dense_shape=np.array(dense.shape))
+    # the same at the headline shape (one 600x1000 query, 3 shots): sampled outputs of the UNMODIFIED reference
+    ff = FORWARD_FULL_CASE
+    net3 = DAnARCNN(["bg", "fg"], "concat", 256, 256, pretrained=False, semantic_enhance=True, num_way=2,
+                    num_shot=ff["n_shot"])
+    net3.create_architecture()
+    missing, unexpected = net3.load_state_dict(O.make_params(ff["seed"], attn_std=ff["attn_std"]), strict=False)
+    assert not unexpected
+    net3.eval()
+    im, info, sup = O.synth_inputs(ff["seed"], 1, ff["height"], ff["width"], ff["n_shot"])
+    cap = {}
+    net3.RCNN_base.register_forward_hook(lambda m, i, o: cap.setdefault("base", []).append(o.detach()))
+    net3.RCNN_rpn.register_forward_hook(lambda m, i, o: cap.__setitem__("corr", i[0].detach()))
+    net3.RCNN_roi_align.register_forward_hook(lambda m, i, o: cap.__setitem__("pooled", o.detach()))
+    with torch.no_grad():
+        rois, cls_prob, bbox_pred, *_ = net3(im, info, torch.zeros(1, 1, 5), torch.zeros(1), sup)
+    base_feat = cap["base"][0]
+    dense = cap["corr"][:, 1024:]
+    np.savez(os.path.join(GOLD, "forward_full.npz"), rois=rois.numpy(), cls_prob=cls_prob.numpy(),
+             bbox_pred=bbox_pred.numpy(), base_feat_sample=sample(base_feat, 53), dense_sample=sample(dense, 53),
+             pooled_sample=sample(cap["pooled"], 1009), base_shape=np.array(base_feat.shape))
+
+    # detections post-processing: the reference's NMS() (utils.py:312-317) exec'd from its source
+    boxes, scores = postprocess_case()
+    NMS = reference_NMS_function(ref_c, 0.3)
+    dets = NMS(torch.from_numpy(boxes), torch.from_numpy(scores))
+    np.savez(os.path.join(GOLD, "postprocess.npz"), dets=dets.numpy())
     print("golden vectors written to", GOLD)
     for f in sorted(os.listdir(GOLD)):
         print("  %-22s %8d bytes" % (f, os.path.getsize(os.path.join(GOLD, f))))

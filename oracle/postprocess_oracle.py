@@ -1,8 +1,10 @@
 """ORACLE -- TEST INFRASTRUCTURE ONLY.  Restatement of the detection post-processing that follows the forward
 in the reference's inference.py:108-142 with NMS() of utils.py:312-317 (torch CPU + the oracle's nms).
 Parity note: inference.py itself cannot be imported here (it pulls datasets / pycocotools), so this file is
-pinned only through its building blocks (bbox_transform_inv, clip_boxes, nms), each of which is pinned to the
-reference in tests/test_oracle_pins.py."""
+pinned through its building blocks: bbox_transform_inv, clip_boxes and nms are each pinned to the reference in
+tests/test_oracle_pins.py, and the sort + NMS composition (lines marked utils.py below) is pinned to the reference's
+own NMS() exec'd from the source text of utils.py:312-317 (oracle/make_golden.py -> tests/golden/postprocess.npz,
+tests/test_oracle_pins.py::test_postprocess_vs_reference_NMS)."""
 import torch
 
 import dana_oracle as O

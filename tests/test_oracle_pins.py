@@ -90,6 +90,41 @@ def test_forward_vs_reference(golden_dir, forward_small):
     close(out["cls_prob"].numpy(), g["cls_prob"], 1e-4)
 
 
+def test_forward_full_size_vs_reference(golden_dir):
+    """The oracle against the UNMODIFIED reference at the headline shape itself (one 600x1000 query, 3 shots;
+    oracle/make_golden.py FORWARD_FULL_CASE): sampled base / dense / pooled features, rois, cls_prob, bbox_pred."""
+    g = _g(golden_dir, "forward_full.npz")
+    ff = MG.FORWARD_FULL_CASE
+    p = O.make_params(ff["seed"], attn_std=ff["attn_std"])
+    im, info, sup = O.synth_inputs(ff["seed"], 1, ff["height"], ff["width"], ff["n_shot"])
+    with torch.no_grad():
+        out = O.dana_forward_eval(p, im, info, sup, ff["n_shot"])
+
+    def close(a, b, tol=2e-5):
+        a = np.asarray(a, dtype=np.float64)
+        b = np.asarray(b, dtype=np.float64)
+        assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-30), np.abs(a - b).max()
+    assert tuple(out["base_feat"].shape) == tuple(g["base_shape"]) == (1, 1024, 38, 63)
+    close(MG.sample(out["base_feat"], 53), g["base_feat_sample"])
+    close(MG.sample(out["dense"], 53), g["dense_sample"])
+    close(MG.sample(out["pooled"], 1009), g["pooled_sample"])
+    close(out["rois"].numpy(), g["rois"], 1e-5)
+    close(out["bbox_pred"].numpy(), g["bbox_pred"], 1e-4)
+    close(out["cls_prob"].numpy(), g["cls_prob"], 1e-4)
+
+
+def test_postprocess_vs_reference_NMS(golden_dir):
+    """oracle/postprocess_oracle.py's sort + NMS composition against the reference's own NMS() (utils.py:312-317,
+    exec'd from its source by oracle/make_golden.py): same detections in the same order."""
+    boxes, scores = MG.postprocess_case()
+    g = _g(golden_dir, "postprocess.npz")["dets"]
+    b, s = torch.from_numpy(boxes), torch.from_numpy(scores)
+    order = torch.sort(s, dim=0, descending=True, stable=True)[1]
+    dets = torch.cat((b, s.unsqueeze(1)), 1)[order]
+    keep = O.nms(b[order].numpy(), s[order].numpy(), 0.3)
+    np.testing.assert_array_equal(dets[keep.view(-1).long()].numpy(), g)
+
+
 def test_ref_extension_matches_oracle_when_present():
     """The reference's own compiled CPU operators (oracle/_ref) travel with the repo; when present they
     must agree with the C restatement on a fresh random case (bit-exact)."""
