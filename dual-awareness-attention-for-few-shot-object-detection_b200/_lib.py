@@ -85,6 +85,10 @@ SIGNATURES = {
                                     c_int, c_int, c_float, c_float, c_float, c_void_p, c_int, c_int, c_void_p]),
     "dana_conv_gemm_workspace_bytes": (c_int64, []),
     "dana_conv_gemm": (c_int, [POINTER(ConvGemmArgs), c_void_p]),
+    "dana_rpn_losses_workspace_bytes": (c_int64, []),
+    "dana_rpn_losses": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int64, c_void_p]),
+    "dana_rcnn_losses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dana_cisa_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "dana_cisa_fwd": (c_int, [POINTER(CisaArgs), c_void_p]),
     "dana_stem_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

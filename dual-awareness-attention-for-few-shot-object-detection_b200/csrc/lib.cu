@@ -10,6 +10,7 @@
 #include "roi_align.cuh"
 #include "dana_ops.cuh"
 #include "episode.cuh"
+#include "train_ops.cuh"
 
 using namespace dana;
 
@@ -118,5 +119,6 @@ int dana_episode_resize(const void* src, int src_is_f32, int src_h, int src_w, i
 
 #include "dana_ops_api.inc"
 #include "cisa_api.inc"
+#include "train_api.inc"
 
 }  // extern "C"

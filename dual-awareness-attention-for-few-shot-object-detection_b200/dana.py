@@ -3,9 +3,10 @@ constructor, `create_architecture()`, parameter names / shapes (346-key state-di
 checkpoints load with `load_state_dict`), `train()` semantics (BatchNorm always in eval) and
 `forward(im_data, im_info, gt_boxes, num_boxes, support_ims, all_cls_gt_boxes=None)` 8-tuple.
 
-The eval forward runs on `engine.DanaEngine` (hand-written sm_100a kernels behind the C ABI); the
-nn.Module only owns the parameters.  The training branch (losses, target layers, backward) is
-row a15 of SURVEY.md section 8 and is not built in this round: calling forward in train mode raises."""
+The forward runs on `engine.DanaEngine` (hand-written sm_100a kernels behind the C ABI); the nn.Module only owns
+the parameters.  Train mode returns the reference's 8-tuple with the four losses (target layers on the host with the
+reference's numpy RNG call order, loss kernels on the device); the BACKWARD pass of this path is not built
+(SURVEY.md section 8 row a15): the losses carry no autograd graph."""
 import math
 
 import torch
@@ -217,10 +218,66 @@ class DAnARCNN(nn.Module):
             self._graphs.clear()
         return self._engine
 
+    def _forward_train(self, im_data, im_info, gt_boxes, num_boxes, support_ims, teacher=None):
+        """Training branch of _DAnARCNN.forward (dana.py:100-108,158-215): the forward and the four losses.
+        support_ims [B, 2*K, 3, H, W]: K positive then K negative crops per image (n_way = 2).  Anchor / proposal
+        targets are drawn on the host with numpy's global RNG exactly like the reference (dana_b200.targets); the
+        losses are device kernels.  Returns the reference's 8-tuple; the losses are 0-dim CUDA tensors WITHOUT a
+        graph: the backward pass of this path is not built."""
+        import numpy as np
+
+        from . import ops, targets
+        if self.n_way != 2:
+            raise NotImplementedError("the training branch is built for n_way = 2 (positive + negative support set), "
+                                      "like the reference's (dana.py:100-108)")
+        if support_ims.shape[1] != 2 * self.n_shot:
+            raise ValueError("train mode expects %d support crops per image (n_way * n_shot), got %d"
+                             % (2 * self.n_shot, support_ims.shape[1]))
+        eng = self.engine()
+        dev = im_data.device
+        b = im_data.shape[0]
+        qh, qw = eng._trunk_hw(im_data.shape[2], im_data.shape[3])
+        gt_host = gt_boxes.detach().float().cpu().numpy()
+        info_host = im_info.detach().float().cpu().numpy()
+        state = {}
+
+        def hook(rois):
+            # anchor targets first, then proposal targets: the order of the reference's numpy RNG draws
+            # (RCNN_rpn.forward -> anchor_target_layer, then RCNN_proposal_target; dana.py:158-170)
+            state["anchor"] = targets.anchor_targets(
+                qh, qw, gt_host, info_host, eng.base_anchors.cpu().numpy(), eng.feat_stride,
+                negative_overlap=cfg.TRAIN.RPN_NEGATIVE_OVERLAP, positive_overlap=cfg.TRAIN.RPN_POSITIVE_OVERLAP,
+                clobber_positives=cfg.TRAIN.RPN_CLOBBER_POSITIVES, fg_fraction=cfg.TRAIN.RPN_FG_FRACTION,
+                batchsize=cfg.TRAIN.RPN_BATCHSIZE, inside_weight=cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0],
+                positive_weight=cfg.TRAIN.RPN_POSITIVE_WEIGHT)
+            state["all_rois"] = rois
+            sample = targets.proposal_targets(
+                rois.detach().cpu().numpy(), gt_host, rois_per_image=cfg.TRAIN.BATCH_SIZE,
+                fg_fraction=cfg.TRAIN.FG_FRACTION, fg_thresh=cfg.TRAIN.FG_THRESH, bg_thresh_hi=cfg.TRAIN.BG_THRESH_HI,
+                bg_thresh_lo=cfg.TRAIN.BG_THRESH_LO, normalize_means=cfg.TRAIN.BBOX_NORMALIZE_MEANS,
+                normalize_stds=cfg.TRAIN.BBOX_NORMALIZE_STDS, inside_weights=cfg.TRAIN.BBOX_INSIDE_WEIGHTS,
+                normalize_targets=cfg.TRAIN.BBOX_NORMALIZE_TARGETS_PRECOMPUTED)
+            state["sample"] = sample
+            return torch.from_numpy(sample[0])
+
+        rois, cls_prob, bbox_pred, ex = eng.forward(
+            im_data, im_info.data, support_ims, pre_nms_top_n=cfg.TRAIN.RPN_PRE_NMS_TOP_N,
+            post_nms_top_n=cfg.TRAIN.RPN_POST_NMS_TOP_N, nms_thresh=cfg.TRAIN.RPN_NMS_THRESH,
+            pooling_size=cfg.POOLING_SIZE, want=("rpn_raw", "cls_score"), rois_hook=hook, teacher=teacher)
+        labels, tgt, in_w, out_w = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in state["anchor"]]
+        rpn = ops.rpn_losses(ex["rpn_raw"], labels, tgt, in_w, out_w, eng.num_a)
+        _, lab_s, tgt_s, inw_s, outw_s = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in state["sample"]]
+        r = b * lab_s.shape[1]
+        rcnn = ops.rcnn_losses(ex["cls_score"], lab_s.view(-1), bbox_pred, tgt_s.view(r, 4), inw_s.view(r, 4),
+                               outw_s.view(r, 4))
+        rois_label = torch.cat([lab_s.view(-1), torch.zeros_like(lab_s.view(-1))]).long()      # dana.py:195-196
+        return rois, cls_prob, bbox_pred, rpn[0], rpn[1], rcnn[0], rcnn[1], rois_label
+
     def forward(self, im_data, im_info, gt_boxes, num_boxes, support_ims, all_cls_gt_boxes=None):
+        if cfg.POOLING_MODE != "align":
+            raise NotImplementedError("POOLING_MODE %r is not built (shipped configs use 'align')" % cfg.POOLING_MODE)
         if self.training:
-            raise NotImplementedError("dana_b200: the training branch of DAnARCNN.forward (target layers, losses, "
-                                      "backward; dana.py:100-108,166-215) is not built yet -- call .eval()")
+            return self._forward_train(im_data, im_info, gt_boxes, num_boxes, support_ims)
         if cfg.POOLING_MODE != "align":
             raise NotImplementedError("POOLING_MODE %r is not built (shipped configs use 'align')" % cfg.POOLING_MODE)
         eng = self.engine()

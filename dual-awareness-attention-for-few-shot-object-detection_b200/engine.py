@@ -352,10 +352,12 @@ class DanaEngine:
 
     @torch.no_grad()
     def forward(self, im_data, im_info, support_ims, pre_nms_top_n=6000, post_nms_top_n=300, nms_thresh=0.7,
-                pooling_size=7, want=None, teacher=None, support_feats=None):
+                pooling_size=7, want=None, teacher=None, support_feats=None, rois_hook=None):
         """Eval forward.  im_data [B,3,H,W] fp32, im_info [B,3], support_ims [B, sets*K, 3, Hs, Ws].
         Returns (rois [B,post,5], cls_prob [sets*B*post, 2], bbox_pred [B*post, 4]); with `want` (a set of
-        stage names) also a dict of intermediates exported in the reference's layouts."""
+        stage names) also a dict of intermediates exported in the reference's layouts.
+        rois_hook (training branch): called as rois_hook(rois [B,post,5]) after the proposal layer, returns the rois
+        the head runs on (the proposal-target layer's [B,R,5] sample, dana.py:166-170)."""
         dev, split, k = self.device, self.split, self.n_shot
         b = im_data.shape[0]
         n_sup = support_ims.shape[1] if support_feats is None else support_feats.hi.shape[0] // b
@@ -457,10 +459,14 @@ class DanaEngine:
                              pre_nms_top_n, post_nms_top_n, nms_thresh, workspace=self._prop_ws)
         if teacher and "rois" in teacher:
             rois = teacher["rois"].to(dev).float().contiguous()
+        if "rpn_raw" in want:
+            extra["rpn_raw"] = rpn_raw
+        if rois_hook is not None:
+            rois = rois_hook(rois).to(dev).float().contiguous()
 
         self._mark("rpn_proposals")
         # ---- RoIAlign on the query feature (dana.py:183)
-        r = b * post_nms_top_n
+        r = rois.shape[0] * rois.shape[1]
         bins = pooling_size * pooling_size
         need_f32 = "pooled" in want
         pooled16 = None

@@ -609,5 +609,39 @@ def nhwc_pair_to_nchw(x: Pair):
     return out
 
 
+# --------------------------------------------------------------------------- training branch: losses
+def rpn_losses(rpn_out_f32, labels_i8, bbox_targets, inside_w, outside_w, num_a):
+    """rpn.py:96-116.  rpn_out_f32 [B,H,W,6A] fp32 (the RPN head's raw output), targets in (y, x, a) order
+    (dana_b200.targets.anchor_targets) -> fp32 [2] = (rpn_loss_cls, rpn_loss_box)."""
+    _need_cuda(rpn_out_f32, labels_i8, bbox_targets, inside_w, outside_w)
+    b, h, w, pitch = rpn_out_f32.shape
+    assert labels_i8.dtype == torch.int8 and labels_i8.numel() == b * h * w * num_a
+    lib = _lib.load()
+    dev = rpn_out_f32.device
+    wsb = lib.dana_rpn_losses_workspace_bytes()
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    out = torch.empty((2,), dtype=torch.float32, device=dev)
+    _count(2)
+    check(lib.dana_rpn_losses(_p(rpn_out_f32), b, b * h * w, num_a, pitch, _p(labels_i8.contiguous()),
+                              _p(bbox_targets.contiguous()), _p(inside_w.contiguous()), _p(outside_w.contiguous()),
+                              _p(out), _p(ws), wsb, _stream()), "dana_rpn_losses")
+    return out
+
+
+def rcnn_losses(cls_scores, labels, bbox_pred, bbox_targets, inside_w, outside_w):
+    """dana.py:199-215.  cls_scores [2R,2] (positive-support rows then negative-support rows), labels fp32 [R],
+    bbox tensors [R,4] -> fp32 [2] = (RCNN_loss_cls, RCNN_loss_bbox)."""
+    _need_cuda(cls_scores, labels, bbox_pred, bbox_targets, inside_w, outside_w)
+    r = labels.numel()
+    assert cls_scores.shape == (2 * r, 2) and bbox_pred.shape == (r, 4)
+    out = torch.empty((2,), dtype=torch.float32, device=cls_scores.device)
+    _count(1)
+    check(_lib.load().dana_rcnn_losses(_p(cls_scores.contiguous()), _p(labels.contiguous().float()), r,
+                                       _p(bbox_pred.contiguous()), _p(bbox_targets.contiguous().float()),
+                                       _p(inside_w.contiguous().float()), _p(outside_w.contiguous().float()), _p(out),
+                                       _stream()), "dana_rcnn_losses")
+    return out
+
+
 def device_error():
     return _lib.load().dana_device_error()

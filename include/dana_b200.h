@@ -273,6 +273,28 @@ int dana_nhwc_pair_to_nchw(const void* in_hi, const void* in_lo, int batch, int 
 int dana_transpose_segments(const float* in, int maps, int shots, int ns, int c, int seg_pitch, int64_t vt_pitch,
                             void* out_hi, void* out_lo, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Training branch: the loss layers.  The target layers that feed them are host code
+ * (dana_b200/targets.py: numpy RNG sampling like the reference's); all tensors below are device memory.
+ *
+ * dana_rpn_losses -- lib/model/rpn/rpn.py:96-116 with _smooth_l1_loss of lib/model/utils/net_utils.py:71-85 (sigma 3).
+ *   rpn_out [pixels][pitch] fp32 NHWC RPN head output: channels [0,A) bg scores, [A,2A) fg scores, [2A,6A) deltas;
+ *   labels int8 [pixels*A] (1 fg, 0 bg, -1 ignored), bbox_targets [pixels*A][4], inside_w / outside_w [pixels*A], all
+ *   in (pixel, anchor) order.  losses[0] = rpn_loss_cls (mean cross entropy over labels >= 0), losses[1] = rpn_loss_box
+ *   (sum over anchors and coordinates, mean over the batch).
+ * dana_rcnn_losses -- lib/model/framework/dana.py:199-215.  cls_scores [2*rois][2]: rows [0,rois) from the positive
+ *   support set, [rois,2*rois) from the negative one; labels fp32 [rois] (0 / 1) of the first half (the second half is
+ *   background); bbox_pred / bbox_targets / inside_w / outside_w [rois][4].  losses[0] = RCNN_loss_cls: cross entropy
+ *   over every foreground row, the max(1, min(2 fg, rows/4)) hardest background rows of the first half and the
+ *   max(1, min(fg, that)) hardest of the second; losses[1] = RCNN_loss_bbox (smooth-L1 sigma 1, mean over rois). */
+int64_t dana_rpn_losses_workspace_bytes(void);
+int dana_rpn_losses(const float* rpn_out, int batch, int64_t pixels, int num_a, int pitch, const int8_t* labels,
+                    const float* bbox_targets, const float* inside_w, const float* outside_w, float* losses,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+int dana_rcnn_losses(const float* cls_scores, const float* labels, int rois, const float* bbox_pred,
+                     const float* bbox_targets, const float* inside_w, const float* outside_w, float* losses,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

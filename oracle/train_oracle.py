@@ -247,6 +247,7 @@ def dana_forward_train(p, im_data, im_info, gt_boxes, num_boxes, support_ims, n_
     t = TRAIN_CFG
     rois = O.proposal_layer(prob, bbox, im_info, base_anchors, c["feat_stride"], t["rpn_pre_nms_top_n"],
                             t["rpn_post_nms_top_n"], t["rpn_nms_thresh"], nms_fn)
+    all_rois = rois
     targets = anchor_target_layer(fh, fw, gt_boxes, im_info, torch.from_numpy(base_anchors).float(), c["feat_stride"])
     rpn_loss_cls, rpn_loss_box = rpn_losses(cls_score, bbox, targets, num_a)
     rois, rois_label, rois_target, in_w, out_w = proposal_target_layer(rois, gt_boxes)
@@ -262,4 +263,5 @@ def dana_forward_train(p, im_data, im_info, gt_boxes, num_boxes, support_ims, n_
     loss_bbox = smooth_l1_loss(bbox_pred, rois_target.view(-1, 4), in_w.view(-1, 4), out_w.view(-1, 4))
     loss_cls = rcnn_cls_loss(cls_score_all, label_all)
     return dict(rois=rois, cls_prob=cls_prob, bbox_pred=bbox_pred, rpn_loss_cls=rpn_loss_cls, rpn_loss_box=rpn_loss_box,
-                RCNN_loss_cls=loss_cls, RCNN_loss_bbox=loss_bbox, rois_label=label_all, rpn_targets=targets)
+                RCNN_loss_cls=loss_cls, RCNN_loss_bbox=loss_bbox, rois_label=label_all, rpn_targets=targets,
+                all_rois=all_rois, rpn_cls_score=cls_score, rpn_bbox_pred=bbox, cls_score=cls_score_all)

@@ -1,0 +1,122 @@
+"""Training branch of DAnARCNN.forward on the GPU: target layers on the host with the
+reference's numpy RNG call order (dana_b200/targets.py), forward on the engine, loss kernels -- against
+oracle/train_oracle.py (pinned to the unmodified reference run in train mode, tests/golden/forward_train_small.npz).
+
+Proposals are discontinuous in the scores, so the proposal layer's output is teacher-forced from the oracle (the
+same practice as in test_gpu_forward.py); everything downstream -- sampled rois, labels, the four losses -- must then
+agree: sampled labels identical, losses to 1e-3 relative (mixed) / 2e-4 (bf16x3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dana_oracle as O
+import make_golden_train as MT
+import train_oracle as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def train_ref():
+    tc = MT.TRAIN_CASE
+    p = O.make_params(tc["seed"], attn_std=tc["attn_std"])
+    im, info, gt, nb, sup = MT.train_inputs()
+    np.random.seed(tc["np_seed"])
+    with torch.no_grad():
+        ref = T.dana_forward_train(p, im, info, gt, nb, sup, tc["n_shot"])
+    return p, (im, info, gt, nb, sup), ref
+
+
+def _net(p, n_shot, precision):
+    import dana_b200  # noqa: F401
+    from dana_b200.config import cfg_from_file, cfg_from_list, reset_cfg
+    from dana_b200.dana import DAnARCNN
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    reset_cfg()
+    cfg_from_file(os.path.join(root, "cfgs", "res50.yml"))
+    cfg_from_list(["ANCHOR_SCALES", "[4,8,16,32]", "ANCHOR_RATIOS", "[0.5,1,2]", "MAX_NUM_GT_BOXES", "50"])
+    net = DAnARCNN(["bg", "fg"], "concat", 256, 256, pretrained=False, semantic_enhance=True, num_way=2, num_shot=n_shot,
+                   precision=precision)
+    net.create_architecture()
+    net.load_state_dict(p, strict=False)
+    return net.cuda().train()
+
+
+@pytest.mark.parametrize("precision,tol", [("mixed", 1e-3), ("bf16x3", 2e-4)])
+def test_train_forward_losses_vs_oracle(train_ref, golden_dir, precision, tol):
+    p, (im, info, gt, nb, sup), ref = train_ref
+    tc = MT.TRAIN_CASE
+    net = _net(p, tc["n_shot"], precision)
+    np.random.seed(tc["np_seed"])
+    out = net._forward_train(im.cuda(), info.cuda(), gt.cuda(), nb.cuda(), sup.cuda(),
+                             teacher={"rois": ref["all_rois"].cuda()})
+    rois, cls_prob, bbox_pred, l_rpn_cls, l_rpn_box, l_cls, l_box, rois_label = out
+    # same RNG draws on the same candidates -> the same sample
+    assert torch.equal(rois.cpu(), ref["rois"])
+    assert torch.equal(rois_label.cpu(), ref["rois_label"])
+    assert tuple(cls_prob.shape) == (2 * 2 * 128, 2) and tuple(bbox_pred.shape) == (2 * 128, 4)
+
+    def rel(a, b):
+        a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert rel(cls_prob, ref["cls_prob"]) <= tol
+    assert rel(bbox_pred, ref["bbox_pred"]) <= tol
+    got = [float(l_rpn_cls), float(l_rpn_box), float(l_cls), float(l_box)]
+    want = [float(ref[k]) for k in ("rpn_loss_cls", "rpn_loss_box", "RCNN_loss_cls", "RCNN_loss_bbox")]
+    for g, w in zip(got, want):
+        assert abs(g - w) <= tol * abs(w), (got, want)
+    # and against the UNMODIFIED reference's own losses (train-mode golden)
+    gold = np.load(os.path.join(golden_dir, "forward_train_small.npz"))["losses"]
+    for g, w in zip(got, gold):
+        assert abs(g - w) <= tol * abs(w), (got, list(gold))
+    for t in (l_rpn_cls, l_rpn_box, l_cls, l_box):
+        assert t.dim() == 0 and t.is_cuda          # callers do .mean() / .item() on them (train.py:129-138)
+
+
+def test_loss_kernels_vs_oracle_functions():
+    """dana_rpn_losses / dana_rcnn_losses on random inputs against the oracle's loss functions (ties included)."""
+    import dana_b200  # noqa: F401
+    from dana_b200 import ops
+    rs = np.random.RandomState(3)
+    b, h, w, a = 2, 9, 13, 12
+    raw = torch.from_numpy(rs.standard_normal((b, h, w, 6 * a)).astype(np.float32))
+    labels = torch.from_numpy(rs.choice([-1, 0, 1], size=(b, h * w * a), p=[0.8, 0.15, 0.05]).astype(np.int8))
+    tgt = torch.from_numpy(rs.standard_normal((b, h * w * a, 4)).astype(np.float32)) * 0.3
+    in_w = (labels == 1).float()
+    out_w = (labels >= 0).float() / 37.0
+    got = ops.rpn_losses(raw.cuda(), labels.cuda(), tgt.cuda(), in_w.cuda(), out_w.cuda(), a).cpu()
+    # the oracle's layouts: cls [B,2A,H,W], bbox [B,4A,H,W], labels [B,1,A*H,W], targets / weights [B,4A,H,W]
+    nchw = raw.permute(0, 3, 1, 2)
+    o_lab = labels.view(b, h, w, a).permute(0, 3, 1, 2).reshape(b, 1, a * h, w).float()
+    to4 = lambda t: t.view(b, h, w, a, 1).expand(b, h, w, a, 4).reshape(b, h, w, 4 * a).permute(0, 3, 1, 2)  # noqa: E731
+    o_tgt = tgt.view(b, h, w, 4 * a).permute(0, 3, 1, 2)
+    want = T.rpn_losses(nchw[:, :2 * a].contiguous(), nchw[:, 2 * a:].contiguous(), (o_lab, o_tgt, to4(in_w), to4(out_w)), a)
+    assert abs(float(got[0]) - float(want[0])) <= 1e-5 * abs(float(want[0]))
+    assert abs(float(got[1]) - float(want[1])) <= 1e-5 * abs(float(want[1]))
+    for r, n_fg in ((256, 20), (256, 0), (128, 100), (512, 3)):
+        scores = torch.from_numpy(rs.standard_normal((2 * r, 2)).astype(np.float32))
+        lab = torch.zeros(r)
+        lab[torch.from_numpy(rs.permutation(r)[:n_fg].copy())] = 1
+        bp = torch.from_numpy(rs.standard_normal((r, 4)).astype(np.float32))
+        bt = torch.from_numpy(rs.standard_normal((r, 4)).astype(np.float32)) * lab.view(-1, 1)
+        iw = lab.view(-1, 1).expand(r, 4).contiguous()
+        got = ops.rcnn_losses(scores.cuda(), lab.cuda(), bp.cuda(), bt.cuda(), iw.cuda(), iw.cuda()).cpu()
+        lab_all = torch.cat([lab, torch.zeros(r)]).long()
+        w_cls = T.rcnn_cls_loss(scores, lab_all)
+        w_box = T.smooth_l1_loss(bp, bt, iw, iw)
+        assert abs(float(got[0]) - float(w_cls)) <= 1e-5 * max(abs(float(w_cls)), 1e-6), (r, n_fg)
+        assert abs(float(got[1]) - float(w_box)) <= 1e-5 * max(abs(float(w_box)), 1e-6), (r, n_fg)
+
+
+def test_eval_after_train_mode_still_works(train_ref):
+    """train() / eval() switch on one module: the eval forward returns python zeros for the losses again."""
+    p, (im, info, gt, nb, sup), ref = train_ref
+    net = _net(p, MT.TRAIN_CASE["n_shot"], "mixed")
+    np.random.seed(0)
+    out_t = net(im.cuda(), info.cuda(), gt.cuda(), nb.cuda(), sup.cuda())
+    assert len(out_t) == 8 and out_t[7].shape[0] == 2 * 2 * 128
+    net.eval()
+    out_e = net(im.cuda(), info.cuda(), gt.cuda(), nb.cuda(), sup[:, :MT.TRAIN_CASE["n_shot"]].contiguous().cuda())
+    assert out_e[3:7] == (0, 0, 0, 0) and out_e[7] is None

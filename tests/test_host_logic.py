@@ -237,3 +237,57 @@ def test_bucketed_grad_allreduce_gloo_world2():
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+# ------------------------------------------------------------------ training target layers (host side, row a15)
+@pytest.mark.parametrize("seed,n_gt,hw", [(0, 1, (10, 14)), (1, 3, (38, 63)), (2, 8, (25, 40)), (3, 0, (12, 12))])
+def test_target_layers_match_oracle(seed, n_gt, hw):
+    """dana_b200.targets (numpy, product path) against oracle/train_oracle.py (torch restatement pinned to the
+    unmodified reference): under the same numpy seed both make the same RNG draws -> identical labels / sampled
+    rois, targets and weights equal to fp32 rounding."""
+    import numpy as np
+    import torch
+
+    import dana_oracle as O
+    import train_oracle as T
+    from dana_b200 import targets as TG
+    rs = np.random.RandomState(seed)
+    fh, fw = hw
+    b = 2
+    gt = np.zeros((b, 6 if n_gt <= 6 else 10, 5), dtype=np.float32)
+    for i in range(b):
+        for j in range(n_gt):
+            x1, y1 = rs.uniform(0, fw * 16 - 80), rs.uniform(0, fh * 16 - 80)
+            gt[i, j] = [x1, y1, x1 + rs.uniform(20, 78), y1 + rs.uniform(20, 78), 1.0]
+    info = np.array([[fh * 16.0, fw * 16.0, 1.0]] * b, dtype=np.float32)
+    base = O.generate_anchors(scales=(4, 8, 16, 32)).astype(np.float32)
+    np.random.seed(100 + seed)
+    want = T.anchor_target_layer(fh, fw, torch.from_numpy(gt), torch.from_numpy(info), torch.from_numpy(base))
+    np.random.seed(100 + seed)
+    labels, tgt, in_w, out_w = TG.anchor_targets(fh, fw, gt, info, base)
+    a = base.shape[0]
+    # the oracle returns the reference's NCHW views; bring them to (y, x, a) order
+    w_lab = want[0].view(b, a, fh, fw).permute(0, 2, 3, 1).reshape(b, -1).numpy()
+    w_tgt = want[1].view(b, a, 4, fh, fw).permute(0, 3, 4, 1, 2).reshape(b, -1, 4).numpy()
+    w_in = want[2].view(b, a, 4, fh, fw).permute(0, 3, 4, 1, 2).reshape(b, -1, 4).numpy()[..., 0]
+    w_out = want[3].view(b, a, 4, fh, fw).permute(0, 3, 4, 1, 2).reshape(b, -1, 4).numpy()[..., 0]
+    np.testing.assert_array_equal(labels, w_lab.astype(np.int8))
+    np.testing.assert_allclose(tgt, w_tgt, rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(in_w, w_in)
+    np.testing.assert_allclose(out_w, w_out, rtol=1e-7, atol=0)
+    if n_gt == 0:
+        return                                   # no box at all: the proposal target layer raises in both
+    rois = np.zeros((b, 300, 5), dtype=np.float32)
+    for i in range(b):
+        x1, y1 = rs.uniform(0, fw * 16 - 40, 300), rs.uniform(0, fh * 16 - 40, 300)
+        rois[i] = np.stack([np.full(300, i), x1, y1, x1 + rs.uniform(8, 200, 300), y1 + rs.uniform(8, 200, 300)], 1)
+        rois[i, :40, 1:] = gt[i, rs.randint(0, n_gt, 40), :4] + rs.normal(0, 4, (40, 4))      # some near the gt
+    np.random.seed(200 + seed)
+    w = T.proposal_target_layer(torch.from_numpy(rois), torch.from_numpy(gt))
+    np.random.seed(200 + seed)
+    g = TG.proposal_targets(rois, gt)
+    np.testing.assert_array_equal(g[0], w[0].numpy())
+    np.testing.assert_array_equal(g[1], w[1].numpy())
+    np.testing.assert_allclose(g[2], w[2].numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_array_equal(g[3], w[3].numpy())
+    np.testing.assert_array_equal(g[4], w[4].numpy())
