@@ -79,8 +79,9 @@ SIGNATURES = {
                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dana_roi_align_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dana_roi_align_backward_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "dana_roi_align_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                        c_int, c_void_p, c_void_p]),
+                                        c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "dana_episode_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_double, c_double,
                                     c_int, c_int, c_float, c_float, c_float, c_void_p, c_int, c_int, c_void_p]),
     "dana_conv_gemm_workspace_bytes": (c_int64, []),

@@ -96,11 +96,18 @@ int dana_roi_align_head(const float* feat_nhwc, const float* rois, int num_rois,
                             out, out_hi, out_lo, pe, qpe_hi, qpe_lo, out_f16, static_cast<cudaStream_t>(stream));
 }
 
+int64_t dana_roi_align_backward_workspace_bytes(int num_rois, int batch, int channels, int height, int width,
+                                                int pooled_h, int pooled_w, int layout) {
+  return roi_align_backward_workspace(num_rois, batch, channels, height, width, pooled_h, pooled_w, layout);
+}
+
 int dana_roi_align_backward(const float* grad_out, const float* rois, int num_rois, int batch, int channels,
                             int height, int width, int pooled_h, int pooled_w, float spatial_scale,
-                            int sampling_ratio, float* grad_input, void* stream) {
+                            int sampling_ratio, int layout, float* grad_input, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
   return roi_align_backward_run(grad_out, rois, num_rois, batch, channels, height, width, pooled_h, pooled_w,
-                                spatial_scale, sampling_ratio, grad_input, static_cast<cudaStream_t>(stream));
+                                spatial_scale, sampling_ratio, layout, grad_input, workspace, workspace_bytes,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int64_t dana_conv_gemm_workspace_bytes(void) { return 4096 + static_cast<int64_t>(sm_count()) * 128 * 256 * 4; }

@@ -668,11 +668,131 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
   }
 }
 
-// Backward: scatter with atomics into NCHW grad (lib/model/csrc/cuda/ROIAlign_cuda.cu:178-254 semantics).
-__global__ void roi_align_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
-                                     long long nthreads, int channels, int height, int width, int pooled_h,
-                                     int pooled_w, float spatial_scale, int sampling_ratio,
-                                     float* __restrict__ grad_in) {
+// ---------------------------------------------------------------------------------------------
+// Backward of the 7x7 RoIAlign (semantics of lib/model/csrc/cuda/ROIAlign_cuda.cu:178-254: every sample scatters its
+// bin gradient to its four taps), as the TRANSPOSE of the forward's separable form:
+//   dF[y][x] += (1/count) * sum_ph wy[ph][y] * sum_pw wx[pw][x] * dOut[ph][pw]
+// NHWC on both sides.  Grid (RoI, 512-channel slab), 128 threads x 4 consecutive channels, the same compact per-bin tap
+// tables as the forward.  A map pixel of the RoI window receives ONE 16-byte vector reduction (red.global.add.v4.f32)
+// per bin row / bin column pair that touches it -- (sum ny) x (sum nx) per thread, coalesced 512-byte runs per warp --
+// instead of grid_h * grid_w * 4 scalar atomics per bin and channel on an NCHW map (a 600-px RoI: ~2 k vector
+// reductions against ~28 k scalar ones per 4 channels).  The x contraction of a bin row is done once per (ph, x) in
+// registers and reused by all its map rows.  RoIs whose bins exceed the tables take the direct per-sample path.
+// (Float atomics: the summation order, hence the last bits, vary run to run -- as in the reference.)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+}
+
+__global__ void __launch_bounds__(kRoi7Threads, 4)
+roi_align7_bwd_kernel(const float* __restrict__ grad_out /*[R][49][C]*/, const float* __restrict__ rois, int channels,
+                      int height, int width, float spatial_scale, int sampling_ratio, float* __restrict__ grad_in /*NHWC*/) {
+  __shared__ Roi7Tables s;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) s.g = roi_geometry(rois + static_cast<long long>(r) * 5, spatial_scale, 7, 7, sampling_ratio);
+  __syncthreads();
+  const RoiGeom g = s.g;
+  const int c0 = (blockIdx.y * kRoi7Threads + tid) * 4;
+  const bool c_ok = c0 < channels;
+  const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
+  float* gbase = grad_in + static_cast<long long>(g.batch_ind) * height * width * channels + (c_ok ? c0 : 0);
+  const float* go = grad_out + static_cast<long long>(r) * 49 * channels + (c_ok ? c0 : 0);
+  if (g.bin_w > 14.0f || g.bin_h > 14.0f) {
+    // bins wider than the tap tables (an RoI much larger than the map): per-sample scatter, still NHWC / vectorised
+    if (!c_ok) return;
+    for (int ph = 0; ph < 7; ++ph) {
+      for (int pw = 0; pw < 7; ++pw) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(go + static_cast<long long>(ph * 7 + pw) * channels));
+        for (int iy = 0; iy < g.grid_h; ++iy) {
+          const float y = sample_coord(g.start_h, g.bin_h, ph, iy, g.grid_h);
+          int yl, yh;
+          float wyl, wyh;
+          if (!axis_taps(y, height, yl, yh, wyl, wyh)) continue;
+          for (int ix = 0; ix < g.grid_w; ++ix) {
+            const float x = sample_coord(g.start_w, g.bin_w, pw, ix, g.grid_w);
+            int xl, xh;
+            float wxl, wxh;
+            if (!axis_taps(x, width, xl, xh, wxl, wxh)) continue;
+            const float w00 = wyl * wxl * inv_count, w01 = wyl * wxh * inv_count, w10 = wyh * wxl * inv_count,
+                        w11 = wyh * wxh * inv_count;
+            red_add4(gbase + (static_cast<long long>(yl) * width + xl) * channels, d.x * w00, d.y * w00, d.z * w00, d.w * w00);
+            red_add4(gbase + (static_cast<long long>(yl) * width + xh) * channels, d.x * w01, d.y * w01, d.z * w01, d.w * w01);
+            red_add4(gbase + (static_cast<long long>(yh) * width + xl) * channels, d.x * w10, d.y * w10, d.z * w10, d.w * w10);
+            red_add4(gbase + (static_cast<long long>(yh) * width + xh) * channels, d.x * w11, d.y * w11, d.z * w11, d.w * w11);
+          }
+        }
+      }
+    }
+    return;
+  }
+  if (tid < 7) build_axis_compact(s.wy[tid], &s.ylo[tid], &s.ny[tid], tid, height, g.start_h, g.bin_h, g.grid_h);
+  if (tid >= 32 && tid < 39)
+    build_axis_compact(s.wx[tid - 32], &s.xlo[tid - 32], &s.nx[tid - 32], tid - 32, width, g.start_w, g.bin_w, g.grid_w);
+  __syncthreads();
+  if (!c_ok) return;
+  for (int ph = 0; ph < 7; ++ph) {
+    const int ny = s.ny[ph];
+    if (ny == 0) continue;
+    float4 d[7];
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw) {
+      d[pw] = __ldg(reinterpret_cast<const float4*>(go + static_cast<long long>(ph * 7 + pw) * channels));
+      d[pw].x *= inv_count; d[pw].y *= inv_count; d[pw].z *= inv_count; d[pw].w *= inv_count;
+    }
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw) {
+      const int nx = s.nx[pw], x0 = s.xlo[pw];
+      for (int j = 0; j < nx; ++j) {
+        const float wx = s.wx[pw][j];
+        if (wx == 0.0f) continue;
+        const float4 e = make_float4(d[pw].x * wx, d[pw].y * wx, d[pw].z * wx, d[pw].w * wx);   // x-contracted, reused over y
+        float* col = gbase + static_cast<long long>(x0 + j) * channels;
+        for (int k = 0; k < ny; ++k) {
+          const float wy = s.wy[ph][k];
+          if (wy == 0.0f) continue;
+          red_add4(col + static_cast<long long>(s.ylo[ph] + k) * width * channels, e.x * wy, e.y * wy, e.z * wy, e.w * wy);
+        }
+      }
+    }
+  }
+}
+
+// [R][C][49] -> [R][49][C] (and back for the map: see nhwc_to_nchw_kernel) -- the reference-layout boundary of the backward
+__global__ void rc49_to_r49c_kernel(const float* __restrict__ in, float* __restrict__ out, int channels) {
+  __shared__ float tile[32][50];
+  const int r = blockIdx.x, c0 = blockIdx.y * 32;
+  const float* src = in + (static_cast<long long>(r) * channels + c0) * 49;
+  const int nch = min(32, channels - c0);
+  for (int i = threadIdx.x; i < nch * 49; i += blockDim.x) tile[i / 49][i % 49] = src[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 49 * 32; i += blockDim.x) {
+    const int bin = i >> 5, c = i & 31;
+    if (c < nch) out[(static_cast<long long>(r) * 49 + bin) * channels + c0 + c] = tile[c][bin];
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int channels, int hw) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* src = in + static_cast<long long>(b) * channels * hw;
+  float* dst = out + static_cast<long long>(b) * channels * hw;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < hw && c < channels) ? src[static_cast<long long>(p) * channels + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < channels && p < hw) dst[static_cast<long long>(c) * hw + p] = tile[threadIdx.x][i];
+  }
+}
+
+// Generic pooled sizes (not used by any shipped configuration): per-element scatter on the reference's NCHW layout.
+__global__ void roi_align_bwd_generic_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
+                                             long long nthreads, int channels, int height, int width, int pooled_h,
+                                             int pooled_w, float spatial_scale, int sampling_ratio,
+                                             float* __restrict__ grad_in) {
   for (long long index = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; index < nthreads;
        index += static_cast<long long>(blockDim.x) * gridDim.x) {
     const int pw = static_cast<int>(index % pooled_w);
@@ -681,8 +801,7 @@ __global__ void roi_align_bwd_kernel(const float* __restrict__ grad_out, const f
     const int n = static_cast<int>(index / pooled_w / pooled_h / channels);
     const RoiGeom g = roi_geometry(rois + static_cast<long long>(n) * 5, spatial_scale, pooled_h, pooled_w, sampling_ratio);
     float* gin = grad_in + (static_cast<long long>(g.batch_ind) * channels + c) * height * width;
-    const float go = grad_out[index];
-    const float count = static_cast<float>(g.grid_h * g.grid_w);
+    const float go = grad_out[index] / static_cast<float>(g.grid_h * g.grid_w);
     for (int iy = 0; iy < g.grid_h; ++iy) {
       const float y = sample_coord(g.start_h, g.bin_h, ph, iy, g.grid_h);
       int yl, yh;
@@ -693,10 +812,10 @@ __global__ void roi_align_bwd_kernel(const float* __restrict__ grad_out, const f
         int xl, xh;
         float wxl, wxh;
         if (!axis_taps(x, width, xl, xh, wxl, wxh)) continue;
-        atomicAdd(gin + yl * width + xl, go * (wyl * wxl) / count);
-        atomicAdd(gin + yl * width + xh, go * (wyl * wxh) / count);
-        atomicAdd(gin + yh * width + xl, go * (wyh * wxl) / count);
-        atomicAdd(gin + yh * width + xh, go * (wyh * wxh) / count);
+        atomicAdd(gin + yl * width + xl, go * (wyl * wxl));
+        atomicAdd(gin + yl * width + xh, go * (wyl * wxh));
+        atomicAdd(gin + yh * width + xl, go * (wyh * wxl));
+        atomicAdd(gin + yh * width + xh, go * (wyh * wxh));
       }
     }
   }
@@ -760,18 +879,55 @@ inline int roi_align_forward_run(const float* input, const float* rois, int num_
   return DANA_OK;
 }
 
+inline int64_t roi_align_backward_workspace(int num_rois, int batch, int channels, int height, int width, int pooled_h,
+                                            int pooled_w, int layout) {
+  if (layout != 0 || pooled_h != 7 || pooled_w != 7 || channels % 4 != 0) return 256;
+  return 4LL * num_rois * channels * 49 + 256 + 4LL * batch * channels * height * width + 256;
+}
+
+// layout 0: grad_out [R][C][ph][pw], grad_input [B][C][H][W] (the reference's operator); 1: [R][ph*pw][C] / [B][H][W][C].
 inline int roi_align_backward_run(const float* grad_out, const float* rois, int num_rois, int batch, int channels,
                                   int height, int width, int pooled_h, int pooled_w, float spatial_scale,
-                                  int sampling_ratio, float* grad_input, cudaStream_t stream) {
-  if (!grad_input || batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return DANA_EINVAL;
-  DANA_CUDA_CHECK(cudaMemsetAsync(grad_input, 0, 4LL * batch * channels * height * width, stream));
-  if (num_rois == 0) return DANA_OK;
-  if (!grad_out || !rois) return DANA_EINVAL;
-  const long long nthreads = static_cast<long long>(num_rois) * channels * pooled_h * pooled_w;
-  const int tb = 256;
-  const long long blocks = (nthreads + tb - 1) / tb;
-  roi_align_bwd_kernel<<<static_cast<int>(blocks > 148 * 32 ? 148 * 32 : blocks), tb, 0, stream>>>(
-      grad_out, rois, nthreads, channels, height, width, pooled_h, pooled_w, spatial_scale, sampling_ratio, grad_input);
+                                  int sampling_ratio, int layout, float* grad_input, void* workspace,
+                                  int64_t workspace_bytes, cudaStream_t stream) {
+  if (!grad_input || batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || (layout != 0 && layout != 1)) return DANA_EINVAL;
+  const int64_t map_bytes = 4LL * batch * channels * height * width;
+  const bool fast = pooled_h == 7 && pooled_w == 7 && channels % 4 == 0;
+  if (layout == 1 && !fast) return DANA_ENOTSUP;
+  if (num_rois == 0) {
+    DANA_CUDA_CHECK(cudaMemsetAsync(grad_input, 0, map_bytes, stream));
+    return DANA_OK;
+  }
+  if (!grad_out || !rois || num_rois < 0) return DANA_EINVAL;
+  if (!fast) {
+    DANA_CUDA_CHECK(cudaMemsetAsync(grad_input, 0, map_bytes, stream));
+    const long long nthreads = static_cast<long long>(num_rois) * channels * pooled_h * pooled_w;
+    const long long blocks = (nthreads + 255) / 256;
+    roi_align_bwd_generic_kernel<<<static_cast<int>(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, stream>>>(
+        grad_out, rois, nthreads, channels, height, width, pooled_h, pooled_w, spatial_scale, sampling_ratio, grad_input);
+    DANA_LAUNCH_CHECK();
+    return DANA_OK;
+  }
+  const float* go = grad_out;
+  float* gi = grad_input;
+  if (layout == 0) {
+    if (!workspace || workspace_bytes < roi_align_backward_workspace(num_rois, batch, channels, height, width, 7, 7, 0))
+      return DANA_EINVAL;
+    float* go_t = static_cast<float*>(workspace);
+    const int64_t off = (4LL * num_rois * channels * 49 + 255) / 256 * 256;
+    gi = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + off);
+    rc49_to_r49c_kernel<<<dim3(num_rois, (channels + 31) / 32), 256, 0, stream>>>(grad_out, go_t, channels);
+    go = go_t;
+  }
+  DANA_CUDA_CHECK(cudaMemsetAsync(gi, 0, map_bytes, stream));
+  const int groups = (channels + kRoi7Threads * 4 - 1) / (kRoi7Threads * 4);
+  roi_align7_bwd_kernel<<<dim3(num_rois, groups), kRoi7Threads, 0, stream>>>(go, rois, channels, height, width,
+                                                                            spatial_scale, sampling_ratio, gi);
+  if (layout == 0) {
+    const int hw = height * width;
+    nhwc_to_nchw_kernel<<<dim3((hw + 31) / 32, (channels + 31) / 32, batch), dim3(32, 8), 0, stream>>>(gi, grad_input,
+                                                                                                      channels, hw);
+  }
   DANA_LAUNCH_CHECK();
   return DANA_OK;
 }

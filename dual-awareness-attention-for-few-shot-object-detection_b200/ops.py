@@ -370,10 +370,26 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch, cha
     grad = grad.contiguous().float()
     rois = rois.contiguous().float()
     gin = torch.empty((batch, channels, height, width), dtype=torch.float32, device=grad.device)
-    _count(1)
-    check(_lib.load().dana_roi_align_backward(_p(grad), _p(rois), rois.shape[0], batch, channels, height, width,
-                                              pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), _p(gin),
-                                              _stream()), "dana_roi_align_backward")
+    lib = _lib.load()
+    wsb = lib.dana_roi_align_backward_workspace_bytes(rois.shape[0], batch, channels, height, width, pooled_h, pooled_w, 0)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=grad.device)
+    _count(4)                                                   # transposes in / out, memset, scatter
+    check(lib.dana_roi_align_backward(_p(grad), _p(rois), rois.shape[0], batch, channels, height, width,
+                                      pooled_h, pooled_w, float(spatial_scale), int(sampling_ratio), 0, _p(gin), _p(ws),
+                                      wsb, _stream()), "dana_roi_align_backward")
+    return gin
+
+
+def roi_align_backward_nhwc(grad_r49c, rois, spatial_scale, batch, height, width, sampling_ratio):
+    """Pipeline-layout backward of the 7x7 RoIAlign: grad [R,49,C] fp32 -> grad of the NHWC map [B,H,W,C] fp32."""
+    _need_cuda(grad_r49c, rois)
+    r, bins, c = grad_r49c.shape
+    assert bins == 49
+    gin = torch.empty((batch, height, width, c), dtype=torch.float32, device=grad_r49c.device)
+    _count(2)
+    check(_lib.load().dana_roi_align_backward(_p(grad_r49c.contiguous().float()), _p(rois.contiguous().float()), r, batch,
+                                              c, height, width, 7, 7, float(spatial_scale), int(sampling_ratio), 1,
+                                              _p(gin), None, 0, _stream()), "dana_roi_align_backward")
     return gin
 
 

@@ -98,10 +98,17 @@ int dana_roi_align_forward(const float* input, const float* rois, int num_rois, 
 int dana_roi_align_head(const float* feat_nhwc, const float* rois, int num_rois, int batch, int channels, int height,
                         int width, float spatial_scale, int sampling_ratio, float* out, void* out_hi, void* out_lo,
                         const float* pe, void* qpe_hi, void* qpe_lo, void* out_f16, void* stream);
-/* grad_input [B,C,H,W] fp32 is ZEROED by the call and then accumulated (NCHW only). */
+/* Backward.  layout 0: grad_out [R,C,ph,pw], grad_input [B,C,H,W] (the reference's operator, csrc/ROIAlign.h:29-45);
+ * layout 1: grad_out [R,ph*pw,C], grad_input [B,H,W,C] (pipeline layout, 7x7 bins only).  grad_input is ZEROED by the
+ * call and then accumulated with vector float reductions.  7x7 bins with channels % 4 == 0 run as the transpose of the
+ * separable forward on NHWC (layout 0 stages through `workspace`: dana_roi_align_backward_workspace_bytes(...) bytes,
+ * 256-byte aligned); other bin counts take a per-element scatter (layout 0 only, no workspace needed). */
+int64_t dana_roi_align_backward_workspace_bytes(int num_rois, int batch, int channels, int height, int width,
+                                                int pooled_h, int pooled_w, int layout);
 int dana_roi_align_backward(const float* grad_out, const float* rois, int num_rois, int batch, int channels,
                             int height, int width, int pooled_h, int pooled_w, float spatial_scale,
-                            int sampling_ratio, float* grad_input, void* stream);
+                            int sampling_ratio, int layout, float* grad_input, void* workspace, int64_t workspace_bytes,
+                            void* stream);
 
 /* ------------------------------------------------------------------------
  * Episode construction -- replaces, on the device, the per-image host work of

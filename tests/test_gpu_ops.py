@@ -123,6 +123,34 @@ def test_roi_align_backward_vs_autograd(ops):
     assert relerr(got, f.grad) <= 1e-4
 
 
+@pytest.mark.parametrize("b,c,h,w,ratio", [(2, 64, 38, 63, 0), (1, 1024, 20, 31, 0), (2, 8, 9, 11, 2), (1, 516, 5, 3, 0)])
+def test_roi_align_backward_layouts_vs_autograd(ops, b, c, h, w, ratio):
+    """Backward of the 7x7 RoIAlign as the transpose of the separable forward (NHWC, 16-byte vector reductions), both
+    layouts, RoIs from sub-pixel to larger than the map (per-sample path), against fp64 autograd of torchvision's
+    roi_align, which implements the same sampling rules (aligned=False).  The reference has NO CPU backward
+    (csrc/ROIAlign.h:44 raises), so there is no reference-derived golden for this operator: its CUDA kernel
+    (ROIAlign_cuda.cu:178-254) is the adjoint of the forward, which is what autograd differentiates."""
+    import torchvision
+    rs = np.random.RandomState(b * 7 + c)
+    feat = torch.from_numpy(rs.standard_normal((b, c, h, w))).cuda()
+    r = 60
+    iw, ih = w * 16.0, h * 16.0
+    x1, y1 = rs.uniform(-0.1 * iw, iw, r), rs.uniform(-0.1 * ih, ih, r)
+    ww = np.exp(rs.uniform(np.log(0.5), np.log(2.5 * iw), r))
+    hh = np.exp(rs.uniform(np.log(0.5), np.log(2.5 * ih), r))
+    rois = torch.from_numpy(np.stack([rs.randint(0, b, r).astype(np.float64), x1, y1, x1 + ww, y1 + hh], 1)).cuda()
+    f = feat.clone().requires_grad_(True)
+    o = torchvision.ops.roi_align(f, rois, (7, 7), 1.0 / 16, ratio, False)
+    go = torch.randn_like(o)
+    o.backward(go)
+    got = ops.roi_align_backward(go.float(), rois.float(), 1.0 / 16, 7, 7, b, c, h, w, ratio)
+    assert relerr(got, f.grad) <= 1e-4
+    if c % 4 == 0:
+        g_nhwc = ops.roi_align_backward_nhwc(go.float().reshape(r, c, 49).transpose(1, 2).contiguous(), rois.float(),
+                                             1.0 / 16, b, h, w, ratio)
+        assert relerr(g_nhwc.permute(0, 3, 1, 2), f.grad) <= 1e-4
+
+
 # ------------------------------------------------------------------------------------ proposals
 def test_proposals_golden(ops, golden_dir):
     prob, bbox, im_info = MG.proposal_case()

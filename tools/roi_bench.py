@@ -81,6 +81,7 @@ if a.only:
     fn = {"nchw": lambda: ops.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 0),
           "pair": lambda: ops.roi_align_nhwc(nhwc, rois, 1.0 / 16, 7, 0, want_f32=False, want_pair=True),
           "head": lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, pe=pe, want_f32=False, want_pair=True, want_qpe=True),
+          "head16": lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, want_f32=False, want_pair=True, want_f16=True),
           "f32": lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, want_f32=True, want_pair=False, want_qpe=False)}[a.only]
     print("%s: %.4f ms" % (a.only, timeit(fn)))
     sys.exit(0)
@@ -96,6 +97,13 @@ ms = timeit(lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, pe=pe, want_f32=
 pb2 = 4 * 2.0 * r * c * 49 + 4.0 * c * h * w * b
 print("roi_align_head NHWC -> pooled pair + (pooled+PE) pair:              %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
       (ms, pb2 / ms / 1e6, pb2 / 1e6))
+ms = timeit(lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, want_f32=False, want_pair=True, want_f16=True))
+pb3 = (4 + 2) * 1.0 * r * c * 49 + 4.0 * c * h * w * b
+print("roi_align_head NHWC -> pooled pair + fp16 plane (the mixed-mode step): %.4f ms  %.0f GB/s algorithmic (%.1f MB)  %.1f %% of HBM peak" %
+      (ms, pb3 / ms / 1e6, pb3 / 1e6, 100 * pb3 / ms / 1e6 / peak))
+g49 = torch.randn(r, 49, c, device="cuda")
+ms = timeit(lambda: ops.roi_align_backward_nhwc(g49, rois, 1.0 / 16, b, h, w, 0))
+print("roi_align backward NHWC (vector reductions, incl. the map memset):  %.4f ms  (reads %.1f MB of gradient)" % (ms, 4.0 * r * c * 49 / 1e6))
 ms = timeit(lambda: ops.roi_align_head(nhwc, rois, 1.0 / 16, 0, want_f32=True, want_pair=False, want_qpe=False))
 print("roi_align_head NHWC -> fp32 [R,7,7,C]:                              %.4f ms  %.0f GB/s algorithmic (%.1f MB)" %
       (ms, alg_bytes / ms / 1e6, alg_bytes / 1e6))
