@@ -53,6 +53,7 @@ struct ConvGemmParams {
   int a_prefetch;       // producer prefetches the next tile's activation boxes into L2
   int ab_f16;           // operands are IEEE fp16 planes (kind::f16 with F16 formats) instead of bf16
   int dx_box_bytes;     // DX3: bytes of one window box per plane, bw * (bh + 2) rows of the K-tile
+  int res_cross;        // epilogue: load the next tile's first residual chunk during this tile's last chunk
 };
 
 constexpr int kGemmThreads = 320;
@@ -442,6 +443,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     int staged_co = -1, staged_n = -1;
+    // residual look-ahead registers; they live across tiles: the loads of a tile's FIRST chunk are issued while the
+    // previous tile's last chunk is processed (pre_valid), so that no chunk meets its residual with zero lead -- with
+    // one or two chunks per warp and tile that was every chunk / every other chunk (ncu: long_scoreboard on the first
+    // use of the residual words was the top stall of the residual layers)
+    uint4 rh[4], rl[4];
+    bool pre_valid = false;
+    const bool cross_tile = (p.res_cross != 0);
     SkRange rng = my_range();
     int wk = cluster_id - num_clusters, kb_lo = 0, kb_hi = num_kb;
     while (stream_k ? rng.next(wk, kb_lo, kb_hi) : ((wk += num_clusters) < num_work)) {
@@ -520,6 +528,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       ty0 = __shfl_sync(0xffffffffu, ty0, 0);
       tn0 = __shfl_sync(0xffffffffu, tn0, 0);
       const int co0 = co_t * BLOCK_N;
+      bool have_next = false;                       // next work item of this CTA (FAST + residual + whole-tile schedule)
+      int n_co = 0, n_x0 = 0, n_y0 = 0, n_n0 = 0;
       if constexpr (FAST) {
         // Residual stream: the layers that carry a residual are the HBM-bound ones (K = 64..512), and their
         // epilogue stalled on the residual loads (ncu: long_scoreboard on the first use of the prefetched words --
@@ -529,6 +539,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const int wn = wk + num_clusters;
           if (wn < num_work) {
             int nco = 0, nx0 = 0, ny0 = 0, nn0 = 0;
+            have_next = true;
             if (lane == 0) {
               const int mg = p.n_fast ? wn / p.tiles_co : wn % m_groups;
               nco = p.n_fast ? wn - mg * p.tiles_co : wn / m_groups;
@@ -545,6 +556,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             nx0 = __shfl_sync(0xffffffffu, nx0, 0);
             ny0 = __shfl_sync(0xffffffffu, ny0, 0);
             nn0 = __shfl_sync(0xffffffffu, nn0, 0);
+            n_co = nco; n_x0 = nx0; n_y0 = ny0; n_n0 = nn0;
             const int m = et >> 1;
             const int x = nx0 + (m & (p.bw - 1));
             const int y = ny0 + ((m >> p.lbw) & (p.bh - 1));
@@ -590,7 +602,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           ohp[i] = p.out_hi + o_off[i] + co0 + c_begin * 32 + cg;
         }
       }
-      uint4 rh[4], rl[4];
       auto prefetch = [&](int c) {
         if constexpr (FAST) {
           if (res_pair && co0 + c * 32 < p.n_out) {
@@ -616,7 +627,28 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
       };
-      if (c_begin < kChunks) prefetch(c_begin);
+      if (c_begin < kChunks && !pre_valid) prefetch(c_begin);
+      pre_valid = false;
+      // next tile's first chunk of this warp (issued from the last chunk of this tile, see above)
+      auto prefetch_next = [&]() {
+        if constexpr (FAST) {
+          if (!(cross_tile && have_next && res_pair) || n_co * BLOCK_N + c_begin * 32 >= p.n_out || c_begin >= kChunks) return;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = q * 32 + 8 * i + sub;
+            const int x = n_x0 + (m & (p.bw - 1));
+            const int y = n_y0 + ((m >> p.lbw) & (p.bh - 1));
+            const int n = n_n0 + (m >> (p.lbw + p.lbh));
+            if (x < p.out_w && y < p.out_h && n < p.out_n) {
+              const __nv_bfloat16* rp = p.res_hi + static_cast<long long>(n) * p.sr_n + static_cast<long long>(y) * p.sr_y +
+                                        static_cast<long long>(x) * p.sr_x + n_co * BLOCK_N + c_begin * 32 + cg;
+              rh[i] = __ldg(reinterpret_cast<const uint4*>(rp));
+              if (OUT2) rl[i] = __ldg(reinterpret_cast<const uint4*>(rp + d_res));
+            }
+          }
+          pre_valid = true;
+        }
+      };
 
       // stage per-channel scale (x alpha) / bias -- only when the N-tile (or, with per-image bias, the image)
       // changes, which with N-major tile order is once or twice per CTA
@@ -880,7 +912,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           ch[i] = rh[i];
           cl[i] = rl[i];
         }
-        if (ci + 1 < kCpw && c + 1 < kChunks) prefetch(c + 1);
+        if (ci + 1 < kCpw && c + 1 < kChunks && co0 + (c + 1) * 32 < p.n_out) {
+          prefetch(c + 1);
+        } else {
+          prefetch_next();
+        }
         tmem_ld_wait();
         for (int cc = sk_first; cc < sk_last; ++cc) {   // stream-K: add the partial sums of the tile's head
           const float* src = p.sk_partials + static_cast<long long>(cc) * (128 * BLOCK_N) + (c * 4 + q) * 1024 + lane;

@@ -224,6 +224,17 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   p.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);
   p.out_f32 = a->out_f32;
   p.ab_f16 = a->ab_f16 ? 1 : 0;
+  {
+    // cross-tile residual look-ahead (conv_gemm.cuh, epilogue).  Measured (round 2, tools/gemm_bench.py): no gain --
+    // layer1 conv3+res 0.0946 ms with it, 0.0920 without; the step 701.6 vs 706.1 images/s -- so it is an opt-in
+    // (DANA_RES_CROSS=1): the residual stall ncu shows is not a matter of issue distance within one warp
+    static int rc = -1;
+    if (rc < 0) {
+      const char* env = getenv("DANA_RES_CROSS");
+      rc = (env != nullptr && atoi(env) == 1) ? 1 : 0;
+    }
+    p.res_cross = rc;
+  }
 
   // BLOCK_N: the widest tile that the output fills (wide tiles read A once per 256 columns and keep the MMA off the
   // shared-memory read limit); wave quantisation is handled by stream-K below, not by shrinking tiles
