@@ -472,19 +472,19 @@ __global__ void support_rbar_kernel(const float* __restrict__ r, int sets, int s
 // Mean-centering over groups of rows (q/k projections, dana.py:125,141,267,272) -> bf16 pair.
 // grid (groups, ceil(c/128)), block 128: thread per column, two passes over the group's rows.
 // ---------------------------------------------------------------------------------------------
-__global__ void center_rows_kernel(const float* __restrict__ in, int group_rows, int c, __nv_bfloat16* __restrict__ hi,
-                                   __nv_bfloat16* __restrict__ lo) {
+// (in_pitch: elements between input rows -- the input may be a column slice of a wider matrix; the output is dense)
+__global__ void center_rows_kernel(const float* __restrict__ in, long long in_pitch, int group_rows, int c,
+                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int g = blockIdx.x;
   const int ch = blockIdx.y * blockDim.x + threadIdx.x;
   if (ch >= c) return;
-  const long long base = static_cast<long long>(g) * group_rows * c + ch;
+  const long long ibase = static_cast<long long>(g) * group_rows * in_pitch + ch;
+  const long long obase = static_cast<long long>(g) * group_rows * c + ch;
   float s = 0.0f;
-  for (int r = 0; r < group_rows; ++r) s += in[base + static_cast<long long>(r) * c];
+  for (int r = 0; r < group_rows; ++r) s += in[ibase + static_cast<long long>(r) * in_pitch];
   const float mean = s / static_cast<float>(group_rows);
-  for (int r = 0; r < group_rows; ++r) {
-    const long long o = base + static_cast<long long>(r) * c;
-    st_pair(hi, lo, o, in[o] - mean);
-  }
+  for (int r = 0; r < group_rows; ++r)
+    st_pair(hi, lo, obase + static_cast<long long>(r) * c, in[ibase + static_cast<long long>(r) * in_pitch] - mean);
 }
 // large groups (RPN level, thousands of rows): per-block partial column sums, combined in a fixed order (no float
 // atomics: the forward is bit-reproducible run to run), then subtract

@@ -159,6 +159,9 @@ class DanaEngine:
         pe49 = positional_encoding(49).double()
         self.pe_q = (pe49 @ sd["rcnn_adapt_q_layer.weight"].double().cpu().t()).float().to(dev).contiguous()
         self.pe_t = (pe49 @ wt[:, :1024].double().cpu().t() + self.tr_b.double().cpu()).float().to(dev).contiguous()
+        # both projections read the same [R*49, 1024] pooled rows: ONE GEMM with the 256 + 64 output columns side by side
+        self.head_qt_w = Pair.from_float(torch.cat([f32(sd["rcnn_adapt_q_layer.weight"]), wt[:, :1024]], 0).contiguous(), split)
+        self.pe_qt = torch.cat([self.pe_q, self.pe_t], 1).contiguous()
         self.ffn1_w, self.ffn1_b = lin("output_score_layer.linear1")
         self.ffn2_w, self.ffn2_b = lin("output_score_layer.linear2")
         self.bbox_w, self.bbox_b = lin("RCNN_bbox_pred")
@@ -401,18 +404,12 @@ class DanaEngine:
             sup = ops.split_f32(teacher["support_feat"].reshape(maps, c, sh, sw).permute(0, 2, 3, 1).contiguous(), split)
 
         self._mark("trunk")
-        # Two branches from here: the head's support side needs only the support maps, the RPN-level attention /
-        # RPN conv / proposal layer only the query side -- the former (a dozen small launches) runs on a side stream
-        # under the latter (captured as parallel branches of the CUDA graph).  Single stream while bench.py's
-        # instrumented step records per-launch / per-stage events, or with DANA_SIDE_STREAM=0.
+        # The head's support side needs only the support maps.  Its dozen small launches (low occupancy: 24 maps) run on
+        # a side stream UNDER the proposal layer's sort + NMS (one CTA per image, 0.27 ms with 144 SMs idle) -- the fork
+        # is placed right before that stage (captured as parallel branches of the CUDA graph).  Single stream while
+        # bench.py's instrumented step records per-launch / per-stage events, or with DANA_SIDE_STREAM=0.
         head_sup, side = None, None
-        if self.stage_events is None and ops.GEMM_TRACE is None and os.environ.get("DANA_SIDE_STREAM", "1") != "0":
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=dev)
-            side = self._side
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                head_sup = self._head_support_side(sup, b, sets, pooling_size, want, extra)
+        use_side = self.stage_events is None and ops.GEMM_TRACE is None and os.environ.get("DANA_SIDE_STREAM", "1") != "0"
         if self.f16:
             base2d = base.view(b * nq, 1024)
         else:
@@ -448,6 +445,13 @@ class DanaEngine:
         rpn_raw = torch.empty((b, qh, qw, 6 * self.num_a), dtype=torch.float32, device=dev)
         ops.conv_nhwc(r1, self.rpn_out.w, 6 * self.num_a, ksize=1, bias=self.rpn_out.bias, out_f32=rpn_raw)
         fg, deltas = ops.rpn_fg_prob(rpn_raw, self.num_a)
+        if use_side:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                head_sup = self._head_support_side(sup, b, sets, pooling_size, want, extra)
         if "rpn_fg" in want:
             extra["rpn_fg"], extra["rpn_deltas"] = fg, deltas
         if teacher and "rpn_fg" in teacher:
@@ -505,12 +509,13 @@ class DanaEngine:
         kc_h, zt, c64 = head_sup
         # query side: the positional encoding of :259 enters as the per-bin bias PE W^T of the two projections
         pooled2d = pooled.view(r * bins, c)
-        q_h = torch.empty((r * bins, 256), dtype=torch.float32, device=dev)
-        t_q = torch.empty((r * bins, 64), dtype=torch.float32, device=dev)
         if bins == 49:
-            ops.linear(pooled2d, self.rcnn_q_w, 256, out_f32=q_h, row_bias=self.pe_q)          # :259,266
-            ops.linear(pooled2d, self.tr_wq, 64, out_f32=t_q, row_bias=self.pe_t)             # query half of :288
+            qt = torch.empty((r * bins, 320), dtype=torch.float32, device=dev)
+            ops.linear(pooled2d, self.head_qt_w, 320, out_f32=qt, row_bias=self.pe_qt)        # :259,266 and query half of :288
+            q_h, t_q = qt[:, :256], qt[:, 256:]
         else:
+            q_h = torch.empty((r * bins, 256), dtype=torch.float32, device=dev)
+            t_q = torch.empty((r * bins, 64), dtype=torch.float32, device=dev)
             qpe = Pair.empty((r * bins, c), dev, split)
             ops.add_pe_split(pooled_f32 if pooled_f32 is not None else ops.merge_pair(pooled), self.pe(bins), bins, qpe, c)
             ops.linear(qpe, self.rcnn_q_w, 256, out_f32=q_h)

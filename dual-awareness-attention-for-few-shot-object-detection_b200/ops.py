@@ -530,9 +530,16 @@ def transpose_segments(x_f32, shots, seg_pitch, vt_pitch, split=True):
 
 
 def center_rows(x_f32, groups, group_rows, split=True):
+    """x - mean over the rows of each group (dana.py:125,141,267,272) -> pair.  x may be a column slice of a wider
+    fp32 matrix (row pitch > columns) when the groups are small (the head: 49 rows)."""
     c = x_f32.shape[-1]
     dev = x_f32.device
     out = Pair.empty((groups * group_rows, c), dev, split=split)
+    if x_f32.dim() == 2 and x_f32.stride(0) != c:
+        _count(1)
+        check(_lib.load().dana_center_rows_pitched(_p(x_f32), x_f32.stride(0), groups, group_rows, c, _p(out.hi),
+                                                   _p(out.lo), _stream()), "dana_center_rows_pitched")
+        return out
     # scratch of the large-group path: final column sums + per-block partial sums (fixed-order reduction, no atomics)
     sums = torch.empty((groups * (1 + (group_rows + 63) // 64), c), dtype=torch.float32, device=dev) if group_rows > 256 else None
     _count(3 if group_rows > 256 else 1)

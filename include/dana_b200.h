@@ -256,6 +256,9 @@ int dana_support_prepare(const void* in_hi, const void* in_lo, const float* in_f
  * reduced in a fixed order, no float atomics: results are bit-reproducible); may be NULL for small groups. */
 int dana_center_rows(const float* in, int groups, int group_rows, int c, void* out_hi, void* out_lo, float* sums,
                      void* stream);
+/* Same for an input whose rows are in_pitch elements apart (a column slice of a wider matrix); group_rows <= 256. */
+int dana_center_rows_pitched(const float* in, int64_t in_pitch, int groups, int group_rows, int c, void* out_hi,
+                             void* out_lo, void* stream);
 /* F.softmax(logits, dim=2) per shot segment (dana.py:143,274) -> pair, pad columns zeroed. */
 int dana_attn_softmax(const float* logits, int64_t rows, int segs, int ns, int pitch, void* p_hi, void* p_lo,
                       void* stream);
