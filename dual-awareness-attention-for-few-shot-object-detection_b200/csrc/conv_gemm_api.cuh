@@ -110,6 +110,9 @@ inline int launch_conv_gemm(const ConvGemmParams& p, int grid, cudaStream_t stre
     if constexpr (CM == 1 && KT == 64 && (NSPLIT == 1 || BLOCK_N <= 128)) {
       if (p.sm_ns == 0 && fast_epilogue_ok(p, NSPLIT, true)) return launch_conv_gemm_v<BLOCK_N, NSPLIT, 3, 1>(p, grid, stream);
     }
+    if constexpr (CM == 2 && KT == 64 && NSPLIT == 1 && BLOCK_N == 256) {   // experiment: DANA_CLUSTER=4 (fp16 planes)
+      if (p.sm_ns == 0 && fast_epilogue_ok(p, NSPLIT, true)) return launch_conv_gemm_v<256, 1, 3, 2>(p, grid, stream);
+    }
     return DANA_ENOTSUP;
   }
   if constexpr (KT == 32) {   // only the plain-epilogue, non-cluster variants are instantiated at KT = 32
@@ -276,6 +279,11 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     // bandwidth -- so the multicast path is opt-in (DANA_CLUSTER=2) and stream-K below is the default remedy
     const char* env = getenv("DANA_CLUSTER");
     if (env != nullptr && atoi(env) == 2 && block_n == 256 && !batched && !io_f16 && k_total_ >= 256 && sp_tiles >= 2) cm = 2;
+    // experiment (DANA_CLUSTER=4): the fp16-plane layers issue a third of the MMAs per operand byte, so their weight
+    // re-streaming weighs more: CTA pairs multicasting the weight tile
+    if (env != nullptr && atoi(env) == 4 && block_n == 256 && nsplit_ == 1 && io_f16 && !batched && !softmax && k_total_ >= 256 &&
+        sp_tiles >= 2)
+      cm = 2;
     // experiment (DANA_CLUSTER=3): the 3x3 convolutions of the 64 / 128-channel stages re-stream their weights for every
     // 128-pixel tile and are bound by L2 -> SM traffic; a CTA pair sharing the weight tile halves that half of it
     if (env != nullptr && atoi(env) == 3 && nsplit_ == 2 && block_n <= 128 && taps == 9 && !batched && !io_f16 && !softmax &&

@@ -21,10 +21,12 @@ CASES = [  # (layers, batch, H, W, sets, shots, support_size)
     (50, 2, 375, 500, 2, 3, 224),
     (50, 1, 1000, 600, 3, 2, 320),
     (101, 1, 608, 1008, 2, 5, 256),
+    (50, 1, 333, 517, 2, 3, 200),      # nothing divides anything
+    (50, 2, 600, 1000, 1, 3, 288),     # 18x18 supports: Ns = 324 (wide softmax tile, odd half width)
 ]
 for layers, b, h, w, sets, k, ss in CASES:
     sd = synthetic_state_dict(1996, num_layers=layers)
-    for prec in ("bf16x3", "bf16"):
+    for prec in ("mixed", "bf16x3", "bf16"):
         eng = DanaEngine(sd, num_layers=layers, n_shot=k, precision=prec)
         im, info, sup = synthetic_episode(5, b, h, w, sets * k, support_size=ss)
         im, info, sup = im.cuda(), info.cuda(), sup.cuda()
