@@ -90,6 +90,9 @@ SIGNATURES = {
     "dana_rpn_losses": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_void_p]),
     "dana_rcnn_losses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dana_group_mean": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    "dana_depthwise_xcorr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
     "dana_cisa_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "dana_cisa_fwd": (c_int, [POINTER(CisaArgs), c_void_p]),
     "dana_stem_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -6,6 +6,7 @@
 //   smooth-L1    lib/model/utils/net_utils.py:71-85
 #pragma once
 #include "api_common.cuh"
+#include "tc_common.cuh"
 
 namespace dana {
 
@@ -170,6 +171,67 @@ rcnn_loss_kernel(const float* __restrict__ scores, const float* __restrict__ lab
     const int cnt = nfg + t0 + t1;
     out[0] = static_cast<float>(cnt > 0 ? (ce_fg + ce_bg) / cnt : 0.0);
     out[1] = static_cast<float>(box_sum / static_cast<double>(r));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sibling model FSOD: the attention-RPN feature of lib/model/framework/fsod.py:96-112 --
+// shot-mean of the support maps, AvgPool2d(14) to a 7x7 kernel per channel, depth-wise cross-correlation of the query
+// feature with it: F.conv2d(feat [1,C,h,w], kernel [C,1,7,7], groups=C) -> [C, h-6, w-6] (no padding).
+// NHWC: thread = (output pixel, 4 channels); the kh*kw taps of a pixel are 16-byte pair loads that neighbouring
+// pixels share through L1, the per-image kernel (kh*kw*C fp32) is read through the read-only path.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+depthwise_xcorr_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int batch, int h, int w,
+                       int c, const float* __restrict__ kern /*[B][kh*kw][C]*/, int kh, int kw, float* __restrict__ out,
+                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  const int oh = h - kh + 1, ow = w - kw + 1, cg = c >> 2;
+  const long long total = static_cast<long long>(batch) * oh * ow * cg;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % cg) * 4;
+    long long t = i / cg;
+    const int x = static_cast<int>(t % ow);
+    t /= ow;
+    const int y = static_cast<int>(t % oh);
+    const int b = static_cast<int>(t / oh);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* kb = kern + static_cast<long long>(b) * kh * kw * c + c0;
+    for (int dy = 0; dy < kh; ++dy) {
+      const long long row = ((static_cast<long long>(b) * h + y + dy) * w + x) * c + c0;
+      for (int dx = 0; dx < kw; ++dx) {
+        const uint2 ph = __ldg(reinterpret_cast<const uint2*>(hi + row + static_cast<long long>(dx) * c));
+        float f0 = __uint_as_float(ph.x << 16), f1 = __uint_as_float(ph.x & 0xFFFF0000u);
+        float f2 = __uint_as_float(ph.y << 16), f3 = __uint_as_float(ph.y & 0xFFFF0000u);
+        if (lo != nullptr) {
+          const uint2 pl = __ldg(reinterpret_cast<const uint2*>(lo + row + static_cast<long long>(dx) * c));
+          f0 += __uint_as_float(pl.x << 16); f1 += __uint_as_float(pl.x & 0xFFFF0000u);
+          f2 += __uint_as_float(pl.y << 16); f3 += __uint_as_float(pl.y & 0xFFFF0000u);
+        }
+        const float4 k4 = __ldg(reinterpret_cast<const float4*>(kb + static_cast<long long>(dy * kw + dx) * c));
+        a0 = fmaf(f0, k4.x, a0); a1 = fmaf(f1, k4.y, a1); a2 = fmaf(f2, k4.z, a2); a3 = fmaf(f3, k4.w, a3);
+      }
+    }
+    const long long o = ((static_cast<long long>(b) * oh + y) * ow + x) * c + c0;
+    if (out != nullptr) *reinterpret_cast<float4*>(out + o) = make_float4(a0, a1, a2, a3);
+    if (out_hi != nullptr) {
+      __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+      split_bf16(a0, h0, l0); split_bf16(a1, h1, l1); split_bf16(a2, h2, l2); split_bf16(a3, h3, l3);
+      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      if (out_lo != nullptr) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+  }
+}
+
+// out[g][i] = mean_k in[g*k + j][i]   (support_feats[:, :n_shot].mean(1), fsod.py:96,103)
+__global__ void group_mean_kernel(const float* __restrict__ in, int groups, int k, long long n, float* __restrict__ out) {
+  const long long total = static_cast<long long>(groups) * n;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long g = i / n, e = i - g * n;
+    float s = 0.0f;
+    for (int j = 0; j < k; ++j) s += in[(g * k + j) * n + e];
+    out[i] = s / static_cast<float>(k);
   }
 }
 

@@ -344,6 +344,22 @@ class DanaEngine:
         ops.linear(cbar, self.tr_wd, 64, out_f32=c64)
         return kc_h, zt, c64
 
+    # ------------------------------------------------------------------ sibling model FSOD
+    @torch.no_grad()
+    def fsod_attention_feature(self, im_data, support_ims):
+        """The attention-RPN input of the sibling model FSOD (lib/model/framework/fsod.py:90-112) on this engine's
+        trunk: shot-mean of the positive support maps, AvgPool2d(14) -> a 7x7 kernel per channel, depth-wise
+        cross-correlation with the query feature.  im_data [B,3,H,W], support_ims [B,K,3,Hs,Ws] -> NCHW fp32
+        [B,1024,h-6,w-6] (what fsod.py feeds to RCNN_rpn).  Only this block of FSOD is built."""
+        k = self.n_shot
+        base = self.trunk(im_data.float().contiguous())
+        sup = self.encode_supports(support_ims[:, :k])
+        maps, sh, sw, c = sup.hi.shape
+        pooled = ops.avgpool(sup, sh - 6)                              # [B*K,7,7,C]  (linear: commutes with the shot mean)
+        kern = ops.group_mean(pooled, k)                               # [B,7,7,C]
+        heat, _ = ops.depthwise_xcorr(base, kern, want_f32=True)
+        return heat.permute(0, 3, 1, 2)
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def encode_supports(self, support_ims):

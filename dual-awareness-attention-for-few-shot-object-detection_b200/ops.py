@@ -666,5 +666,34 @@ def rcnn_losses(cls_scores, labels, bbox_pred, bbox_targets, inside_w, outside_w
     return out
 
 
+# --------------------------------------------------------------------------- sibling model FSOD: attention-RPN feature
+def group_mean(x_f32, k):
+    """[groups*k, ...] fp32 -> [groups, ...]: mean over consecutive groups of k (fsod.py:96,103)."""
+    _need_cuda(x_f32)
+    groups = x_f32.shape[0] // k
+    n = x_f32[0].numel()
+    out = torch.empty((groups,) + tuple(x_f32.shape[1:]), dtype=torch.float32, device=x_f32.device)
+    _count(1)
+    check(_lib.load().dana_group_mean(_p(x_f32.contiguous()), groups, k, n, _p(out), _stream()), "dana_group_mean")
+    return out
+
+
+def depthwise_xcorr(x: Pair, kernel_f32, *, want_f32=True, want_pair=False, split=True):
+    """x [B,h,w,C] pair, kernel [B,kh,kw,C] fp32 -> [B,h-kh+1,w-kw+1,C] (fsod.py:106-112).  Returns (f32, pair)."""
+    _need_cuda(x.hi, kernel_f32)
+    b, h, w, c = x.hi.shape
+    kb, kh, kw, kc = kernel_f32.shape
+    assert kb == b and kc == c and x.hi.is_contiguous()
+    dev = x.hi.device
+    out = torch.empty((b, h - kh + 1, w - kw + 1, c), dtype=torch.float32, device=dev) if want_f32 else None
+    pair = Pair.empty((b, h - kh + 1, w - kw + 1, c), dev, split=split) if want_pair else None
+    _count(1)
+    check(_lib.load().dana_depthwise_xcorr(_p(x.hi), _p(x.lo), b, h, w, c, _p(kernel_f32.contiguous()), kh, kw, _p(out),
+                                           _p(pair.hi) if pair else None,
+                                           _p(pair.lo) if (pair and pair.lo is not None) else None, _stream()),
+          "dana_depthwise_xcorr")
+    return out, pair
+
+
 def device_error():
     return _lib.load().dana_device_error()

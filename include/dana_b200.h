@@ -305,6 +305,15 @@ int dana_rcnn_losses(const float* cls_scores, const float* labels, int rois, con
                      const float* bbox_targets, const float* inside_w, const float* outside_w, float* losses,
                      void* stream);
 
+/* ------------------------------------------------------------------------
+ * Sibling model FSOD, the attention-RPN feature of lib/model/framework/fsod.py:96-112:
+ * dana_group_mean     support_feats[:, :n_shot].mean(1) on fp32 [groups*k][n] -> [groups][n]
+ * dana_depthwise_xcorr  F.conv2d(feat, kernel.view(C,1,kh,kw), groups=C), no padding: NHWC pair [B,h,w,C] and a
+ *                     per-image kernel fp32 [B][kh*kw][C] -> [B,h-kh+1,w-kw+1,C] as fp32 (out) and / or bf16 pair. */
+int dana_group_mean(const float* in, int groups, int k, int64_t n, float* out, void* stream);
+int dana_depthwise_xcorr(const void* in_hi, const void* in_lo, int batch, int h, int w, int c, const float* kernel,
+                         int kh, int kw, float* out, void* out_hi, void* out_lo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -475,3 +475,22 @@ def test_fused_softmax_wide_segments(ops, split, rows, ns, shots, batch):
         assert relerr(seg, ref) <= (3e-5 if split else 8e-3)
         assert (got[:, :, s * sp + ns:(s + 1) * sp] == 0).all()
     assert (got[:, :, shots * sp:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------ sibling model FSOD (8f rank 4)
+@pytest.mark.parametrize("b,h,w,c,split", [(2, 20, 31, 64, True), (1, 38, 63, 1024, True), (3, 7, 9, 8, False)])
+def test_depthwise_xcorr_vs_torch(ops, b, h, w, c, split):
+    """F.conv2d(feat, kernel, groups=C) with a per-image 7x7 kernel (fsod.py:106-112), NHWC, against torch fp64."""
+    torch.manual_seed(h * w)
+    x = torch.randn(b, h, w, c, device="cuda")
+    k = torch.randn(b, 7, 7, c, device="cuda") * 0.1
+    xp = ops.Pair.from_float(x, split)
+    out, pair = ops.depthwise_xcorr(xp, k, want_f32=True, want_pair=True, split=split)
+    xr = xp.float().double().permute(0, 3, 1, 2)
+    ref = torch.stack([torch.nn.functional.conv2d(xr[i:i + 1], k[i].double().permute(2, 0, 1).unsqueeze(1), groups=c)[0]
+                       for i in range(b)]).permute(0, 2, 3, 1)
+    assert tuple(out.shape) == (b, h - 6, w - 6, c)
+    assert relerr(out, ref) <= 2e-6
+    assert relerr(pair.float(), ref) <= (2e-5 if split else 6e-3)
+    m = ops.group_mean(torch.arange(24, dtype=torch.float32, device="cuda").view(6, 2, 2), 3)
+    assert torch.equal(m.cpu(), torch.arange(24, dtype=torch.float32).view(2, 3, 2, 2).mean(1))

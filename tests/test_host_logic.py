@@ -291,3 +291,43 @@ def test_target_layers_match_oracle(seed, n_gt, hw):
     np.testing.assert_allclose(g[2], w[2].numpy(), rtol=0, atol=2e-5)
     np.testing.assert_array_equal(g[3], w[3].numpy())
     np.testing.assert_array_equal(g[4], w[4].numpy())
+
+
+def test_pretrained_trunk_load(tmp_path):
+    """pretrained=True (dana.py:337-341): the caffe-converted resnet checkpoint (torchvision-style keys conv1 / bn1 /
+    layer1..4 / fc) is loaded into RCNN_base / RCNN_top; fc.* is ignored; a checkpoint lacking a trunk tensor is an error."""
+    import torch
+
+    import dana_b200  # noqa: F401
+    from dana_b200.config import cfg_from_file, reset_cfg
+    from dana_b200.dana import DAnARCNN
+    reset_cfg()
+    cfg_from_file(os.path.join(ROOT, "cfgs", "res50.yml"))
+    ref = DAnARCNN(["bg", "fg"], "concat", 256, 256, pretrained=False, semantic_enhance=True)
+    ref.create_architecture()
+    key_map = (("RCNN_base.0.", "conv1."), ("RCNN_base.1.", "bn1."), ("RCNN_base.4.", "layer1."),
+               ("RCNN_base.5.", "layer2."), ("RCNN_base.6.", "layer3."), ("RCNN_top.0.", "layer4."))
+    g = torch.Generator().manual_seed(3)
+    ckpt = {}
+    for k, v in ref.state_dict().items():
+        for src, dst in key_map:
+            if k.startswith(src) and not k.endswith("num_batches_tracked"):
+                ckpt[dst + k[len(src):]] = torch.randn(v.shape, generator=g)
+    ckpt["fc.weight"] = torch.zeros(1000, 2048)
+    ckpt["fc.bias"] = torch.zeros(1000)
+    path = str(tmp_path / "resnet50_caffe.pth")
+    torch.save(ckpt, path)
+    net = DAnARCNN(["bg", "fg"], "concat", 256, 256, pretrained=True, semantic_enhance=True)
+    net.model_path = path
+    net.create_architecture()
+    sd = net.state_dict()
+    assert torch.equal(sd["RCNN_base.0.weight"], ckpt["conv1.weight"])
+    assert torch.equal(sd["RCNN_base.6.5.bn3.running_var"], ckpt["layer3.5.bn3.running_var"])
+    assert torch.equal(sd["RCNN_top.0.2.conv3.weight"], ckpt["layer4.2.conv3.weight"])
+    assert not net.RCNN_base[0].weight.requires_grad and not net.RCNN_base[4][0].conv1.weight.requires_grad
+    del ckpt["layer2.0.conv1.weight"]
+    torch.save(ckpt, path)
+    bad = DAnARCNN(["bg", "fg"], "concat", 256, 256, pretrained=True)
+    bad.model_path = path
+    with pytest.raises(RuntimeError):
+        bad.create_architecture()

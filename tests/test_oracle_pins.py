@@ -125,6 +125,22 @@ def test_postprocess_vs_reference_NMS(golden_dir):
     np.testing.assert_array_equal(dets[keep.view(-1).long()].numpy(), g)
 
 
+def test_fsod_attention_feature_vs_reference(golden_dir):
+    """oracle/fsod_oracle.py (sibling model FSOD's attention-RPN feature, fsod.py:90-112) against the UNMODIFIED
+    reference FSOD module (oracle/make_golden_fsod.py hooks the input of its RPN)."""
+    import fsod_oracle as FO
+    import make_golden_fsod as MF
+    g = _g(golden_dir, "fsod_attention.npz")
+    fc = MF.FSOD_CASE
+    p = O.make_params(fc["seed"])
+    im, info, sup = O.synth_inputs(fc["input_seed"], 1, fc["height"], fc["width"], fc["n_shot"])
+    with torch.no_grad():
+        corr = FO.fsod_attention_feature(p, im, sup, fc["n_shot"])
+    assert tuple(corr.shape) == tuple(g["corr_shape"])
+    a, b = corr.reshape(-1)[::5].double().numpy(), g["corr_sample"].astype(np.float64)
+    assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
+
+
 def test_ref_extension_matches_oracle_when_present():
     """The reference's own compiled CPU operators (oracle/_ref) travel with the repo; when present they
     must agree with the C restatement on a fresh random case (bit-exact)."""
