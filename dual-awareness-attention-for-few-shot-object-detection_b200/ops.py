@@ -462,7 +462,7 @@ def support_prepare(x, pe, shots, *, ba_w=None, ba_b=None, gamma=0.1, un_w, un_b
     r = torch.empty((maps, c), **f)
     colmean = torch.empty((maps, c), **f)
     vc = Pair.empty((maps * ns, c), dev, split=split)
-    vt = Pair.zeros((sets, c, vt_pitch), dev, split=split)
+    vt = Pair.empty((sets, c, vt_pitch), dev, split=split)       # pad columns are zeroed by the C entry
     rbar = torch.empty((sets, c), **f)
     cbar = Pair.empty((sets, c), dev, split=split) if want_cbar else None
     _count(4)                                  # logits, weighted sums, finalize, rbar

@@ -243,8 +243,8 @@ int dana_maxpool3x3s2(const void* in_hi, const void* in_lo, int batch, int h, in
 int dana_avgpool(const void* in_hi, const void* in_lo, int maps, int h, int w, int c, int k, float* out, void* stream);
 /* Support side of BA + CISA (dana.py:126-147; rcnn_head :255-276 with ba_w == NULL): positional
  * encoding, background-attenuation gate, unary term r, mean-centred k-projection input (vc) and the
- * transposed values vt[set][c][shot*seg_pitch + n] (row pitch vt_pitch, seg_pitch >= ns) for the P.V
- * contraction.  cbar_hi/lo (optional, [sets][c] pair): rbar + mean over shots of the column means -- the row-constant
+ * transposed values vt[set][c][shot*seg_pitch + n] (row pitch vt_pitch, seg_pitch >= ns; pad columns zeroed by the
+ * call) for the P.V contraction.  cbar_hi/lo (optional, [sets][c] pair): rbar + mean over shots of the column means -- the row-constant
  * part of the attended value when the head contracts P with the centred values. */
 int dana_support_prepare(const void* in_hi, const void* in_lo, const float* in_f32, const float* pe, int maps,
                          int shots, int ns, int c, const float* ba_w, const float* ba_b, float gamma,
