@@ -347,9 +347,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop on warp-uniform values (so the shared-memory descriptors sit in uniform
+    // registers and a k-step costs one add per operand); one elected lane issues the MMAs and the commits.
+    {
       const int mma_n = SOFTMAXW ? p.sm_half : BLOCK_N;
       const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(kTileM, mma_n) : umma_idesc_bf16(kTileM, mma_n);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t tiles_u = __shfl_sync(0xffffffffu, smem_u32(tiles), 0);
+      // descriptor of a tile = constant high word + (address >> 4); a 16-element k-step is 32 B = +2
+      constexpr uint64_t kDescHi = (kTileK == 64)
+          ? ((static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61))
+          : ((static_cast<uint64_t>(512 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(4) << 61));
+      auto desc_of = [&](uint32_t addr) -> uint64_t {
+        return kDescHi | static_cast<uint64_t>(((addr & 0x3FFFFu) >> 4) | (1u << 16));
+      };
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -359,53 +370,53 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       while (stream_k ? rng.next(wk, kb_lo, kb_hi) : ((wk += num_clusters) < num_work)) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1, 102);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        const uint32_t d_addr = tmem_u + static_cast<uint32_t>(acc * BLOCK_N);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase, 103);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint32_t a_hi = tiles_u + static_cast<uint32_t>(stage * Cfg::kStageBytes);
           const uint32_t b_hi = a_hi + NSPLIT * kATileBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int dy = 0; dy < Cfg::kBTaps; ++dy) {
-            // DX3: tap (dy, dx) reads the window box from row dy * bw on (a whole number of 8-row swizzle atoms)
-            const uint32_t a_t = a_hi + (DX3 ? static_cast<uint32_t>(dy * p.bw * (kTileK * 2)) : 0u);
-            const uint32_t b_t = b_hi + static_cast<uint32_t>(dy * Cfg::kBTileBytes);
+            for (int dy = 0; dy < Cfg::kBTaps; ++dy) {
+              // DX3: tap (dy, dx) reads the window box from row dy * bw on (a whole number of 8-row swizzle atoms)
+              const uint32_t a_t = a_hi + (DX3 ? static_cast<uint32_t>(dy * p.bw * (kTileK * 2)) : 0u);
+              const uint32_t b_t = b_hi + static_cast<uint32_t>(dy * Cfg::kBTileBytes);
 #pragma unroll
-          for (int k = 0; k < kTileK / 16; ++k) {
-            const uint32_t koff = k * 32;  // 16 bf16 = 32 B inside the swizzled row
+              for (int hf = 0; hf < (SOFTMAXW ? 2 : 1); ++hf) {
+                // wide softmax tile: columns [hf * sm_half, (hf + 1) * sm_half) from the hf-th box of keys
+                const uint32_t d_h = d_addr + (SOFTMAXW ? static_cast<uint32_t>(hf * p.sm_half) : 0u);
+                const uint32_t b_h = b_t + (SOFTMAXW ? static_cast<uint32_t>(hf * p.sm_half * (kTileK * 2)) : 0u);
+                const uint64_t da0 = desc_of(a_t), db0 = desc_of(b_h);
+                const uint64_t dal0 = desc_of(a_t + kATileBytes), dbl0 = desc_of(b_h + Cfg::kBGroupBytes);
 #pragma unroll
-            for (int hf = 0; hf < (SOFTMAXW ? 2 : 1); ++hf) {
-            // wide softmax tile: columns [hf * sm_half, (hf + 1) * sm_half) from the hf-th box of keys
-            const uint32_t d_h = d_addr + (SOFTMAXW ? static_cast<uint32_t>(hf * p.sm_half) : 0u);
-            const uint32_t b_h = b_t + (SOFTMAXW ? static_cast<uint32_t>(hf * p.sm_half * (kTileK * 2)) : 0u);
-            const uint64_t da = (kTileK == 64) ? umma_desc_sw128(a_t + koff) : umma_desc_sw64(a_t + koff);
-            const uint64_t db = (kTileK == 64) ? umma_desc_sw128(b_h + koff) : umma_desc_sw64(b_h + koff);
-            if (NSPLIT == 2) {
-              const uint64_t dal = (kTileK == 64) ? umma_desc_sw128(a_t + kATileBytes + koff)
-                                                  : umma_desc_sw64(a_t + kATileBytes + koff);
-              const uint64_t dbl = (kTileK == 64) ? umma_desc_sw128(b_h + Cfg::kBGroupBytes + koff)
-                                                  : umma_desc_sw64(b_h + Cfg::kBGroupBytes + koff);
-              // small cross terms first, leading term last
-              umma_bf16(d_h, dal, db, idesc, ((kb - kb_lo) | k | dy) != 0);
-              umma_bf16(d_h, da, dbl, idesc, 1);
-              umma_bf16(d_h, da, db, idesc, 1);
+                for (int k = 0; k < kTileK / 16; ++k) {
+                  const uint32_t first = static_cast<uint32_t>((kb - kb_lo) | k | dy);
+                  if (NSPLIT == 2) {
+                    // small cross terms first, leading term last
+                    umma_bf16(d_h, dal0 + 2 * k, db0 + 2 * k, idesc, first);
+                    umma_bf16(d_h, da0 + 2 * k, dbl0 + 2 * k, idesc, 1);
+                    umma_bf16(d_h, da0 + 2 * k, db0 + 2 * k, idesc, 1);
+                  } else {
+                    umma_bf16(d_h, da0 + 2 * k, db0 + 2 * k, idesc, first);
+                  }
+                }
+              }
+            }
+            if (CM == 1) {
+              umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
             } else {
-              umma_bf16(d_h, da, db, idesc, ((kb - kb_lo) | k | dy) != 0);
+              umma_commit_mc(&empty_bar[stage], kMcMask);  // ... in every CTA of the cluster
             }
-            }
           }
-          }
-          if (CM == 1) {
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          } else {
-            umma_commit_mc(&empty_bar[stage], kMcMask);  // ... in every CTA of the cluster
-          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[acc]);  // accumulator ready for the epilogue
+        if (elect_one()) umma_commit(&acc_full[acc]);  // accumulator ready for the epilogue
+        __syncwarp();
         if (++acc == kAccBufs) {
           acc = 0;
           acc_phase ^= 1;
