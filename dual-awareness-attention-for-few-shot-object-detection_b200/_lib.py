@@ -116,6 +116,11 @@ SIGNATURES = {
     "dana_nhwc_pair_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dana_transpose_segments": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p,
                                         c_void_p]),
+    "dana_grad_prepare": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int64, c_void_p]),
+    "dana_im2col_t": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int,
+                              c_void_p, c_void_p, c_int64, c_void_p]),
+    "dana_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,191 @@
+"""torch.autograd bindings of the tensor-core kernels for the TRAINING step (BASELINE
+configs[3]): every convolution / linear / batched product of the training branch runs forward AND backward on
+dana_conv_gemm (tcgen05), the way train.py:138 `loss.backward()` runs them on cuDNN / cuBLAS in the reference.
+
+  conv (+ frozen-BN fold) (+ residual) (+ ReLU)   resnet.py:66-102 (Bottleneck), rpn.py:58-72, dana.py:124,140,288
+      forward      y = relu(conv(x, W * s) + t + res)                one implicit GEMM, fp32 + bf16-pair outputs
+      data grad    dx = conv^T(g', W * s),  g' = g * (y > 0)         the same kernel on transposed / rotated weights;
+                                                                     a strided 1x1 writes every s-th pixel of a zeroed dx
+      weight grad  dW[co][tap][ci] = sum_p g'[p][co] x[p+tap][ci]    one K-major GEMM over the pixel index on the
+                                                                     channel-major operands written by dana_grad_prepare
+                                                                     and dana_im2col_t (stream-K spreads the long K)
+  bmm_nt   c[b] = a[b] @ b[b]^T                   dana.py:142,147,273,278 (torch.bmm) -- three batched GEMMs fwd + bwd
+
+Activations cross the autograd graph as fp32 NHWC tensors; the bf16 (hi, lo) operand planes of a tensor produced by
+one of these functions ride along as `tensor._dana_pair` so that the consumer does not split again.  Operands are
+split-bf16 everywhere (three MMAs per product, fp32-equivalent), gradients included."""
+import torch
+
+from . import ops
+from .ops import Pair
+
+_W_CACHE = {}
+_LAST_PAIR = None
+
+
+def begin_step():
+    """Drop the packed-weight cache (weights change with every optimiser step)."""
+    _W_CACHE.clear()
+
+
+def _packed(w, scale):
+    """Packed operand planes of a conv / linear weight [Cout, Cin, k, k] with the frozen-BN scale folded in."""
+    key = (w.data_ptr(), w._version, 0 if scale is None else scale.data_ptr())
+    ent = _W_CACHE.get(key)
+    if ent is None:
+        with torch.no_grad():
+            wf = w.detach().float()
+            if scale is not None:
+                wf = wf * scale.view(-1, 1, 1, 1)
+            co, ci, kh, kw = wf.shape
+            ent = {"wf": wf, "fwd": Pair.from_float(wf.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous())}
+        _W_CACHE[key] = ent
+    return ent
+
+
+def _dgrad_weight(ent):
+    if "dgrad" not in ent:
+        wf = ent["wf"]
+        co, ci, kh, kw = wf.shape
+        # dx[p][ci] = sum_{tap,co} g[p - tap][co] W[co][ci][tap]: a convolution of g with the 180-degree rotated kernel
+        wr = wf.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, kh * kw * co).contiguous()
+        ent["dgrad"] = Pair.from_float(wr)
+    return ent["dgrad"]
+
+
+def pair_of(x):
+    """Operand planes of an fp32 NHWC activation (cached on the tensor when a dana op produced it)."""
+    p = getattr(x, "_dana_pair", None)
+    if p is None:
+        p = ops.split_f32(x.detach().contiguous())
+    return p
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, res, scale, relu, ksize, stride, xp, rp):
+        global _LAST_PAIR
+        ent = _packed(w, scale)
+        n, h, wd, ci = x.shape
+        co = w.shape[0]
+        oh, ow = (h, wd) if ksize == 3 else ((h - 1) // stride + 1, (wd - 1) // stride + 1)
+        y = torch.empty((n, oh, ow, co), dtype=torch.float32, device=x.device)
+        yp = Pair.empty((n, oh, ow, co), x.device)
+        if xp is None:
+            xp = ops.split_f32(x.detach().contiguous())
+        if res is not None and rp is None:
+            rp = ops.split_f32(res.detach().contiguous())
+        ops.conv_nhwc(xp, ent["fwd"], co, ksize=ksize, stride=stride, bias=None if bias is None else bias.detach(),
+                      res=rp, relu=relu, out=yp, out_f32=y)
+        ctx.ent, ctx.xp, ctx.relu, ctx.ksize, ctx.stride, ctx.scale = ent, xp, relu, ksize, stride, scale
+        ctx.x_shape = tuple(x.shape)
+        ctx.has_bias, ctx.has_res = bias is not None, res is not None
+        ctx.save_for_backward(y if relu else None)
+        _LAST_PAIR = yp
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
+        ent, ksize, stride = ctx.ent, ctx.ksize, ctx.stride
+        n, h, wd, ci = ctx.x_shape
+        co = gy.shape[-1]
+        want_f32 = (need_r and ctx.relu) or need_b
+        gf, gp, gt = ops.grad_prepare(gy, y, want_f32=want_f32, want_pair=need_x, want_t=need_w)
+        dx = dw = db = dr = None
+        if need_r:
+            dr = gf if ctx.relu else gy
+        if need_b:
+            db = gf.sum(dim=(0, 1, 2))
+        if need_x:
+            wd_pair = _dgrad_weight(ent)
+            if stride == 1:
+                dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=gy.device)
+                ops.conv_nhwc(gp, wd_pair, ci, ksize=ksize, stride=1, out_f32=dx)
+            else:                                        # strided 1x1: only every stride-th pixel was read
+                dx = torch.zeros(ctx.x_shape, dtype=torch.float32, device=gy.device)
+                ops.conv_nhwc(gp, wd_pair, ci, ksize=1, stride=1, out_f32=dx[:, ::stride, ::stride, :])
+        if need_w:
+            xt = ops.im2col_t(ctx.xp, ksize, stride)                      # [taps*ci, pixels]
+            dwk = torch.empty((co, ksize * ksize * ci), dtype=torch.float32, device=gy.device)
+            ops.linear(gt, xt, ksize * ksize * ci, out_f32=dwk)
+            dw = dwk.view(co, ksize, ksize, ci).permute(0, 3, 1, 2)
+            if ctx.scale is not None:
+                dw = dw * ctx.scale.view(-1, 1, 1, 1)
+        return dx, dw, db, dr, None, None, None, None, None, None
+
+
+def conv(x, w, bias=None, res=None, scale=None, relu=False, ksize=1, stride=1):
+    """y = relu?(conv(x, w * scale) + bias + res) on fp32 NHWC tensors; w [Cout, Cin, k, k]."""
+    xp = getattr(x, "_dana_pair", None)
+    rp = None if res is None else getattr(res, "_dana_pair", None)
+    y = _ConvFn.apply(x, w, bias, res, scale, relu, ksize, stride, xp, rp)
+    y._dana_pair = _LAST_PAIR
+    return y
+
+
+def linear(x, w, bias=None, relu=False):
+    """nn.Linear on [..., K] (K % 8 == 0): the 1x1 convolution of a one-row image."""
+    lead = x.shape[:-1]
+    co = w.shape[0]
+    pad = (-co) % 8
+    if pad:
+        # the C -> 1 layers (unary / channel attention, dana.py:133,144): zero rows up to 8 outputs, so that the
+        # gradient GEMMs see a 16-byte row pitch; the extra columns are sliced off (and receive zero gradient)
+        w = torch.cat([w, w.new_zeros(pad, w.shape[1])], 0)
+        if bias is not None:
+            bias = torch.cat([bias, bias.new_zeros(pad)], 0)
+    x4 = x.reshape(1, 1, -1, x.shape[-1])
+    if hasattr(x, "_dana_pair") and x.is_contiguous():
+        x4._dana_pair = x._dana_pair.view(*x4.shape)
+    y = conv(x4, w.view(w.shape[0], w.shape[1], 1, 1), bias=bias, relu=relu)
+    out = y.view(*lead, w.shape[0])
+    if pad:
+        return out[..., :co]
+    out._dana_pair = y._dana_pair.view(*out.shape)
+    return out
+
+
+def _operand(t):
+    """Split a [batch, rows, K] fp32 tensor into GEMM operand planes [batch*rows, K]; K is padded to a multiple of 8
+    in memory (16-byte row pitch for the tensor map) while the logical extent stays K (out-of-bounds reads are zero)."""
+    b, r, k = t.shape
+    t = t.detach()
+    if k % 8 == 0:
+        return ops.split_f32(t.reshape(b * r, k).contiguous())
+    kp = (k + 7) // 8 * 8
+    buf = torch.zeros((b * r, kp), dtype=torch.float32, device=t.device)
+    buf[:, :k] = t.reshape(b * r, k)
+    return ops.split_f32(buf)[:, :k]
+
+
+class _BmmNTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return _bmm_nt_run(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = _bmm_nt_run(g, b.transpose(1, 2))           # [B,M,N] x [B,K,N]^T
+        if ctx.needs_input_grad[1]:
+            db = _bmm_nt_run(g.transpose(1, 2), a.transpose(1, 2))   # [B,N,M] x [B,K,M]^T
+        return da, db
+
+
+def _bmm_nt_run(a, b):
+    bsz, m, k = a.shape
+    n = b.shape[1]
+    ap, bp = _operand(a), _operand(b)
+    out = torch.empty((bsz, m, n), dtype=torch.float32, device=a.device)
+    ops.linear(ap, bp, n, out_f32=out.view(bsz * m, n), batch=bsz, b_batch_stride=n * bp.hi.stride(0))
+    return out
+
+
+def bmm_nt(a, b):
+    """torch.bmm(a, b.transpose(1, 2)) on the tensor-core GEMM, forward and backward."""
+    return _BmmNTFn.apply(a, b)

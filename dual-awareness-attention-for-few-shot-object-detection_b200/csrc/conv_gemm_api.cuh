@@ -176,7 +176,8 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
     }
     dx3 = a->a_c <= dx3_env && a->taps_r == 3 && a->taps_s == 3 && a->pad_y == 1 && a->pad_x == 1 && a->a_lo != nullptr && !batched &&
           !softmax && !io_f16 && a->bias_sn == 0 && (a->a_c == 64 || a->a_c == 128 || a->a_c == 256) &&
-          (a->n_out == 64 || a->n_out % 128 == 0) && a->tile_w <= 0 && a->out_w == a->a_w && a->out_h == a->a_h;
+          (a->n_out == 64 || a->n_out % 128 == 0) && a->tile_w <= 0 && a->out_w == a->a_w && a->out_h == a->a_h &&
+          a->out_f32 == nullptr && a->res_f32 == nullptr && a->out_hi != nullptr;   // the schedule only has the fast epilogue
     if (dx3) {
       auto cost = [&](int bw) {
         const int bh = 128 / bw;

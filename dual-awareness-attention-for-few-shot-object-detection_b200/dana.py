@@ -223,7 +223,8 @@ class DAnARCNN(nn.Module):
         support_ims [B, 2*K, 3, H, W]: K positive then K negative crops per image (n_way = 2).  Anchor / proposal
         targets are drawn on the host with numpy's global RNG exactly like the reference (dana_b200.targets); the
         losses are device kernels.  Returns the reference's 8-tuple; the losses are 0-dim CUDA tensors WITHOUT a
-        graph: the backward pass of this path is not built."""
+        graph (the torch.no_grad() variant: validation losses); with gradients enabled forward() takes
+        _forward_train_graph instead."""
         import numpy as np
 
         from . import ops, targets
@@ -273,10 +274,41 @@ class DAnARCNN(nn.Module):
         rois_label = torch.cat([lab_s.view(-1), torch.zeros_like(lab_s.view(-1))]).long()      # dana.py:195-196
         return rois, cls_prob, bbox_pred, rpn[0], rpn[1], rcnn[0], rcnn[1], rois_label
 
+    def _forward_train_graph(self, im_data, im_info, gt_boxes, num_boxes, support_ims, teacher=None):
+        """Training branch with the autograd graph (train.py:129-139: the four losses are summed and `.backward()`ed):
+        dana_b200.train_model.TrainGraph over this module's own parameters -- forward, data- and weight-gradients of
+        every trainable convolution / projection / attention product on the tcgen05 GEMM."""
+        from .anchors import generate_anchors
+        from .train_model import FrozenStem, TrainGraph
+        if self.n_way != 2:
+            raise NotImplementedError("the training branch is built for n_way = 2 (positive + negative support set), "
+                                      "like the reference's (dana.py:100-108)")
+        if support_ims.shape[1] != 2 * self.n_shot:
+            raise ValueError("train mode expects %d support crops per image (n_way * n_shot), got %d"
+                             % (2 * self.n_shot, support_ims.shape[1]))
+        if cfg.RESNET.FIXED_BLOCKS != 1:
+            raise NotImplementedError("the training graph is built for RESNET.FIXED_BLOCKS = 1 (config.py:223)")
+        dev = im_data.device
+        if dev.type != "cuda":
+            raise RuntimeError("DAnARCNN (dana_b200) runs on CUDA only: call .cuda() first (there is no CPU fallback)")
+        named = dict(self.named_parameters())
+        named.update(dict(self.named_buffers()))
+        frozen = [t for n, t in named.items() if n.startswith(("RCNN_base.0.", "RCNN_base.1.", "RCNN_base.4."))]
+        key = tuple((t.data_ptr(), t._version) for t in frozen)
+        if getattr(self, "_stem_key", None) != key:
+            self._stem, self._stem_key = FrozenStem(named, dev), key
+        anchors = torch.from_numpy(generate_anchors(ratios=tuple(cfg.ANCHOR_RATIOS), scales=tuple(cfg.ANCHOR_SCALES)))
+        graph = TrainGraph(named, num_layers=self.num_layers, n_shot=self.n_shot, semantic_enhance=self.semantic_enhance,
+                           channel_gamma=self.channel_gamma, unary_gamma=self.unary_gamma)
+        return graph.forward(self._stem, im_data, im_info.data, gt_boxes, num_boxes, support_ims,
+                             anchors.float().to(dev), cfg.FEAT_STRIDE[0], teacher=teacher)
+
     def forward(self, im_data, im_info, gt_boxes, num_boxes, support_ims, all_cls_gt_boxes=None):
         if cfg.POOLING_MODE != "align":
             raise NotImplementedError("POOLING_MODE %r is not built (shipped configs use 'align')" % cfg.POOLING_MODE)
         if self.training:
+            if torch.is_grad_enabled():
+                return self._forward_train_graph(im_data, im_info, gt_boxes, num_boxes, support_ims)
             return self._forward_train(im_data, im_info, gt_boxes, num_boxes, support_ims)
         if cfg.POOLING_MODE != "align":
             raise NotImplementedError("POOLING_MODE %r is not built (shipped configs use 'align')" % cfg.POOLING_MODE)

@@ -695,5 +695,51 @@ def depthwise_xcorr(x: Pair, kernel_f32, *, want_f32=True, want_pair=False, spli
     return out, pair
 
 
+# --------------------------------------------------------------------------- backward-pass layout kernels
+def grad_prepare(grad_f32, relu_out=None, *, want_f32=False, want_pair=True, want_t=True):
+    """g' = grad * (relu_out > 0) on an fp32 [..., C] gradient (C % 4 == 0).  Returns (g' fp32 | None, NHWC pair | None,
+    channel-major pair [C, pitch] viewed [C, pixels] | None): the operands of the data- and weight-gradient GEMMs."""
+    _need_cuda(grad_f32)
+    g = grad_f32.contiguous()
+    c = g.shape[-1]
+    pixels = g.numel() // c
+    dev = g.device
+    out_f32 = torch.empty_like(g) if want_f32 else None
+    pair = Pair.empty(g.shape, dev) if want_pair else None
+    pitch = (pixels + 7) // 8 * 8
+    tp = Pair.empty((c, pitch), dev) if want_t else None
+    y = None if relu_out is None else relu_out.contiguous()
+    _count(1)
+    check(_lib.load().dana_grad_prepare(_p(g), _p(y), pixels, c, _p(out_f32), _p(pair.hi) if pair else None,
+                                        _p(pair.lo) if pair else None, _p(tp.hi) if tp else None,
+                                        _p(tp.lo) if tp else None, pitch, _stream()), "dana_grad_prepare")
+    return out_f32, pair, (tp[:, :pixels] if tp else None)
+
+
+def im2col_t(x: Pair, ksize=1, stride=1):
+    """Channel-major im2col of an NHWC pair [N,H,W,C] -> pair [taps*C, pixels] (a view of a [taps*C, pitch] buffer)."""
+    _need_cuda(x.hi)
+    n, h, w, c = x.hi.shape
+    sn, sy, sx, sc = x.hi.stride()
+    assert sc == 1 and (x.lo is None or x.lo.stride() == x.hi.stride())
+    oh, ow = (h, w) if ksize == 3 else ((h - 1) // stride + 1, (w - 1) // stride + 1)
+    pixels = n * oh * ow
+    pitch = (pixels + 7) // 8 * 8
+    out = Pair.empty((ksize * ksize * c, pitch), x.hi.device, split=x.lo is not None)
+    _count(1)
+    check(_lib.load().dana_im2col_t(_p(x.hi), _p(x.lo), n, h, w, c, sn, sy, sx, ksize, stride, _p(out.hi), _p(out.lo),
+                                    pitch, _stream()), "dana_im2col_t")
+    return out[:, :pixels]
+
+
+def sgd_momentum(param_flat, grad_flat, mom_flat, lr, momentum, weight_decay, grad_scale=1.0):
+    """In-place torch.optim.SGD step (train.py:89,139) on flat fp32 buffers."""
+    _need_cuda(param_flat, grad_flat, mom_flat)
+    _count(1)
+    check(_lib.load().dana_sgd_momentum(_p(param_flat), _p(grad_flat), _p(mom_flat), param_flat.numel(), float(lr),
+                                        float(momentum), float(weight_decay), float(grad_scale), _stream()),
+          "dana_sgd_momentum")
+
+
 def device_error():
     return _lib.load().dana_device_error()

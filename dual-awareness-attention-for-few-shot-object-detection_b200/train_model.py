@@ -1,0 +1,289 @@
+"""Training branch of _DAnARCNN.forward WITH its autograd graph (BASELINE configs[3]):
+`loss.backward()` of train.py:138 runs every convolution / projection / attention product backward on the tcgen05
+GEMM through dana_b200.autograd_ops, the RoIAlign backward on dana_roi_align_backward.
+
+What runs where:
+  frozen stem + layer1 (dana.py:350-368, FIXED_BLOCKS = 1)   the eval kernels, no graph
+  layer2, layer3 (query and support crops), layer4           autograd_ops.conv: fwd + data-grad + weight-grad GEMMs
+  RPN 3x3 conv + heads, q / k projections, transform, FFN    autograd_ops.conv / linear
+  attention logits and P.V products (dana.py:142,147,273,278) autograd_ops.bmm_nt
+  RoIAlign (dana.py:183)                                     dana_roi_align_forward / dana_roi_align_backward (NHWC)
+  proposals + NMS (no gradient, rpn.py:74-78)                dana_proposals
+  anchor / proposal targets                                  host numpy, the reference's RNG call order (targets.py)
+  softmax, mean-centering, leaky-ReLU gate, PE add, the C -> 1 weighted sums, average pool, losses
+                                                             torch element-wise ops (ATen) -- glue, < 2 % of the FLOPs
+
+Activations are fp32 NHWC; every GEMM operand is a split-bf16 pair (fp32-equivalent products)."""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import autograd_ops as A
+from . import ops, targets
+from .config import cfg
+from .engine import BN_EPS, RES_LAYERS, _Block, positional_encoding
+
+
+class _RoIAlignNHWC(torch.autograd.Function):
+    """ROIAlign(7, 7, 1/16, 0) on an NHWC map (roi_layers/roi_align.py:12-45): forward and backward kernels."""
+
+    @staticmethod
+    def forward(ctx, feat, rois):
+        out, _ = ops.roi_align_nhwc(feat.contiguous(), rois, 1.0 / 16.0, 7, 0, want_f32=True, want_pair=False)
+        ctx.save_for_backward(rois)
+        ctx.shape = tuple(feat.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rois,) = ctx.saved_tensors
+        b, h, w, c = ctx.shape
+        return ops.roi_align_backward_nhwc(g.reshape(g.shape[0], 49, c), rois, 1.0 / 16.0, b, h, w, 0), None
+
+
+class FrozenStem:
+    """conv1 / bn1 / relu / maxpool / layer1 -- frozen in training (dana.py:350-359) -- packed once for the eval kernels."""
+
+    def __init__(self, sd, device):
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
+        self.stem_w = ops.pack_stem_weight(f32(sd["RCNN_base.0.weight"]), True)
+        g, b, m, v = [f32(sd["RCNN_base.1." + n]) for n in ("weight", "bias", "running_mean", "running_var")]
+        self.scale = (g / torch.sqrt(v + BN_EPS)).contiguous()
+        self.bias = (b - m * self.scale).contiguous()
+        n_blocks = len([k for k in sd if k.startswith("RCNN_base.4.") and k.endswith(".conv1.weight")])
+        sdf = {k: v.detach().float() for k, v in sd.items() if k.startswith("RCNN_base.4.")}
+        self.blocks = [_Block(sdf, "RCNN_base.4.%d" % i, device, True) for i in range(n_blocks)]
+
+    def __call__(self, im_nchw):
+        x = ops.stem(im_nchw.float().contiguous(), self.stem_w, self.scale, self.bias, split=True)
+        for blk in self.blocks:
+            y = ops.conv_nhwc(x, blk.c1.w, blk.c1.n_out, ksize=1, scale=blk.c1.scale, bias=blk.c1.bias, relu=True)
+            y = ops.conv_nhwc(y, blk.c2.w, blk.c2.n_out, ksize=3, scale=blk.c2.scale, bias=blk.c2.bias, relu=True)
+            res = x if blk.down is None else ops.conv_nhwc(x, blk.down.w, blk.down.n_out, ksize=1, scale=blk.down.scale,
+                                                           bias=blk.down.bias)
+            x = ops.conv_nhwc(y, blk.c3.w, blk.c3.n_out, ksize=1, scale=blk.c3.scale, bias=blk.c3.bias, res=res, relu=True)
+        out = ops.merge_pair(x)
+        out._dana_pair = x
+        return out
+
+
+class TrainGraph:
+    """Functional training forward over a name -> tensor dict `p` (the module's parameters and buffers)."""
+
+    def __init__(self, p, num_layers=50, n_shot=3, semantic_enhance=True, channel_gamma=0.1, unary_gamma=0.1):
+        self.p = p
+        self.layers = RES_LAYERS[num_layers]
+        self.n_shot = n_shot
+        self.semantic_enhance = semantic_enhance
+        self.channel_gamma, self.unary_gamma = channel_gamma, unary_gamma
+        self._bn = {}
+        self._pe = {}
+
+    # ------------------------------------------------------------------ trunk
+    def bn(self, name):
+        """Frozen BatchNorm as an affine fold (dana.py:362-368): (scale, shift)."""
+        v = self._bn.get(name)
+        if v is None:
+            p = self.p
+            with torch.no_grad():
+                s = p[name + ".weight"].float() / torch.sqrt(p[name + ".running_var"].float() + BN_EPS)
+                t = p[name + ".bias"].float() - p[name + ".running_mean"].float() * s
+            v = self._bn[name] = (s.contiguous(), t.contiguous())
+        return v
+
+    def bottleneck(self, x, name, stride):
+        """resnet.py:66-102 (stride on the first 1x1)."""
+        p = self.p
+        s1, t1 = self.bn(name + ".bn1")
+        s2, t2 = self.bn(name + ".bn2")
+        s3, t3 = self.bn(name + ".bn3")
+        y = A.conv(x, p[name + ".conv1.weight"], bias=t1, scale=s1, relu=True, ksize=1, stride=stride)
+        y = A.conv(y, p[name + ".conv2.weight"], bias=t2, scale=s2, relu=True, ksize=3)
+        if (name + ".downsample.0.weight") in p:
+            sd, td = self.bn(name + ".downsample.1")
+            res = A.conv(x, p[name + ".downsample.0.weight"], bias=td, scale=sd, ksize=1, stride=stride)
+        else:
+            res = x
+        return A.conv(y, p[name + ".conv3.weight"], bias=t3, scale=s3, res=res, relu=True)
+
+    def stage(self, x, prefix, blocks, stride):
+        for i in range(blocks):
+            x = self.bottleneck(x, "%s.%d" % (prefix, i), stride if i == 0 else 1)
+        return x
+
+    def trunk_tail(self, x):
+        """layer2 + layer3 on the frozen layer1 output (NHWC fp32)."""
+        x = self.stage(x, "RCNN_base.5", self.layers[1], 2)
+        return self.stage(x, "RCNN_base.6", self.layers[2], 2)
+
+    def head_to_tail(self, pooled):
+        """RCNN_top + spatial mean (dana.py:387-389): [R,7,7,1024] -> [R,2048]."""
+        return self.stage(pooled, "RCNN_top.0", self.layers[3], 2).mean(dim=(1, 2))
+
+    # ------------------------------------------------------------------ attention
+    def pe(self, n, c, device):
+        key = (n, c, device)
+        if key not in self._pe:
+            self._pe[key] = positional_encoding(n, c).to(device)
+        return self._pe[key]
+
+    def lin(self, x, name, relu=False):
+        return A.linear(x, self.p[name + ".weight"], self.p[name + ".bias"], relu=relu)
+
+    def attend(self, qc, shots, prefix, d, enhance=None, repeat=1):
+        """dana.py:126-150 / 268-281 for every shot: BA gate, k-projection, centred logits, softmax + unary term, P.V;
+        the shot mean.  shots: [G0, Ns, C] each (PE applied); with repeat > 1 each support row serves `repeat`
+        consecutive query rows (the head's per-RoI copy, dana.py:254-258): the support-only quantities are computed
+        once per image and repeated, which is the same function."""
+        outs = []
+        for s in shots:
+            if enhance is not None:                                           # BA block, dana.py:133-137
+                w = F.softmax(self.lin(s, enhance), 1)                        # [G0, Ns, 1]
+                g = (w * s).sum(1, keepdim=True)                              # bmm(w^T, s): a weighted sum over positions
+                s = s + self.channel_gamma * F.leaky_relu(g)
+            k = self.lin(s, prefix + "_adapt_k_layer")
+            k = k - k.mean(1, keepdim=True)
+            un = F.softmax(self.lin(s, prefix + "_unary_layer"), 1)           # [G0, Ns, 1]
+            if repeat > 1:
+                k, un, s = [t.repeat_interleave(repeat, dim=0) for t in (k, un, s)]
+            att = F.softmax(A.bmm_nt(qc, k) / math.sqrt(d), dim=2)
+            att = att + self.unary_gamma * un.transpose(1, 2)
+            outs.append(A.bmm_nt(att, s.transpose(1, 2)))                     # att @ s
+        return torch.stack(outs, 0).mean(0)
+
+    def rpn_attention(self, base, sup_pos):
+        """dana.py:117-151.  base [B,h,w,C]; sup_pos [B,K,hs,ws,C] -> dense [B,h,w,C]."""
+        b, h, w, c = base.shape
+        k, ns = sup_pos.shape[1], sup_pos.shape[2] * sup_pos.shape[3]
+        q = self.lin(base.view(b, h * w, c), "rpn_adapt_q_layer")
+        q = q - q.mean(1, keepdim=True)
+        pe = self.pe(ns, c, base.device)
+        shots = [sup_pos[:, i].reshape(b, ns, c) + pe for i in range(k)]
+        dense = self.attend(q, shots, "rpn", 256, "rpn_channel_k_layer" if self.semantic_enhance else None)
+        return dense.view(b, h, w, c)
+
+    def rcnn_head(self, pooled, sup_pooled, per):
+        """dana.py:247-290.  pooled [R,7,7,C]; sup_pooled [B,K,7,7,C] -> cls_score [R,2]."""
+        r, c = pooled.shape[0], pooled.shape[-1]
+        b, k = sup_pooled.shape[0], sup_pooled.shape[1]
+        pe = self.pe(49, c, pooled.device)
+        q_mat = pooled.reshape(r, 49, c) + pe
+        q = self.lin(q_mat, "rcnn_adapt_q_layer")
+        q = q - q.mean(1, keepdim=True)
+        shots = [sup_pooled[:, i].reshape(b, 49, c) + pe for i in range(k)]
+        dense = self.attend(q, shots, "rcnn", 256, None, repeat=per)
+        corr = self.lin(torch.cat([q_mat, dense], 2), "rcnn_transform_layer")          # [R,49,64]
+        hid = self.lin(corr.reshape(r, -1), "output_score_layer.linear1", relu=True)
+        return self.lin(hid, "output_score_layer.linear2")
+
+    # ------------------------------------------------------------------ losses (rpn.py:96-116, dana.py:199-215)
+    @staticmethod
+    def smooth_l1(pred, tgt, in_w, out_w, sigma, dims):
+        s2 = sigma * sigma
+        d = in_w * (pred - tgt)
+        a = d.abs()
+        small = (a < 1.0 / s2).float()
+        loss = out_w * (d * d * (s2 / 2.0) * small + (a - 0.5 / s2) * (1.0 - small))
+        return loss.sum(dim=dims).mean()
+
+    def rpn_losses(self, rpn_raw, anchor_t, num_a):
+        labels, tgt, in_w, out_w = anchor_t                 # (y, x, a) anchor order, flat per image
+        b = rpn_raw.shape[0]
+        raw = rpn_raw.view(b, -1, 6 * num_a)
+        score = torch.stack([raw[..., :num_a].reshape(-1), raw[..., num_a:2 * num_a].reshape(-1)], 1)
+        lab = labels.view(-1).long()
+        keep = torch.nonzero(lab != -1).view(-1)
+        loss_cls = F.cross_entropy(score[keep], lab[keep])
+        deltas = raw[..., 2 * num_a:].reshape(b, -1, 4)
+        loss_box = self.smooth_l1(deltas, tgt, in_w.unsqueeze(2), out_w.unsqueeze(2), 3.0, (1, 2))
+        return loss_cls, loss_box
+
+    @staticmethod
+    def rcnn_cls_loss(scores, labels):
+        """dana.py:203-214: all fg, the hardest bg of the positive-support half (2 x fg, at most a quarter of the rows)
+        and of the negative-support half (<= fg)."""
+        n = labels.shape[0]
+        fg = torch.nonzero(labels == 1).view(-1)
+        bg = torch.nonzero(labels == 0).view(-1)
+        sm = F.softmax(scores.detach(), dim=1)
+        bg0 = max(1, min(fg.numel() * 2, int(n * 0.25)))
+        bg1 = max(1, min(fg.numel(), bg0))
+        real_bg = bg[torch.sort(sm[bg, 1], descending=True)[1]]
+        top0 = real_bg[real_bg < int(n * 0.5)][:bg0]
+        top1 = real_bg[real_bg >= int(n * 0.5)][:bg1]
+        idx = torch.cat([fg, top0, top1], 0)
+        return F.cross_entropy(scores[idx], labels[idx])
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, stem, im_data, im_info, gt_boxes, num_boxes, support_ims, base_anchors, feat_stride=16,
+                teacher=None):
+        """-> (rois [B,R,5], cls_prob [2BR,2], bbox_pred [BR,4], rpn_loss_cls, rpn_loss_box, RCNN_loss_cls,
+        RCNN_loss_bbox, rois_label [2BR]) -- the reference's 8-tuple; the four losses carry the autograd graph."""
+        p, k = self.p, self.n_shot
+        dev = im_data.device
+        b = im_data.shape[0]
+        num_a = base_anchors.shape[0]
+        A.begin_step()
+        self._bn.clear()
+        with torch.no_grad():
+            q1 = stem(im_data)
+            s1 = stem(support_ims.reshape(-1, *support_ims.shape[2:]))
+        base = self.trunk_tail(q1)                                            # [B,h,w,1024]
+        sup = self.trunk_tail(s1)                                             # [B*2K,hs,ws,1024]
+        _, qh, qw, c = base.shape
+        hs, ws = sup.shape[1], sup.shape[2]
+        if hs != ws:
+            raise ValueError("support feature maps must be square (AvgPool2d of dana.py:42)")
+        sup = sup.view(b, 2, k, hs, ws, c)                                    # positive set, negative set (dana.py:100-108)
+        sup_pooled = F.avg_pool2d(sup.reshape(-1, hs, ws, c).permute(0, 3, 1, 2), hs - 6, 1).permute(0, 2, 3, 1)
+        sup_pooled = sup_pooled.reshape(b, 2, k, 7, 7, c)
+
+        dense = self.rpn_attention(base, sup[:, 0])
+        corr = torch.cat([base, dense], 3)                                    # dana.py:154
+        x = A.conv(corr, p["RCNN_rpn.RPN_Conv.weight"], bias=p["RCNN_rpn.RPN_Conv.bias"], relu=True, ksize=3)
+        w_out = torch.cat([p["RCNN_rpn.RPN_cls_score.weight"], p["RCNN_rpn.RPN_bbox_pred.weight"]], 0)
+        b_out = torch.cat([p["RCNN_rpn.RPN_cls_score.bias"], p["RCNN_rpn.RPN_bbox_pred.bias"]], 0)
+        rpn_raw = A.conv(x, w_out, bias=b_out, ksize=1)                       # [B,h,w,6A]: bg | fg | deltas
+
+        # ---- proposal layer + targets: no gradient (rpn.py:74-93, dana.py:166-170)
+        with torch.no_grad():
+            fg, deltas = ops.rpn_fg_prob(rpn_raw.detach().contiguous(), num_a)
+            rois_all = ops.proposals(fg, deltas, base_anchors, im_info.to(dev).float(), qh, qw, feat_stride,
+                                     cfg.TRAIN.RPN_PRE_NMS_TOP_N, cfg.TRAIN.RPN_POST_NMS_TOP_N, cfg.TRAIN.RPN_NMS_THRESH)
+            if teacher and "rois" in teacher:
+                rois_all = teacher["rois"].to(dev).float().contiguous()
+            gt_host = gt_boxes.detach().float().cpu().numpy()
+            info_host = im_info.detach().float().cpu().numpy()
+            # anchor targets first, then proposal targets: the order of the reference's numpy RNG draws
+            anchor_t = targets.anchor_targets(
+                qh, qw, gt_host, info_host, base_anchors.cpu().numpy(), feat_stride,
+                negative_overlap=cfg.TRAIN.RPN_NEGATIVE_OVERLAP, positive_overlap=cfg.TRAIN.RPN_POSITIVE_OVERLAP,
+                clobber_positives=cfg.TRAIN.RPN_CLOBBER_POSITIVES, fg_fraction=cfg.TRAIN.RPN_FG_FRACTION,
+                batchsize=cfg.TRAIN.RPN_BATCHSIZE, inside_weight=cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0],
+                positive_weight=cfg.TRAIN.RPN_POSITIVE_WEIGHT)
+            sample = targets.proposal_targets(
+                rois_all.cpu().numpy(), gt_host, rois_per_image=cfg.TRAIN.BATCH_SIZE, fg_fraction=cfg.TRAIN.FG_FRACTION,
+                fg_thresh=cfg.TRAIN.FG_THRESH, bg_thresh_hi=cfg.TRAIN.BG_THRESH_HI, bg_thresh_lo=cfg.TRAIN.BG_THRESH_LO,
+                normalize_means=cfg.TRAIN.BBOX_NORMALIZE_MEANS, normalize_stds=cfg.TRAIN.BBOX_NORMALIZE_STDS,
+                inside_weights=cfg.TRAIN.BBOX_INSIDE_WEIGHTS,
+                normalize_targets=cfg.TRAIN.BBOX_NORMALIZE_TARGETS_PRECOMPUTED)
+            anchor_t = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in anchor_t]
+            rois, lab_s, tgt_s, inw_s, outw_s = [torch.from_numpy(np.ascontiguousarray(t)).to(dev).float() for t in sample]
+        rpn_loss_cls, rpn_loss_box = self.rpn_losses(rpn_raw, anchor_t, num_a)
+
+        per = rois.shape[1]
+        r = b * per
+        pooled = _RoIAlignNHWC.apply(base, rois.view(-1, 5).contiguous())     # [R,7,7,1024]
+        fc7 = self.head_to_tail(pooled)
+        bbox_pred = self.lin(fc7, "RCNN_bbox_pred")
+        sc_pos = self.rcnn_head(pooled, sup_pooled[:, 0], per)                # dana.py:189-194
+        sc_neg = self.rcnn_head(pooled, sup_pooled[:, 1], per)
+        cls_score = torch.cat([sc_pos, sc_neg], 0)
+        cls_prob = F.softmax(cls_score.detach(), 1)
+        labels = lab_s.view(-1).long()
+        rois_label = torch.cat([labels, torch.zeros_like(labels)], 0)         # dana.py:195-196
+        loss_bbox = self.smooth_l1(bbox_pred, tgt_s.view(r, 4), inw_s.view(r, 4), outw_s.view(r, 4), 1.0, (1,))
+        loss_cls = self.rcnn_cls_loss(cls_score, rois_label)
+        return rois, cls_prob, bbox_pred.detach(), rpn_loss_cls, rpn_loss_box, loss_cls, loss_bbox, rois_label

@@ -311,6 +311,32 @@ int dana_rcnn_losses(const float* cls_scores, const float* labels, int rois, con
  * dana_depthwise_xcorr  F.conv2d(feat, kernel.view(C,1,kh,kw), groups=C), no padding: NHWC pair [B,h,w,C] and a
  *                     per-image kernel fp32 [B][kh*kw][C] -> [B,h-kh+1,w-kw+1,C] as fp32 (out) and / or bf16 pair. */
 int dana_group_mean(const float* in, int groups, int k, int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backward pass (training step, BASELINE configs[3]).  The gradient GEMMs run on dana_conv_gemm: the data-gradient of
+ * a convolution is the same implicit GEMM with transposed / rotated weights; the weight-gradient
+ *     dW[co][tap][ci] = sum_p g[p][co] * x[p + tap][ci]
+ * is a K-major GEMM over the pixel index on channel-major operands, which the two layout kernels below write.
+ * Together they replace the cuDNN backward-data / backward-filter calls that torch.autograd issues for
+ * lib/model/framework/resnet.py:66-102 and dana.py:120-151,244-290 under train.py:138 (loss.backward()).
+ *
+ * dana_grad_prepare   g' = grad * (relu_out > 0) (relu_out NULL: no mask) on fp32 [pixels][channels].
+ *                     Any of: out_f32 (masked gradient, the residual branch's share), out_hi/out_lo (NHWC bf16 pair,
+ *                     operand of the data-gradient), t_hi/t_lo (channel-major pair [channels][t_pitch], t_pitch % 8 == 0,
+ *                     t_pitch >= pixels; operand of the weight-gradient).
+ * dana_im2col_t       channel-major im2col of an NHWC bf16 pair x[batch][height][width][channels] (element strides,
+ *                     channel stride 1, channels % 8 == 0): t[(tap*channels + c)][(n*OH + oy)*OW + ox] =
+ *                     x[n][oy*s + r - pad][ox*s + t - pad][c], zero outside.  ksize 1 (any stride s) or 3 (s = 1, pad 1).
+ * dana_sgd_momentum   torch.optim.SGD.step with momentum (train.py:89,139) on a flat fp32 buffer:
+ *                     d = grad*grad_scale + weight_decay*p;  m = momentum*m + d;  p -= lr*m.
+ */
+int dana_grad_prepare(const float* grad, const float* relu_out, int64_t pixels, int channels, float* out_f32,
+                      void* out_hi, void* out_lo, void* t_hi, void* t_lo, int64_t t_pitch, void* stream);
+int dana_im2col_t(const void* x_hi, const void* x_lo, int batch, int height, int width, int channels, int64_t stride_n,
+                  int64_t stride_y, int64_t stride_x, int ksize, int conv_stride, void* t_hi, void* t_lo, int64_t t_pitch,
+                  void* stream);
+int dana_sgd_momentum(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                      float weight_decay, float grad_scale, void* stream);
 int dana_depthwise_xcorr(const void* in_hi, const void* in_lo, int batch, int h, int w, int c, const float* kernel,
                          int kh, int kw, float* out, void* out_hi, void* out_lo, void* stream);
 

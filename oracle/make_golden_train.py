@@ -47,12 +47,38 @@ def main():
     np.random.seed(tc["np_seed"])
     with torch.no_grad():
         rois, cls_prob, bbox_pred, l1, l2, l3, l4, rois_label = net(im, info, gt, nb, sup)
+    # the training step's gradients (train.py:129-138: sum of the four losses, backward): per-parameter L2 norm and 16
+    # evenly spaced elements of every trainable tensor -- pins the oracle's autograd and, through it, the CUDA backward
+    # The reference has no CPU RoIAlign backward (csrc/ROIAlign.h:44 raises "Not implemented on the CPU"): that ONE
+    # operator is substituted by the exact adjoint of its (linear) forward, taken from torchvision's roi_align with the
+    # same sampling rules (aligned=False); everything else in the backward is the reference's own autograd graph.
+    import torchvision
+
+    def roi_align_backward_cpu(grad, rois, scale, ph, pw, bs, ch, h, w, ratio):
+        with torch.enable_grad():          # the caller is @once_differentiable
+            x = torch.zeros(bs, ch, h, w, dtype=grad.dtype, requires_grad=True)
+            o = torchvision.ops.roi_align(x, rois, (ph, pw), scale, ratio, False)
+            return torch.autograd.grad(o, x, grad)[0].detach()
+    model._C.roi_align_backward = roi_align_backward_cpu
+    np.random.seed(tc["np_seed"])
+    net.zero_grad()
+    out = net(im, info, gt, nb, sup)
+    (out[3].mean() + out[4].mean() + out[5].mean() + out[6].mean()).backward()
+    g_names, g_norms, g_samples = [], [], []
+    for name, prm in net.named_parameters():
+        if prm.requires_grad:
+            assert prm.grad is not None, name
+            g = prm.grad.detach().double().reshape(-1)
+            g_names.append(name)
+            g_norms.append(float(g.norm()))
+            g_samples.append(g[torch.linspace(0, g.numel() - 1, 16).long()].numpy())
     lab = cap["rpn_targets"][0]
     np.savez_compressed(os.path.join(GOLD, "forward_train_small.npz"), rois=rois.numpy(), cls_prob=cls_prob.numpy(),
                         bbox_pred=bbox_pred.numpy(), rois_label=rois_label.numpy(),
                         losses=np.array([float(l1), float(l2), float(l3), float(l4)], dtype=np.float64),
                         rpn_labels=lab.numpy().astype(np.int8), rpn_bbox_targets_abs_sum=float(cap["rpn_targets"][1].abs().sum()),
-                        rpn_outside_sum=float(cap["rpn_targets"][3].sum()))
+                        rpn_outside_sum=float(cap["rpn_targets"][3].sum()), grad_names=np.array(g_names),
+                        grad_norms=np.array(g_norms), grad_samples=np.stack(g_samples))
     print("losses", float(l1), float(l2), float(l3), float(l4), "fg rois", int(rois_label.sum()),
           "rpn fg/bg", int((lab == 1).sum()), int((lab == 0).sum()))
 

@@ -245,7 +245,8 @@ def dana_forward_train(p, im_data, im_info, gt_boxes, num_boxes, support_ims, n_
     prob = F.softmax(cls_score.view(b, 2, num_a * fh, fw), 1).view(b, 2 * num_a, fh, fw)
     bbox = F.conv2d(x, p["RCNN_rpn.RPN_bbox_pred.weight"], p["RCNN_rpn.RPN_bbox_pred.bias"])
     t = TRAIN_CFG
-    rois = O.proposal_layer(prob, bbox, im_info, base_anchors, c["feat_stride"], t["rpn_pre_nms_top_n"],
+    # the proposal layer works on .data (proposal_layer.py:61-62): no gradient through the boxes
+    rois = O.proposal_layer(prob.detach(), bbox.detach(), im_info, base_anchors, c["feat_stride"], t["rpn_pre_nms_top_n"],
                             t["rpn_post_nms_top_n"], t["rpn_nms_thresh"], nms_fn)
     all_rois = rois
     targets = anchor_target_layer(fh, fw, gt_boxes, im_info, torch.from_numpy(base_anchors).float(), c["feat_stride"])

@@ -120,3 +120,70 @@ def test_eval_after_train_mode_still_works(train_ref):
     net.eval()
     out_e = net(im.cuda(), info.cuda(), gt.cuda(), nb.cuda(), sup[:, :MT.TRAIN_CASE["n_shot"]].contiguous().cuda())
     assert out_e[3:7] == (0, 0, 0, 0) and out_e[7] is None
+
+
+def _tv_roi_align(feat, rois, scale, ph, pw, ratio):
+    """Differentiable RoIAlign with the reference's sampling rules (aligned=False) for the oracle's autograd pass; the
+    oracle's own forward is the C restatement, which has no graph."""
+    import torchvision
+    return torchvision.ops.roi_align(feat, rois, (ph, pw), scale, ratio, False)
+
+
+def test_train_backward_vs_oracle_and_reference_golden(train_ref, golden_dir):
+    """loss.backward() of the training step (train.py:129-138): every trainable parameter's gradient from the CUDA
+    path (tcgen05 data- / weight-gradient GEMMs, RoIAlign backward kernel) against (i) autograd of the CPU oracle on
+    the same sampled RoIs, normwise per tensor, and (ii) the gradient norms / sampled elements recorded from the
+    UNMODIFIED reference's own backward (oracle/make_golden_train.py)."""
+    p, (im, info, gt, nb, sup), ref = train_ref
+    tc = MT.TRAIN_CASE
+    net = _net(p, tc["n_shot"], "bf16x3")
+    trainable = [n for n, q in net.named_parameters() if q.requires_grad]
+    po = {k: v.clone() for k, v in p.items()}
+    for n in trainable:
+        po[n].requires_grad_(True)
+    np.random.seed(tc["np_seed"])
+    o = T.dana_forward_train(po, im, info, gt, nb, sup, tc["n_shot"], roi_align_fn=_tv_roi_align)
+    (o["rpn_loss_cls"] + o["rpn_loss_box"] + o["RCNN_loss_cls"] + o["RCNN_loss_bbox"]).backward()
+
+    np.random.seed(tc["np_seed"])
+    out = net._forward_train_graph(im.cuda(), info.cuda(), gt.cuda(), nb.cuda(), sup.cuda(),
+                                   teacher={"rois": ref["all_rois"].cuda()})
+    assert torch.equal(out[0].cpu(), ref["rois"]) and torch.equal(out[7].cpu(), ref["rois_label"])
+    losses = out[3:7]
+    want = [float(ref[k]) for k in ("rpn_loss_cls", "rpn_loss_box", "RCNN_loss_cls", "RCNN_loss_bbox")]
+    for g, w in zip(losses, want):
+        assert abs(float(g) - w) <= 2e-4 * abs(w), ([float(v) for v in losses], want)
+    (losses[0].mean() + losses[1].mean() + losses[2].mean() + losses[3].mean()).backward()
+
+    named = dict(net.named_parameters())
+    worst, errs = (0.0, None), []
+    # biases that cancel analytically (softmax over positions, mean-centering) have pure rounding-noise gradients:
+    # errors are measured against max(norm of the tensor's gradient, 1e-6 of the largest gradient norm)
+    floor = 1e-6 * max(float(po[n].grad.double().norm()) for n in trainable)
+    for n in trainable:
+        g_ref = po[n].grad
+        assert g_ref is not None, n
+        g = named[n].grad
+        assert g is not None, "no gradient reached %s" % n
+        err = float((g.detach().cpu().double() - g_ref.double()).norm() / g_ref.double().norm().clamp_min(floor))
+        worst = max(worst, (err, n))
+        errs.append((err, n))
+    print("gradient errors vs oracle autograd, ten largest:", ["%.1e %s" % e for e in sorted(errs, reverse=True)[:10]])
+    print("median %.1e" % sorted(errs)[len(errs) // 2][0])
+    assert worst[0] <= 5e-3, worst
+    # frozen tensors get no gradient (dana.py:350-368)
+    for n, q in net.named_parameters():
+        if not q.requires_grad:
+            assert q.grad is None, n
+
+    gold = np.load(os.path.join(golden_dir, "forward_train_small.npz"))
+    names = [str(s) for s in gold["grad_names"]]
+    assert sorted(names) == sorted(trainable)
+    for i, n in enumerate(names):
+        g = named[n].grad.detach().cpu().double().reshape(-1)
+        assert abs(float(g.norm()) - gold["grad_norms"][i]) <= 1e-3 * gold["grad_norms"][i] + floor, n
+        smp = g[torch.linspace(0, g.numel() - 1, 16).long()].numpy()
+        assert np.abs(smp - gold["grad_samples"][i]).max() <= 1e-3 * max(np.abs(gold["grad_samples"][i]).max(),
+                                                                          0.05 * gold["grad_norms"][i]) + floor, n
+    from dana_b200 import ops
+    assert ops.device_error() == 0

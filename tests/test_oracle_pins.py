@@ -226,6 +226,35 @@ def test_train_forward_vs_reference(golden_dir):
     assert tuple(out["rois"].shape) == (2, 128, 5) and tuple(out["cls_prob"].shape) == (512, 2)
 
 
+def test_train_backward_vs_reference(golden_dir):
+    """Autograd of the oracle's training forward against the gradients of the UNMODIFIED reference's own
+    loss.backward() (oracle/make_golden_train.py: per-parameter norms and 16 sampled elements; the reference's missing
+    CPU RoIAlign backward is the one substituted operator, documented there)."""
+    import make_golden_train as MT
+    import torchvision
+    import train_oracle as T
+    g = _g(golden_dir, "forward_train_small.npz")
+    tc = MT.TRAIN_CASE
+    p = O.make_params(tc["seed"], attn_std=tc["attn_std"])
+    names = [str(s) for s in g["grad_names"]]
+    for n in names:
+        p[n].requires_grad_(True)
+    im, info, gt, nb, sup = MT.train_inputs()
+    np.random.seed(tc["np_seed"])
+    out = T.dana_forward_train(p, im, info, gt, nb, sup, tc["n_shot"],
+                               roi_align_fn=lambda f, r, s, ph, pw, q: torchvision.ops.roi_align(f, r, (ph, pw), s, q, False))
+    (out["rpn_loss_cls"] + out["rpn_loss_box"] + out["RCNN_loss_cls"] + out["RCNN_loss_bbox"]).backward()
+    assert len(names) == 70 and not any(n.startswith(("RCNN_base.0.", "RCNN_base.1.", "RCNN_base.4.")) or ".bn" in n for n in names)
+    # biases that cancel analytically (softmax over positions / mean-centering: unary, channel and q / k projection
+    # biases) have gradients of pure rounding noise: compared on the absolute scale of the largest gradient
+    tiny = 1e-7 * float(g["grad_norms"].max())
+    for i, n in enumerate(names):
+        gr = p[n].grad.double().reshape(-1)
+        assert abs(float(gr.norm()) - g["grad_norms"][i]) <= 1e-4 * g["grad_norms"][i] + tiny, n
+        smp = gr[torch.linspace(0, gr.numel() - 1, 16).long()].numpy()
+        np.testing.assert_allclose(smp, g["grad_samples"][i], rtol=1e-3, atol=1e-4 * g["grad_norms"][i] + tiny, err_msg=n)
+
+
 def test_train_target_layers_edge_cases():
     """Target layers on hand-made inputs: zero-padded gt columns never match, an anchor that is the best for a gt is
     positive even below the threshold, images without positives contribute no regression weight."""
