@@ -120,6 +120,9 @@ SIGNATURES = {
                                   c_int64, c_void_p]),
     "dana_im2col_t": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int,
                               c_void_p, c_void_p, c_int64, c_void_p]),
+    "dana_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    "dana_unpack_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dana_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_void_p]),
 }
 

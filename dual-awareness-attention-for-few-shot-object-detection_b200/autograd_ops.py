@@ -28,28 +28,21 @@ def begin_step():
     _W_CACHE.clear()
 
 
-def _packed(w, scale):
-    """Packed operand planes of a conv / linear weight [Cout, Cin, k, k] with the frozen-BN scale folded in."""
+def _packed(w, scale, need_dgrad=True):
+    """Packed operand planes of a conv / linear weight [Cout, Cin, k, k] with the frozen-BN scale folded in: the
+    forward / weight-gradient layout and the rotated data-gradient layout, one kernel (dana_pack_conv_weight)."""
     key = (w.data_ptr(), w._version, 0 if scale is None else scale.data_ptr())
     ent = _W_CACHE.get(key)
     if ent is None:
-        with torch.no_grad():
-            wf = w.detach().float()
-            if scale is not None:
-                wf = wf * scale.view(-1, 1, 1, 1)
-            co, ci, kh, kw = wf.shape
-            ent = {"wf": wf, "fwd": Pair.from_float(wf.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous())}
+        fwd, dg = ops.pack_conv_weight(w.detach().float(), scale, want_dgrad=need_dgrad)
+        ent = {"fwd": fwd, "dgrad": dg, "w": w}
         _W_CACHE[key] = ent
     return ent
 
 
-def _dgrad_weight(ent):
-    if "dgrad" not in ent:
-        wf = ent["wf"]
-        co, ci, kh, kw = wf.shape
-        # dx[p][ci] = sum_{tap,co} g[p - tap][co] W[co][ci][tap]: a convolution of g with the 180-degree rotated kernel
-        wr = wf.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, kh * kw * co).contiguous()
-        ent["dgrad"] = Pair.from_float(wr)
+def _dgrad_weight(ent, scale):
+    if ent["dgrad"] is None:
+        ent["dgrad"] = ops.pack_conv_weight(ent["w"].detach().float(), scale, want_dgrad=True)[1]
     return ent["dgrad"]
 
 
@@ -65,7 +58,7 @@ class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, res, scale, relu, ksize, stride, xp, rp):
         global _LAST_PAIR
-        ent = _packed(w, scale)
+        ent = _packed(w, scale, need_dgrad=ctx.needs_input_grad[0])
         n, h, wd, ci = x.shape
         co = w.shape[0]
         oh, ow = (h, wd) if ksize == 3 else ((h - 1) // stride + 1, (wd - 1) // stride + 1)
@@ -99,7 +92,7 @@ class _ConvFn(torch.autograd.Function):
         if need_b:
             db = gf.sum(dim=(0, 1, 2))
         if need_x:
-            wd_pair = _dgrad_weight(ent)
+            wd_pair = _dgrad_weight(ent, ctx.scale)
             if stride == 1:
                 dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=gy.device)
                 ops.conv_nhwc(gp, wd_pair, ci, ksize=ksize, stride=1, out_f32=dx)
@@ -110,9 +103,7 @@ class _ConvFn(torch.autograd.Function):
             xt = ops.im2col_t(ctx.xp, ksize, stride)                      # [taps*ci, pixels]
             dwk = torch.empty((co, ksize * ksize * ci), dtype=torch.float32, device=gy.device)
             ops.linear(gt, xt, ksize * ksize * ci, out_f32=dwk)
-            dw = dwk.view(co, ksize, ksize, ci).permute(0, 3, 1, 2)
-            if ctx.scale is not None:
-                dw = dw * ctx.scale.view(-1, 1, 1, 1)
+            dw = ops.unpack_conv_wgrad(dwk, ctx.scale, co, ci, ksize, ksize)
         return dx, dw, db, dr, None, None, None, None, None, None
 
 

@@ -198,6 +198,56 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
   }
 }
 
+// Operand planes of a convolution weight w[co][ci][r][s] (fp32, frozen-BN scale folded in) for both GEMMs that read it:
+//   forward / weight-gradient layout  f[co][(r*kw + s)*ci_n + ci] = w[co][ci][r][s] * scale[co]
+//   data-gradient layout              d[ci][(r*kw + s)*co_n + co] = w[co][ci][kh-1-r][kw-1-s] * scale[co]   (rotated kernel)
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, int co_n, int ci_n,
+                                        int kh, int kw, __nv_bfloat16* __restrict__ fh, __nv_bfloat16* __restrict__ fl,
+                                        __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dl) {
+  const long long total = static_cast<long long>(co_n) * ci_n * kh * kw;
+  const int taps = kh * kw;
+  const bool dgrad = blockIdx.y == 1;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int co, ci, tap;
+    if (!dgrad) {
+      ci = static_cast<int>(i % ci_n);
+      tap = static_cast<int>((i / ci_n) % taps);
+      co = static_cast<int>(i / (static_cast<long long>(ci_n) * taps));
+    } else {
+      co = static_cast<int>(i % co_n);
+      tap = taps - 1 - static_cast<int>((i / co_n) % taps);          // 180-degree rotation
+      ci = static_cast<int>(i / (static_cast<long long>(co_n) * taps));
+    }
+    float v = w[(static_cast<long long>(co) * ci_n + ci) * taps + tap];
+    if (scale != nullptr) v *= scale[co];
+    __nv_bfloat16 h, l;
+    split2(v, h, l);
+    if (!dgrad) {
+      fh[i] = h;
+      fl[i] = l;
+    } else {
+      dh[i] = h;
+      dl[i] = l;
+    }
+  }
+}
+
+// dW[co][ci][r][s] = g[co][(r*kw + s)*ci_n + ci] * scale[co]: the weight-gradient GEMM's output back in the parameter's layout
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ scale, int co_n, int ci_n,
+                                         int taps, float* __restrict__ dw) {
+  const long long total = static_cast<long long>(co_n) * ci_n * taps;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % taps);
+    const int ci = static_cast<int>((i / taps) % ci_n);
+    const int co = static_cast<int>(i / (static_cast<long long>(taps) * ci_n));
+    float v = g[(static_cast<long long>(co) * taps + tap) * ci_n + ci];
+    if (scale != nullptr) v *= scale[co];
+    dw[i] = v;
+  }
+}
+
 inline bool al(const void* q, int a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; }
 
 }  // namespace
@@ -248,6 +298,35 @@ int dana_im2col_t(const void* x_hi, const void* x_lo, int batch, int height, int
   const dim3 grid(static_cast<unsigned>((pixels + kTP - 1) / kTP), static_cast<unsigned>((channels + kTC - 1) / kTC),
                   static_cast<unsigned>(ksize * ksize));
   im2col_t_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
+int dana_pack_conv_weight(const float* weight, const float* scale, int out_channels, int in_channels, int kh, int kw,
+                          void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* dgrad_lo, void* stream) {
+  if (!weight || !fwd_hi || !fwd_lo || out_channels <= 0 || in_channels <= 0 || kh <= 0 || kw <= 0) return DANA_EINVAL;
+  if ((dgrad_hi == nullptr) != (dgrad_lo == nullptr)) return DANA_EINVAL;
+  const long long total = static_cast<long long>(out_channels) * in_channels * kh * kw;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  const dim3 grid(static_cast<unsigned>(blocks), dgrad_hi ? 2 : 1);
+  pack_conv_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      weight, scale, out_channels, in_channels, kh, kw, static_cast<__nv_bfloat16*>(fwd_hi),
+      static_cast<__nv_bfloat16*>(fwd_lo), static_cast<__nv_bfloat16*>(dgrad_hi), static_cast<__nv_bfloat16*>(dgrad_lo));
+  DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
+int dana_unpack_conv_wgrad(const float* wgrad, const float* scale, int out_channels, int in_channels, int taps,
+                           float* weight_grad, void* stream) {
+  if (!wgrad || !weight_grad || out_channels <= 0 || in_channels <= 0 || taps <= 0) return DANA_EINVAL;
+  const long long total = static_cast<long long>(out_channels) * in_channels * taps;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  unpack_conv_wgrad_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      wgrad, scale, out_channels, in_channels, taps, weight_grad);
   DANA_LAUNCH_CHECK();
   return DANA_OK;
 }

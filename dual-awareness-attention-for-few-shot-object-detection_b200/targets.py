@@ -67,6 +67,16 @@ def regression_targets(ex, gt):
     return np.stack([(gcx - ecx) / ew, (gcy - ecy) / eh, np.log(gw / ew), np.log(gh / eh)], -1).astype(F32)
 
 
+def _used_columns(gt):
+    """Number of leading ground-truth columns that hold a box in at least one image.  The trailing zero padding
+    (gt_boxes is padded to MAX_NUM_GT_BOXES = 50) scores 0 against everything (-1 against zero-area rows), so
+    leaving it out changes neither the row maxima / argmaxima nor the per-column tests -- it only spares the host
+    50 columns of IoU arithmetic for the 1-8 boxes an image has."""
+    real = ((gt[:, :, 2] - gt[:, :, 0] != 0) | (gt[:, :, 3] - gt[:, :, 1] != 0)).any(0)
+    idx = np.nonzero(real)[0]
+    return int(idx[-1]) + 1 if idx.size else 1
+
+
 def anchor_targets(feat_h, feat_w, gt_boxes, im_info, base_anchors, feat_stride=16, *, negative_overlap=0.3,
                    positive_overlap=0.7, clobber_positives=False, fg_fraction=0.5, batchsize=256, inside_weight=1.0,
                    positive_weight=-1.0, allowed_border=0):
@@ -85,7 +95,7 @@ def anchor_targets(feat_h, feat_w, gt_boxes, im_info, base_anchors, feat_stride=
     anchors = all_anchors[inside]
     n_in = inside.size
     labels = np.full((b, n_in), -1, dtype=np.int8)
-    ov = overlaps_batch(anchors, gt)                                   # [B, n_in, G]
+    ov = overlaps_batch(anchors, gt[:, :_used_columns(gt)])            # [B, n_in, G']
     max_ov = ov.max(2)
     argmax_ov = ov.argmax(2)
     gt_max = ov.max(1)                                                 # [B, G]
@@ -142,7 +152,7 @@ def proposal_targets(all_rois, gt_boxes, *, rois_per_image=128, fg_fraction=0.25
     rois_all = np.concatenate([rois_in, app], 1)                       # the ground-truth boxes join the candidates (:44)
     rpi = int(rois_per_image)
     fg_rpi = int(np.round(fg_fraction * rpi)) or 1
-    ov = overlaps_batch(rois_all[:, :, 1:5], gt)
+    ov = overlaps_batch(rois_all[:, :, 1:5], gt[:, :_used_columns(gt)])
     max_ov = ov.max(2)
     assign = ov.argmax(2)
     labels = np.take_along_axis(gt[:, :, 4], assign, 1)

@@ -335,6 +335,15 @@ int dana_grad_prepare(const float* grad, const float* relu_out, int64_t pixels, 
 int dana_im2col_t(const void* x_hi, const void* x_lo, int batch, int height, int width, int channels, int64_t stride_n,
                   int64_t stride_y, int64_t stride_x, int ksize, int conv_stride, void* t_hi, void* t_lo, int64_t t_pitch,
                   void* stream);
+/* dana_pack_conv_weight    operand planes of an fp32 weight w[co][ci][kh][kw] (x scale[co], the frozen-BN fold; NULL: none)
+ *                          for the forward / weight-gradient GEMM  f[co][(r*kw+s)*ci_n + ci]  and (dgrad_* non-NULL) for the
+ *                          data-gradient GEMM  d[ci][(r*kw+s)*co_n + co] = w[co][ci][kh-1-r][kw-1-s] * scale[co].
+ * dana_unpack_conv_wgrad   dW[co][ci][tap] = wgrad[co][tap*ci_n + ci] * scale[co]: the weight-gradient GEMM's output in the
+ *                          parameter's own layout (what torch.autograd accumulates into .grad). */
+int dana_pack_conv_weight(const float* weight, const float* scale, int out_channels, int in_channels, int kh, int kw,
+                          void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* dgrad_lo, void* stream);
+int dana_unpack_conv_wgrad(const float* wgrad, const float* scale, int out_channels, int in_channels, int taps,
+                           float* weight_grad, void* stream);
 int dana_sgd_momentum(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                       float weight_decay, float grad_scale, void* stream);
 int dana_depthwise_xcorr(const void* in_hi, const void* in_lo, int batch, int h, int w, int c, const float* kernel,
