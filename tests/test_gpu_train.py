@@ -187,3 +187,52 @@ def test_train_backward_vs_oracle_and_reference_golden(train_ref, golden_dir):
                                                                           0.05 * gold["grad_norms"][i]) + floor, n
     from dana_b200 import ops
     assert ops.device_error() == 0
+
+
+def test_sgd_trainer_steps_match_torch_optim(train_ref):
+    """SGDTrainer (flat arenas + dana_sgd_momentum, train_step.py) against torch.optim.SGD with train.py:78-89's
+    parameter groups on a twin module: two steps (momentum in play), same gradients path, parameters must agree to the
+    rounding of the update."""
+    from dana_b200.config import cfg
+    from dana_b200.train_step import SGDTrainer
+    p, (im, info, gt, nb, sup), ref = train_ref
+    tc = MT.TRAIN_CASE
+    a, b = _net(p, tc["n_shot"], "bf16x3"), _net(p, tc["n_shot"], "bf16x3")
+    args = [t.cuda() for t in (im, info, gt, nb, sup)]
+    # proposals are teacher-forced on both modules: after the first update the two differ by rounding (atomics in the
+    # RoIAlign backward), which must not flip an NMS decision and with it the sampled RoIs
+    for net in (a, b):
+        net.forward = (lambda n: lambda *t: n._forward_train_graph(*t, teacher={"rois": ref["all_rois"].cuda()}))(net)
+    lr = 0.01
+    tr = SGDTrainer(a, lr=lr)
+    groups = []
+    for name, q in b.named_parameters():
+        if q.requires_grad:
+            if "bias" in name:
+                groups.append({"params": [q], "lr": lr * (cfg.TRAIN.DOUBLE_BIAS + 1),
+                               "weight_decay": cfg.TRAIN.BIAS_DECAY and cfg.TRAIN.WEIGHT_DECAY or 0})
+            else:
+                groups.append({"params": [q], "lr": lr, "weight_decay": cfg.TRAIN.WEIGHT_DECAY})
+    opt = torch.optim.SGD(groups, momentum=cfg.TRAIN.MOMENTUM)
+    for step in range(2):
+        np.random.seed(11 + step)
+        loss_a, _ = tr.step(*args)
+        np.random.seed(11 + step)
+        out = b(*args)
+        loss_b = out[3].mean() + out[4].mean() + out[5].mean() + out[6].mean()
+        opt.zero_grad()
+        loss_b.backward()
+        opt.step()
+        assert abs(float(loss_a) - float(loss_b.detach())) <= 1e-4 * abs(float(loss_b.detach())), (step, float(loss_a), float(loss_b.detach()))
+    start = dict(_net(p, tc["n_shot"], "bf16x3").named_parameters())
+    moved = 0
+    for (name, qa), (_, qb) in zip(a.named_parameters(), b.named_parameters()):
+        if not qa.requires_grad:
+            assert torch.equal(qa, qb)
+            continue
+        upd = (qb.detach() - start[name].detach()).abs().max().item()
+        moved += upd > 0
+        # a few ulp of the parameter, plus the second step's gradients differing at the 1e-3 level once the two modules differ by
+        # rounding (ReLU masks of near-zero pre-activations flip); a wrong lr / decay / momentum would be off by >= 10 %
+        assert (qa.detach() - qb.detach()).abs().max().item() <= 1e-2 * upd + 5e-7 * qb.detach().abs().max().item() + 1e-9, name
+    assert moved > 60

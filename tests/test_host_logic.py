@@ -239,6 +239,65 @@ def test_bucketed_grad_allreduce_gloo_world2():
     assert q.get(timeout=10) is True
 
 
+def _arena_sync_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import dana_b200  # noqa: F401
+    from dana_b200.train_step import ArenaGradAllReduce, ParamArena
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                        # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.ReLU(), torch.nn.Linear(64, 19), torch.nn.ReLU(),
+                              torch.nn.Linear(19, 3))
+    before = [p.detach().clone() for p in net.parameters()]
+    named = [(n, p) for n, p in net.named_parameters()]
+    named.reverse()
+    arenas = [ParamArena([(n, p) for n, p in named if "bias" not in n], 0.1, 0.0, 200),
+              ParamArena([(n, p) for n, p in named if "bias" in n], 0.2, 0.0, 64)]
+    ok = all(torch.equal(a, b) for a, b in zip(before, net.parameters()))          # values moved into the arena intact
+    ok = ok and len(arenas[0].buckets) >= 2 and all(o % 4 == 0 for a in arenas for o in a.offsets)
+    sync = ArenaGradAllReduce(arenas)
+    g = torch.Generator().manual_seed(100 + rank)                # different data per rank
+    x, y = torch.randn(8, 37, generator=g), torch.randn(8, 3, generator=g)
+    for step in range(2):                                        # twice: arm / finish are per step, grads re-zeroed
+        for a in arenas:
+            a.rebind_grads()
+            a.grad.zero_()
+        sync.arm()
+        ((net(x) - y) ** 2).mean().backward()
+        sync.finish()
+        # every parameter's .grad is still an arena slice and holds the SUM over ranks (1/world goes into the SGD kernel)
+        ref = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.ReLU(), torch.nn.Linear(64, 19), torch.nn.ReLU(),
+                                  torch.nn.Linear(19, 3))
+        ref.load_state_dict(net.state_dict())
+        ((ref(x) - y) ** 2).mean().backward()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            t = q.grad.clone()
+            dist.all_reduce(t)
+            ok = ok and torch.allclose(p.grad, t, rtol=0, atol=1e-6)
+            ok = ok and any(a.grad.data_ptr() <= p.grad.data_ptr() < a.grad.data_ptr() + 4 * a.total for a in arenas)
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_arena_grad_allreduce_gloo_world2():
+    """The training step's collective as shipped (train_step.py): gradients accumulate straight into flat arenas, whose
+    contiguous bucket ranges are all-reduced from post-accumulate hooks in bucket order -- equals a per-parameter
+    all-reduce sum; parameter values survive the move into the arena."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 1000
+    procs = [ctx.Process(target=_arena_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
+
+
 # ------------------------------------------------------------------ training target layers (host side, row a15)
 @pytest.mark.parametrize("seed,n_gt,hw", [(0, 1, (10, 14)), (1, 3, (38, 63)), (2, 8, (25, 40)), (3, 0, (12, 12))])
 def test_target_layers_match_oracle(seed, n_gt, hw):
