@@ -60,6 +60,20 @@ class CisaArgs(Structure):
     ]
 
 
+class ConvBwdArgs(ctypes.Structure):
+    """dana_conv_bwd_args (include/dana_b200.h)."""
+    _fields_ = [
+        ("batch", c_int32), ("height", c_int32), ("width", c_int32), ("in_channels", c_int32), ("out_channels", c_int32),
+        ("ksize", c_int32), ("stride", c_int32),
+        ("grad_out", c_void_p), ("relu_out", c_void_p), ("x_hi", c_void_p), ("x_lo", c_void_p),
+        ("x_sn", c_int64), ("x_sy", c_int64), ("x_sx", c_int64),
+        ("wd_hi", c_void_p), ("wd_lo", c_void_p), ("scale", c_void_p),
+        ("dx", c_void_p), ("dw", c_void_p), ("dres", c_void_p), ("dw_accumulate", c_int32),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("gemm_workspace", c_void_p), ("gemm_workspace_bytes", c_int64), ("sk_epoch", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header.
 SIGNATURES = {
     "dana_abi_version": (c_int, []),
@@ -122,7 +136,9 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_int64, c_void_p]),
     "dana_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
-    "dana_unpack_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dana_unpack_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "dana_conv_backward_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "dana_conv_backward": (c_int, [POINTER(ConvBwdArgs), c_void_p]),
     "dana_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_void_p]),
 }
 

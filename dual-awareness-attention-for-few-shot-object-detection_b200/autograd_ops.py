@@ -54,9 +54,24 @@ def pair_of(x):
     return p
 
 
+# Direct gradient sink (train_step.SGDTrainer): when set, the weight gradient of a LEAF parameter is accumulated by the
+# unpack kernel straight into `sink(param)` (its slice of the gradient arena) instead of travelling through
+# AccumulateGrad as a fresh tensor (one allocation + one add launch per use); `done(param)` is called once the last of
+# the parameter's uses of this step has written (what a post-accumulate hook would signal).
+_SINK = None
+_DONE = None
+_USES = {}
+
+
+def set_direct_grads(sink=None, done=None):
+    global _SINK, _DONE
+    _SINK, _DONE = sink, done
+    _USES.clear()
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, res, scale, relu, ksize, stride, xp, rp):
+    def forward(ctx, x, w, bias, res, scale, relu, ksize, stride, xp, rp, leaf):
         global _LAST_PAIR
         ent = _packed(w, scale, need_dgrad=ctx.needs_input_grad[0])
         n, h, wd, ci = x.shape
@@ -71,8 +86,10 @@ class _ConvFn(torch.autograd.Function):
         ops.conv_nhwc(xp, ent["fwd"], co, ksize=ksize, stride=stride, bias=None if bias is None else bias.detach(),
                       res=rp, relu=relu, out=yp, out_f32=y)
         ctx.ent, ctx.xp, ctx.relu, ctx.ksize, ctx.stride, ctx.scale = ent, xp, relu, ksize, stride, scale
-        ctx.x_shape = tuple(x.shape)
-        ctx.has_bias, ctx.has_res = bias is not None, res is not None
+        ctx.leaf = None
+        if leaf is not None and _SINK is not None and ctx.needs_input_grad[1] and _SINK(leaf) is not None:
+            ctx.leaf = leaf
+            _USES[id(leaf)] = _USES.get(id(leaf), 0) + 1
         ctx.save_for_backward(y if relu else None)
         _LAST_PAIR = yp
         return y
@@ -81,37 +98,29 @@ class _ConvFn(torch.autograd.Function):
     def backward(ctx, gy):
         (y,) = ctx.saved_tensors
         need_x, need_w, need_b, need_r = ctx.needs_input_grad[:4]
-        ent, ksize, stride = ctx.ent, ctx.ksize, ctx.stride
-        n, h, wd, ci = ctx.x_shape
-        co = gy.shape[-1]
-        want_f32 = (need_r and ctx.relu) or need_b
-        gf, gp, gt = ops.grad_prepare(gy, y, want_f32=want_f32, want_pair=need_x, want_t=need_w)
-        dx = dw = db = dr = None
-        if need_r:
-            dr = gf if ctx.relu else gy
-        if need_b:
-            db = gf.sum(dim=(0, 1, 2))
-        if need_x:
-            wd_pair = _dgrad_weight(ent, ctx.scale)
-            if stride == 1:
-                dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=gy.device)
-                ops.conv_nhwc(gp, wd_pair, ci, ksize=ksize, stride=1, out_f32=dx)
-            else:                                        # strided 1x1: only every stride-th pixel was read
-                dx = torch.zeros(ctx.x_shape, dtype=torch.float32, device=gy.device)
-                ops.conv_nhwc(gp, wd_pair, ci, ksize=1, stride=1, out_f32=dx[:, ::stride, ::stride, :])
-        if need_w:
-            xt = ops.im2col_t(ctx.xp, ksize, stride)                      # [taps*ci, pixels]
-            dwk = torch.empty((co, ksize * ksize * ci), dtype=torch.float32, device=gy.device)
-            ops.linear(gt, xt, ksize * ksize * ci, out_f32=dwk)
-            dw = ops.unpack_conv_wgrad(dwk, ctx.scale, co, ci, ksize, ksize)
-        return dx, dw, db, dr, None, None, None, None, None, None
+        want_dres = (need_r and ctx.relu) or need_b
+        leaf = ctx.leaf
+        into = _SINK(leaf).view(gy.shape[-1], -1, ctx.ksize, ctx.ksize) if (leaf is not None and need_w) else None
+        dx, dw, gf = ops.conv_backward(gy, y, ctx.xp, _dgrad_weight(ctx.ent, ctx.scale) if need_x else None, ctx.scale,
+                                       ctx.ksize, ctx.stride, need_dx=need_x, need_dw=need_w, want_dres=want_dres,
+                                       dw_into=into)
+        if leaf is not None and need_w:
+            _USES[id(leaf)] -= 1
+            if _USES[id(leaf)] == 0 and _DONE is not None:
+                _DONE(leaf)
+        dr = (gf if ctx.relu else gy) if need_r else None
+        db = gf.sum(dim=(0, 1, 2)) if need_b else None
+        return dx, dw, db, dr, None, None, None, None, None, None, None
 
 
-def conv(x, w, bias=None, res=None, scale=None, relu=False, ksize=1, stride=1):
-    """y = relu?(conv(x, w * scale) + bias + res) on fp32 NHWC tensors; w [Cout, Cin, k, k]."""
+def conv(x, w, bias=None, res=None, scale=None, relu=False, ksize=1, stride=1, leaf=None):
+    """y = relu?(conv(x, w * scale) + bias + res) on fp32 NHWC tensors; w [Cout, Cin, k, k].  leaf: the Parameter behind
+    `w` when w is a reshaped view of it (nn.Linear weights), for the direct gradient sink."""
     xp = getattr(x, "_dana_pair", None)
     rp = None if res is None else getattr(res, "_dana_pair", None)
-    y = _ConvFn.apply(x, w, bias, res, scale, relu, ksize, stride, xp, rp)
+    if leaf is None and w.is_leaf:
+        leaf = w
+    y = _ConvFn.apply(x, w, bias, res, scale, relu, ksize, stride, xp, rp, leaf)
     y._dana_pair = _LAST_PAIR
     return y
 
@@ -130,7 +139,7 @@ def linear(x, w, bias=None, relu=False):
     x4 = x.reshape(1, 1, -1, x.shape[-1])
     if hasattr(x, "_dana_pair") and x.is_contiguous():
         x4._dana_pair = x._dana_pair.view(*x4.shape)
-    y = conv(x4, w.view(w.shape[0], w.shape[1], 1, 1), bias=bias, relu=relu)
+    y = conv(x4, w.view(w.shape[0], w.shape[1], 1, 1), bias=bias, relu=relu, leaf=w if (w.is_leaf and not pad) else None)
     out = y.view(*lead, w.shape[0])
     if pad:
         return out[..., :co]

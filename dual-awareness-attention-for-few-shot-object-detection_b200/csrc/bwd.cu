@@ -9,6 +9,7 @@
 // lib/model/framework/resnet.py:66-102, dana.py:120-151,244-290 (train.py:138 loss.backward()) and torch.optim.SGD.step
 // (train.py:89,139).
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "api_common.cuh"
 
@@ -235,7 +236,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float
 
 // dW[co][ci][r][s] = g[co][(r*kw + s)*ci_n + ci] * scale[co]: the weight-gradient GEMM's output back in the parameter's layout
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ scale, int co_n, int ci_n,
-                                         int taps, float* __restrict__ dw) {
+                                         int taps, float* __restrict__ dw, const bool accumulate) {
   const long long total = static_cast<long long>(co_n) * ci_n * taps;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -244,7 +245,7 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ g, const floa
     const int co = static_cast<int>(i / (static_cast<long long>(taps) * ci_n));
     float v = g[(static_cast<long long>(co) * taps + tap) * ci_n + ci];
     if (scale != nullptr) v *= scale[co];
-    dw[i] = v;
+    dw[i] = accumulate ? dw[i] + v : v;
   }
 }
 
@@ -319,15 +320,107 @@ int dana_pack_conv_weight(const float* weight, const float* scale, int out_chann
 }
 
 int dana_unpack_conv_wgrad(const float* wgrad, const float* scale, int out_channels, int in_channels, int taps,
-                           float* weight_grad, void* stream) {
+                           float* weight_grad, int accumulate, void* stream) {
   if (!wgrad || !weight_grad || out_channels <= 0 || in_channels <= 0 || taps <= 0) return DANA_EINVAL;
   const long long total = static_cast<long long>(out_channels) * in_channels * taps;
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   unpack_conv_wgrad_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      wgrad, scale, out_channels, in_channels, taps, weight_grad);
+      wgrad, scale, out_channels, in_channels, taps, weight_grad, accumulate != 0);
   DANA_LAUNCH_CHECK();
+  return DANA_OK;
+}
+
+// The whole backward of one convolution (+ frozen-BN fold + ReLU) in one call: mask / split / transpose of the incoming
+// gradient, data-gradient GEMM, transposing im2col of the saved input, weight-gradient GEMM, unpack (+ accumulate).
+static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+int64_t dana_conv_backward_workspace_bytes(int batch, int height, int width, int in_channels, int out_channels, int ksize,
+                                           int stride) {
+  if (batch <= 0 || height <= 0 || width <= 0 || in_channels <= 0 || out_channels <= 0 || ksize <= 0 || stride <= 0) return 256;
+  const int64_t oh = ksize == 3 ? height : (height - 1) / stride + 1, ow = ksize == 3 ? width : (width - 1) / stride + 1;
+  const int64_t pixels = static_cast<int64_t>(batch) * oh * ow, pitch = (pixels + 7) / 8 * 8, taps = ksize * ksize;
+  return 2 * align256(2 * pixels * out_channels) + 2 * align256(2 * out_channels * pitch) +
+         2 * align256(2 * taps * in_channels * pitch) + align256(4 * out_channels * taps * in_channels) + 256;
+}
+
+int dana_conv_backward(const dana_conv_bwd_args* a, void* stream) {
+  if (!a || !a->grad_out) return DANA_EINVAL;
+  if (a->batch <= 0 || a->height <= 0 || a->width <= 0 || a->in_channels <= 0 || a->out_channels <= 0) return DANA_EINVAL;
+  if (!((a->ksize == 1 && a->stride >= 1) || (a->ksize == 3 && a->stride == 1))) return DANA_ENOTSUP;
+  const int n = a->batch, ci = a->in_channels, co = a->out_channels, ks = a->ksize, taps = ks * ks;
+  const int oh = ks == 3 ? a->height : (a->height - 1) / a->stride + 1, ow = ks == 3 ? a->width : (a->width - 1) / a->stride + 1;
+  const int64_t pixels = static_cast<int64_t>(n) * oh * ow, pitch = (pixels + 7) / 8 * 8;
+  const bool need_dx = a->dx != nullptr, need_dw = a->dw != nullptr;
+  if (need_dx && (!a->wd_hi || !a->wd_lo)) return DANA_EINVAL;
+  if (need_dw && (!a->x_hi || !a->x_lo)) return DANA_EINVAL;
+  if (a->workspace_bytes < dana_conv_backward_workspace_bytes(n, a->height, a->width, ci, co, ks, a->stride) ||
+      (reinterpret_cast<uintptr_t>(a->workspace) & 255))
+    return DANA_EINVAL;
+  char* w = static_cast<char*>(a->workspace);
+  auto take = [&](int64_t bytes) { char* q = w; w += align256(bytes); return q; };
+  void* gp_hi = take(2 * pixels * co);
+  void* gp_lo = take(2 * pixels * co);
+  void* gt_hi = take(2 * co * pitch);
+  void* gt_lo = take(2 * co * pitch);
+  void* xt_hi = take(2 * static_cast<int64_t>(taps) * ci * pitch);
+  void* xt_lo = take(2 * static_cast<int64_t>(taps) * ci * pitch);
+  float* dwk = reinterpret_cast<float*>(take(4LL * co * taps * ci));
+  int rc = dana_grad_prepare(a->grad_out, a->relu_out, pixels, co, a->dres, need_dx ? gp_hi : nullptr,
+                             need_dx ? gp_lo : nullptr, need_dw ? gt_hi : nullptr, need_dw ? gt_lo : nullptr, pitch, stream);
+  if (rc != DANA_OK && (need_dx || need_dw || a->dres)) return rc;
+  dana_conv_gemm_args g;
+  if (need_dx) {
+    // dx[p][ci] = sum_{tap,co} g'[p - tap][co] W[co][ci][tap]: the forward kernel on the rotated weight planes; a strided
+    // 1x1 wrote only every stride-th input pixel, so its data-gradient lands on those pixels of a zeroed map
+    if (a->stride > 1) {
+      cudaError_t e = cudaMemsetAsync(a->dx, 0, 4LL * n * a->height * a->width * ci, static_cast<cudaStream_t>(stream));
+      if (e != cudaSuccess) return cuda_fail(e);
+    }
+    memset(&g, 0, sizeof(g));
+    g.a_hi = gp_hi, g.a_lo = gp_lo;
+    g.a_c = co, g.a_w = ow, g.a_h = oh, g.a_n = n;
+    g.a_sx = co, g.a_sy = static_cast<int64_t>(ow) * co, g.a_sn = static_cast<int64_t>(oh) * ow * co;
+    g.taps_r = g.taps_s = ks;
+    g.pad_y = g.pad_x = ks == 3 ? 1 : 0;
+    g.b_hi = a->wd_hi, g.b_lo = a->wd_lo;
+    g.b_pitch = static_cast<int64_t>(taps) * co;
+    g.n_out = ci;
+    g.out_w = ow, g.out_h = oh, g.out_n = n;
+    g.o_sx = static_cast<int64_t>(a->stride) * ci;
+    g.o_sy = static_cast<int64_t>(a->stride) * a->width * ci;
+    g.o_sn = static_cast<int64_t>(a->height) * a->width * ci;
+    g.out_f32 = a->dx;
+    g.alpha = 1.0f;
+    g.workspace = a->gemm_workspace, g.workspace_bytes = a->gemm_workspace_bytes, g.sk_epoch = a->sk_epoch;
+    rc = dana_conv_gemm(&g, stream);
+    if (rc != DANA_OK) return rc;
+  }
+  if (need_dw) {
+    rc = dana_im2col_t(a->x_hi, a->x_lo, n, a->height, a->width, ci, a->x_sn, a->x_sy, a->x_sx, ks, a->stride, xt_hi, xt_lo,
+                       pitch, stream);
+    if (rc != DANA_OK) return rc;
+    // dW'[co][tap*ci_n + ci] = sum_p g'^T[co][p] * x^T[tap*ci_n + ci][p]: rows = co, K = pixels
+    memset(&g, 0, sizeof(g));
+    g.a_hi = gt_hi, g.a_lo = gt_lo;
+    g.a_c = pixels, g.a_w = co, g.a_h = 1, g.a_n = 1;
+    g.a_sx = pitch, g.a_sy = pitch * co, g.a_sn = pitch * co;
+    g.taps_r = g.taps_s = 1;
+    g.b_hi = xt_hi, g.b_lo = xt_lo;
+    g.b_pitch = pitch;
+    g.n_out = taps * ci;
+    g.out_w = co, g.out_h = 1, g.out_n = 1;
+    g.o_sx = static_cast<int64_t>(taps) * ci, g.o_sy = g.o_sx * co, g.o_sn = g.o_sy;
+    g.out_f32 = dwk;
+    g.alpha = 1.0f;
+    g.workspace = a->gemm_workspace, g.workspace_bytes = a->gemm_workspace_bytes;
+    g.sk_epoch = a->sk_epoch ? a->sk_epoch + 1 : 0;
+    rc = dana_conv_gemm(&g, stream);
+    if (rc != DANA_OK) return rc;
+    rc = dana_unpack_conv_wgrad(dwk, a->scale, co, ci, taps, a->dw, a->dw_accumulate, stream);
+    if (rc != DANA_OK) return rc;
+  }
   return DANA_OK;
 }
 

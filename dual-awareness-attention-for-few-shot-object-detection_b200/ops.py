@@ -7,7 +7,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvGemmArgs, check
+from ._lib import ConvBwdArgs, ConvGemmArgs, check
 
 
 # Kernel-launch accounting (bench.py's gpu_launches) and optional per-GEMM CUDA-event trace
@@ -758,13 +758,65 @@ def pack_conv_weight(w, scale=None, want_dgrad=True):
     return fwd, dg
 
 
-def unpack_conv_wgrad(wgrad, scale, co, ci, kh, kw):
+def unpack_conv_wgrad(wgrad, scale, co, ci, kh, kw, accumulate_into=None):
     """Weight-gradient GEMM output [Cout, kh*kw*Cin] -> contiguous fp32 [Cout,Cin,kh,kw] (x scale[Cout])."""
-    out = torch.empty((co, ci, kh, kw), dtype=torch.float32, device=wgrad.device)
+    out = accumulate_into if accumulate_into is not None else \
+        torch.empty((co, ci, kh, kw), dtype=torch.float32, device=wgrad.device)
     _count(1)
-    check(_lib.load().dana_unpack_conv_wgrad(_p(wgrad), _p(scale), co, ci, kh * kw, _p(out), _stream()),
+    check(_lib.load().dana_unpack_conv_wgrad(_p(wgrad), _p(scale), co, ci, kh * kw, _p(out),
+                                             1 if accumulate_into is not None else 0, _stream()),
           "dana_unpack_conv_wgrad")
     return out
+
+
+_BWD_WS = {}
+
+
+def conv_backward(grad_out, relu_out, x: Pair, w_dgrad: Optional[Pair], scale, ksize, stride, *, need_dx, need_dw,
+                  want_dres, dw_into=None):
+    """Backward of y = relu?(conv(x, W*s) + t (+ res)) in ONE C call (dana_conv_backward): -> (dx | None, dw | None,
+    dres | None).  grad_out fp32 [N,OH,OW,Cout]; x the saved NHWC input pair; dw_into: an fp32 [Cout,Cin,k,k] tensor
+    that receives dw += (gradient arenas; a parameter used by several calls) instead of a fresh tensor."""
+    _need_cuda(grad_out, x.hi)
+    g = grad_out.contiguous()
+    n, h, w, ci = x.hi.shape
+    co = g.shape[-1]
+    dev = g.device
+    lib = _lib.load()
+    sn, sy, sx, sc = x.hi.stride()
+    assert sc == 1 and x.lo.stride() == x.hi.stride()
+    a = ConvBwdArgs()
+    a.batch, a.height, a.width, a.in_channels, a.out_channels, a.ksize, a.stride = n, h, w, ci, co, ksize, stride
+    a.grad_out = g.data_ptr()
+    a.relu_out = None if relu_out is None else relu_out.data_ptr()
+    a.x_hi, a.x_lo = x.hi.data_ptr(), x.lo.data_ptr()
+    a.x_sn, a.x_sy, a.x_sx = sn, sy, sx
+    dx = dw = dres = None
+    if need_dx:
+        dx = torch.empty((n, h, w, ci), dtype=torch.float32, device=dev)
+        a.dx = dx.data_ptr()
+        a.wd_hi, a.wd_lo = w_dgrad.hi.data_ptr(), w_dgrad.lo.data_ptr()
+    if need_dw:
+        dw = dw_into if dw_into is not None else torch.empty((co, ci, ksize, ksize), dtype=torch.float32, device=dev)
+        a.dw = dw.data_ptr()
+        a.dw_accumulate = 1 if dw_into is not None else 0
+    if want_dres:
+        dres = torch.empty_like(g)
+        a.dres = dres.data_ptr()
+    a.scale = None if scale is None else scale.data_ptr()
+    need = lib.dana_conv_backward_workspace_bytes(n, h, w, ci, co, ksize, stride)
+    key = (dev.index, _raw_stream())
+    ws = _BWD_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _BWD_WS[key] = torch.empty((int(need * 1.25),), dtype=torch.uint8, device=dev)   # grows, then stays
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    global _SK_EPOCH
+    gws, epoch = _sk_workspace(dev)
+    _SK_EPOCH = _SK_EPOCH % 0x7FFFFFF0 + 1            # the call uses two consecutive epochs
+    a.gemm_workspace, a.gemm_workspace_bytes, a.sk_epoch = gws.data_ptr(), gws.numel(), epoch
+    _count(1 + (1 if need_dx else 0) + (3 if need_dw else 0))
+    check(lib.dana_conv_backward(ctypes.byref(a), _stream()), "dana_conv_backward")
+    return dx, (dw if dw_into is None else None), dres
 
 
 def sgd_momentum(param_flat, grad_flat, mom_flat, lr, momentum, weight_decay, grad_scale=1.0):

@@ -189,13 +189,16 @@ class TrainGraph:
         return loss.sum(dim=dims).mean()
 
     def rpn_losses(self, rpn_raw, anchor_t, num_a):
+        """rpn.py:96-116 with static shapes (no index_select of the kept anchors: a 0 / 1 weight per anchor instead, so
+        that the step can be captured into a CUDA graph): mean cross entropy over the anchors labelled 0 / 1."""
         labels, tgt, in_w, out_w = anchor_t                 # (y, x, a) anchor order, flat per image
         b = rpn_raw.shape[0]
         raw = rpn_raw.view(b, -1, 6 * num_a)
         score = torch.stack([raw[..., :num_a].reshape(-1), raw[..., num_a:2 * num_a].reshape(-1)], 1)
         lab = labels.view(-1).long()
-        keep = torch.nonzero(lab != -1).view(-1)
-        loss_cls = F.cross_entropy(score[keep], lab[keep])
+        keep = (lab != -1).float()
+        ce = F.cross_entropy(score, lab.clamp_min(0), reduction="none")
+        loss_cls = (ce * keep).sum() / keep.sum().clamp_min(1.0)
         deltas = raw[..., 2 * num_a:].reshape(b, -1, 4)
         loss_box = self.smooth_l1(deltas, tgt, in_w.unsqueeze(2), out_w.unsqueeze(2), 3.0, (1, 2))
         return loss_cls, loss_box
@@ -203,30 +206,38 @@ class TrainGraph:
     @staticmethod
     def rcnn_cls_loss(scores, labels):
         """dana.py:203-214: all fg, the hardest bg of the positive-support half (2 x fg, at most a quarter of the rows)
-        and of the negative-support half (<= fg)."""
+        and of the negative-support half (<= fg) -- as a 0 / 1 weight per row computed on the device (ranks from two
+        sorts), static shapes, no host read-back."""
         n = labels.shape[0]
-        fg = torch.nonzero(labels == 1).view(-1)
-        bg = torch.nonzero(labels == 0).view(-1)
-        sm = F.softmax(scores.detach(), dim=1)
-        bg0 = max(1, min(fg.numel() * 2, int(n * 0.25)))
-        bg1 = max(1, min(fg.numel(), bg0))
-        real_bg = bg[torch.sort(sm[bg, 1], descending=True)[1]]
-        top0 = real_bg[real_bg < int(n * 0.5)][:bg0]
-        top1 = real_bg[real_bg >= int(n * 0.5)][:bg1]
-        idx = torch.cat([fg, top0, top1], 0)
-        return F.cross_entropy(scores[idx], labels[idx])
+        half = int(n * 0.5)
+        idx = torch.arange(n, device=scores.device)
+        fg = labels == 1
+        bg = labels == 0
+        nfg = fg.sum()
+        bg0 = torch.clamp(torch.minimum(nfg * 2, torch.full_like(nfg, int(n * 0.25))), min=1)
+        bg1 = torch.clamp(torch.minimum(nfg, bg0), min=1)
+        p1 = F.softmax(scores.detach(), dim=1)[:, 1]
+        neg_inf = torch.full_like(p1, float("-inf"))
+        sel = fg
+        for in_half, quota in ((idx < half, bg0), (idx >= half, bg1)):
+            cand = bg & in_half
+            order = torch.sort(torch.where(cand, p1, neg_inf), descending=True)[1]
+            rank = torch.empty_like(order)
+            rank[order] = idx
+            sel = sel | (cand & (rank < quota))
+        w = sel.float()
+        ce = F.cross_entropy(scores, labels, reduction="none")
+        return (ce * w).sum() / w.sum()
 
     # ------------------------------------------------------------------ forward
-    def forward(self, stem, im_data, im_info, gt_boxes, num_boxes, support_ims, base_anchors, feat_stride=16,
-                teacher=None):
-        """-> (rois [B,R,5], cls_prob [2BR,2], bbox_pred [BR,4], rpn_loss_cls, rpn_loss_box, RCNN_loss_cls,
-        RCNN_loss_bbox, rois_label [2BR]) -- the reference's 8-tuple; the four losses carry the autograd graph."""
+    def part1(self, stem, im_data, im_info, support_ims, base_anchors, feat_stride=16):
+        """Trunks, RPN-level attention, RPN head and the proposal layer: everything up to the point where the host draws
+        the training targets.  No host synchronisation (capturable into a CUDA graph).  -> state dict."""
         p, k = self.p, self.n_shot
         dev = im_data.device
         b = im_data.shape[0]
         num_a = base_anchors.shape[0]
         A.begin_step()
-        self._bn.clear()
         with torch.no_grad():
             q1 = stem(im_data)
             s1 = stem(support_ims.reshape(-1, *support_ims.shape[2:]))
@@ -246,40 +257,46 @@ class TrainGraph:
         w_out = torch.cat([p["RCNN_rpn.RPN_cls_score.weight"], p["RCNN_rpn.RPN_bbox_pred.weight"]], 0)
         b_out = torch.cat([p["RCNN_rpn.RPN_cls_score.bias"], p["RCNN_rpn.RPN_bbox_pred.bias"]], 0)
         rpn_raw = A.conv(x, w_out, bias=b_out, ksize=1)                       # [B,h,w,6A]: bg | fg | deltas
-
-        # ---- proposal layer + targets: no gradient (rpn.py:74-93, dana.py:166-170)
+        # ---- proposal layer: no gradient (rpn.py:74-78)
         with torch.no_grad():
             fg, deltas = ops.rpn_fg_prob(rpn_raw.detach().contiguous(), num_a)
             rois_all = ops.proposals(fg, deltas, base_anchors, im_info.to(dev).float(), qh, qw, feat_stride,
                                      cfg.TRAIN.RPN_PRE_NMS_TOP_N, cfg.TRAIN.RPN_POST_NMS_TOP_N, cfg.TRAIN.RPN_NMS_THRESH)
-            if teacher and "rois" in teacher:
-                rois_all = teacher["rois"].to(dev).float().contiguous()
-            gt_host = gt_boxes.detach().float().cpu().numpy()
-            info_host = im_info.detach().float().cpu().numpy()
-            # anchor targets first, then proposal targets: the order of the reference's numpy RNG draws
-            anchor_t = targets.anchor_targets(
-                qh, qw, gt_host, info_host, base_anchors.cpu().numpy(), feat_stride,
-                negative_overlap=cfg.TRAIN.RPN_NEGATIVE_OVERLAP, positive_overlap=cfg.TRAIN.RPN_POSITIVE_OVERLAP,
-                clobber_positives=cfg.TRAIN.RPN_CLOBBER_POSITIVES, fg_fraction=cfg.TRAIN.RPN_FG_FRACTION,
-                batchsize=cfg.TRAIN.RPN_BATCHSIZE, inside_weight=cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0],
-                positive_weight=cfg.TRAIN.RPN_POSITIVE_WEIGHT)
-            sample = targets.proposal_targets(
-                rois_all.cpu().numpy(), gt_host, rois_per_image=cfg.TRAIN.BATCH_SIZE, fg_fraction=cfg.TRAIN.FG_FRACTION,
-                fg_thresh=cfg.TRAIN.FG_THRESH, bg_thresh_hi=cfg.TRAIN.BG_THRESH_HI, bg_thresh_lo=cfg.TRAIN.BG_THRESH_LO,
-                normalize_means=cfg.TRAIN.BBOX_NORMALIZE_MEANS, normalize_stds=cfg.TRAIN.BBOX_NORMALIZE_STDS,
-                inside_weights=cfg.TRAIN.BBOX_INSIDE_WEIGHTS,
-                normalize_targets=cfg.TRAIN.BBOX_NORMALIZE_TARGETS_PRECOMPUTED)
-            anchor_t = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in anchor_t]
-            rois, lab_s, tgt_s, inw_s, outw_s = [torch.from_numpy(np.ascontiguousarray(t)).to(dev).float() for t in sample]
-        rpn_loss_cls, rpn_loss_box = self.rpn_losses(rpn_raw, anchor_t, num_a)
+        return dict(base=base, sup_pooled=sup_pooled, rpn_raw=rpn_raw, rois_all=rois_all, qh=qh, qw=qw, num_a=num_a, b=b)
 
+    @staticmethod
+    def anchor_targets_host(qh, qw, gt_host, info_host, anchors_host, feat_stride=16):
+        """anchor_target_layer.py:48-193 on the host (numpy RNG draws :131,:143)."""
+        return targets.anchor_targets(
+            qh, qw, gt_host, info_host, anchors_host, feat_stride,
+            negative_overlap=cfg.TRAIN.RPN_NEGATIVE_OVERLAP, positive_overlap=cfg.TRAIN.RPN_POSITIVE_OVERLAP,
+            clobber_positives=cfg.TRAIN.RPN_CLOBBER_POSITIVES, fg_fraction=cfg.TRAIN.RPN_FG_FRACTION,
+            batchsize=cfg.TRAIN.RPN_BATCHSIZE, inside_weight=cfg.TRAIN.RPN_BBOX_INSIDE_WEIGHTS[0],
+            positive_weight=cfg.TRAIN.RPN_POSITIVE_WEIGHT)
+
+    @staticmethod
+    def proposal_targets_host(rois_all_host, gt_host):
+        """proposal_target_layer_cascade.py:33-213 on the host (numpy RNG draws :159,:168,:175,:183)."""
+        return targets.proposal_targets(
+            rois_all_host, gt_host, rois_per_image=cfg.TRAIN.BATCH_SIZE, fg_fraction=cfg.TRAIN.FG_FRACTION,
+            fg_thresh=cfg.TRAIN.FG_THRESH, bg_thresh_hi=cfg.TRAIN.BG_THRESH_HI, bg_thresh_lo=cfg.TRAIN.BG_THRESH_LO,
+            normalize_means=cfg.TRAIN.BBOX_NORMALIZE_MEANS, normalize_stds=cfg.TRAIN.BBOX_NORMALIZE_STDS,
+            inside_weights=cfg.TRAIN.BBOX_INSIDE_WEIGHTS, normalize_targets=cfg.TRAIN.BBOX_NORMALIZE_TARGETS_PRECOMPUTED)
+
+    def part2(self, st, anchor_t, sample):
+        """Losses of the RPN, RoIAlign on the sampled RoIs, layer4 + box regressor, both head passes and the R-CNN
+        losses.  anchor_t: (labels int8, bbox targets, inside w, outside w) device tensors; sample: (rois [B,R,5],
+        labels [B,R], bbox targets, inside w, outside w) fp32 device tensors.  No host synchronisation."""
+        b, num_a = st["b"], st["num_a"]
+        rois, lab_s, tgt_s, inw_s, outw_s = sample
+        rpn_loss_cls, rpn_loss_box = self.rpn_losses(st["rpn_raw"], anchor_t, num_a)
         per = rois.shape[1]
         r = b * per
-        pooled = _RoIAlignNHWC.apply(base, rois.view(-1, 5).contiguous())     # [R,7,7,1024]
+        pooled = _RoIAlignNHWC.apply(st["base"], rois.view(-1, 5).contiguous())     # [R,7,7,1024]
         fc7 = self.head_to_tail(pooled)
         bbox_pred = self.lin(fc7, "RCNN_bbox_pred")
-        sc_pos = self.rcnn_head(pooled, sup_pooled[:, 0], per)                # dana.py:189-194
-        sc_neg = self.rcnn_head(pooled, sup_pooled[:, 1], per)
+        sc_pos = self.rcnn_head(pooled, st["sup_pooled"][:, 0], per)                # dana.py:189-194
+        sc_neg = self.rcnn_head(pooled, st["sup_pooled"][:, 1], per)
         cls_score = torch.cat([sc_pos, sc_neg], 0)
         cls_prob = F.softmax(cls_score.detach(), 1)
         labels = lab_s.view(-1).long()
@@ -287,3 +304,23 @@ class TrainGraph:
         loss_bbox = self.smooth_l1(bbox_pred, tgt_s.view(r, 4), inw_s.view(r, 4), outw_s.view(r, 4), 1.0, (1,))
         loss_cls = self.rcnn_cls_loss(cls_score, rois_label)
         return rois, cls_prob, bbox_pred.detach(), rpn_loss_cls, rpn_loss_box, loss_cls, loss_bbox, rois_label
+
+    def forward(self, stem, im_data, im_info, gt_boxes, num_boxes, support_ims, base_anchors, feat_stride=16,
+                teacher=None):
+        """-> (rois [B,R,5], cls_prob [2BR,2], bbox_pred [BR,4], rpn_loss_cls, rpn_loss_box, RCNN_loss_cls,
+        RCNN_loss_bbox, rois_label [2BR]) -- the reference's 8-tuple; the four losses carry the autograd graph."""
+        dev = im_data.device
+        self._bn.clear()
+        st = self.part1(stem, im_data, im_info, support_ims, base_anchors, feat_stride)
+        gt_host = gt_boxes.detach().float().cpu().numpy()
+        info_host = im_info.detach().float().cpu().numpy()
+        # anchor targets first, then proposal targets: the order of the reference's numpy RNG draws.  The anchor targets
+        # do not depend on the network: they are drawn while the GPU is still working on part 1.
+        anchor_t = self.anchor_targets_host(st["qh"], st["qw"], gt_host, info_host, base_anchors.cpu().numpy(), feat_stride)
+        rois_all = st["rois_all"]
+        if teacher and "rois" in teacher:
+            rois_all = teacher["rois"].to(dev).float().contiguous()
+        sample = self.proposal_targets_host(rois_all.cpu().numpy(), gt_host)
+        anchor_t = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in anchor_t]
+        sample = [torch.from_numpy(np.ascontiguousarray(t)).to(dev).float() for t in sample]
+        return self.part2(st, anchor_t, sample)

@@ -16,7 +16,7 @@ else lr and WEIGHT_DECAY; momentum cfg.TRAIN.MOMENTUM."""
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import autograd_ops, ops
 from .config import cfg
 
 
@@ -116,9 +116,111 @@ class ArenaGradAllReduce:
         self.disarm()
 
 
+class _CapturedStep:
+    """The device side of one training step as two CUDA graphs around the host's target layers:
+         graph 1   gradient arenas zeroed, weights packed, frozen stem, layer2-3 on query and supports, RPN-level
+                   attention, RPN head, proposal layer                                   (TrainGraph.part1)
+         host      anchor targets (drawn while graph 1 runs), proposals D2H, proposal targets, targets H2D
+         graph 2   RPN losses, RoIAlign, layer4, both head passes, R-CNN losses, and the WHOLE backward (through the
+                   autograd graph that the capture of graph 1 recorded), gradients accumulated into the arenas
+       ~3800 launches issued from Python become two graph launches: the eager step is host-bound (47 ms of device work
+       in 84 ms), the captured one is not.  The all-reduce and the two SGD launches follow graph 2."""
+
+    def __init__(self, trainer, im_data, im_info, gt_boxes, support_ims):
+        import numpy as np
+
+        from .anchors import generate_anchors
+        from .train_model import FrozenStem, TrainGraph
+        net = trainer.net
+        dev = im_data.device
+        named = dict(net.named_parameters())
+        named.update(dict(net.named_buffers()))
+        self.tg = TrainGraph(named, num_layers=net.num_layers, n_shot=net.n_shot, semantic_enhance=net.semantic_enhance,
+                             channel_gamma=net.channel_gamma, unary_gamma=net.unary_gamma)
+        self.stem = FrozenStem(named, dev)
+        self.anchors = torch.from_numpy(generate_anchors(ratios=tuple(cfg.ANCHOR_RATIOS),
+                                                         scales=tuple(cfg.ANCHOR_SCALES))).float().to(dev)
+        self.anchors_host = self.anchors.cpu().numpy()
+        self.stride = cfg.FEAT_STRIDE[0]
+        self.s_im, self.s_info, self.s_sup = im_data.detach().clone(), im_info.detach().float().clone(), support_ims.detach().clone()
+        sink = lambda p: trainer._grad_of.get(id(p))  # noqa: E731
+        rng_state = np.random.get_state()          # capture draws targets too: leave the caller's RNG stream untouched
+
+        def host_targets(st, gt_host, info_host):
+            anchor_t = self.tg.anchor_targets_host(st["qh"], st["qw"], gt_host, info_host, self.anchors_host, self.stride)
+            sample = self.tg.proposal_targets_host(st["rois_all"].cpu().numpy(), gt_host)
+            return ([torch.from_numpy(np.ascontiguousarray(t)) for t in anchor_t],
+                    [torch.from_numpy(np.ascontiguousarray(t)).float() for t in sample])
+        gt_host = gt_boxes.detach().float().cpu().numpy()
+        info_host = im_info.detach().float().cpu().numpy()
+        # AccumulateGrad nodes of the bias parameters are created by the first warm-up pass on the side stream and
+        # reused on the capture stream: intended, both are ordered by the waits below
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):              # warm-up outside capture: lazy workspaces, kernel attributes, PE tables
+            for _ in range(2):
+                autograd_ops.set_direct_grads(sink, None)
+                st = self.tg.part1(self.stem, self.s_im, self.s_info, self.s_sup, self.anchors, self.stride)
+                a_t, smp = host_targets(st, gt_host, info_host)
+                out = self.tg.part2(st, [t.to(dev) for t in a_t], [t.to(dev) for t in smp])
+                (out[3] + out[4] + out[5] + out[6]).backward()
+                autograd_ops.set_direct_grads(None, None)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.s_anchor = [t.to(dev) for t in a_t]
+        self.s_sample = [t.to(dev) for t in smp]
+        pool = torch.cuda.graph_pool_handle()
+        self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        autograd_ops.set_direct_grads(sink, None)
+        launches0 = ops.LAUNCHES
+        try:
+            with torch.cuda.graph(self.g1, pool=pool):
+                for a in trainer.arenas:
+                    a.grad.zero_()
+                self.st = self.tg.part1(self.stem, self.s_im, self.s_info, self.s_sup, self.anchors, self.stride)
+            with torch.cuda.graph(self.g2, pool=pool):
+                out = self.tg.part2(self.st, self.s_anchor, self.s_sample)
+                self.losses = out[3:7]
+                self.loss = out[3] + out[4] + out[5] + out[6]
+                self.loss.backward()
+        finally:
+            autograd_ops.set_direct_grads(None, None)
+        self.launches = ops.LAUNCHES - launches0       # own kernels recorded in the two graphs (replayed every step)
+        self.out = out
+        np.random.set_state(rng_state)
+        for a in trainer.arenas:                   # the warm-up / capture passes left gradients behind
+            a.grad.zero_()
+
+    def run(self, im_data, im_info, gt_boxes, support_ims):
+        import numpy as np
+        for dst, src in ((self.s_im, im_data), (self.s_info, im_info), (self.s_sup, support_ims)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        gt_host = gt_boxes.detach().float().cpu().numpy()        # before the replay: a D2H copy waits for the stream
+        info_host = im_info.detach().float().cpu().numpy()
+        self.g1.replay()
+        # anchor targets first (they do not depend on the network: drawn while graph 1 runs), then proposal targets:
+        # the order of the reference's numpy RNG draws
+        anchor_t = self.tg.anchor_targets_host(self.st["qh"], self.st["qw"], gt_host, info_host, self.anchors_host, self.stride)
+        sample = self.tg.proposal_targets_host(self.st["rois_all"].cpu().numpy(), gt_host)
+        for dst, src in zip(self.s_anchor, anchor_t):
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(src)), non_blocking=True)
+        for dst, src in zip(self.s_sample, sample):
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(src)).float(), non_blocking=True)
+        self.g2.replay()
+        ops.LAUNCHES += self.launches
+        return self.out
+
+
 class SGDTrainer:
-    def __init__(self, net, lr=None, momentum=None, weight_decay=None, bucket_bytes=25 << 20):
+    def __init__(self, net, lr=None, momentum=None, weight_decay=None, bucket_bytes=25 << 20, cuda_graph=False):
         self.net = net
+        self.cuda_graph = cuda_graph
+        self._captured = {}
         self.lr = cfg.TRAIN.LEARNING_RATE if lr is None else lr
         self.momentum = cfg.TRAIN.MOMENTUM if momentum is None else momentum
         wd = cfg.TRAIN.WEIGHT_DECAY if weight_decay is None else weight_decay
@@ -134,6 +236,10 @@ class SGDTrainer:
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.sync = ArenaGradAllReduce(self.arenas) if self.world > 1 else None
         self.events = None               # optional: list receiving (name, CUDA event) marks of one step
+        self._grad_of = {}               # id(param) -> its slice of the gradient arena (autograd_ops' direct sink)
+        for a in self.arenas:
+            for (_, p), off in zip(a.named, a.offsets):
+                self._grad_of[id(p)] = a.grad[off:off + p.numel()].view(p.shape)
 
     def _mark(self, name):
         if self.events is not None:
@@ -141,12 +247,54 @@ class SGDTrainer:
             e.record()
             self.events.append((name, e))
 
-    def step(self, im_data, im_info, gt_boxes, num_boxes, support_ims):
+    def _finish(self):
+        """All-reduce of the arenas after backward (the captured step: not overlapped, ~1 ms on NVSwitch) + SGD."""
+        if self.world > 1:
+            work = [dist.all_reduce(a.grad[begin:end], op=dist.ReduceOp.SUM, async_op=True)
+                    for a in self.arenas for (_, _, begin, end) in a.buckets]
+            for w in work:
+                w.wait()
+        for a in self.arenas:
+            ops.sgd_momentum(a.param, a.grad, a.mom, a.lr, self.momentum, a.weight_decay, grad_scale=1.0 / self.world)
+            torch.autograd.graph.increment_version([p for _, p in a.named])
+
+    def step_captured(self, im_data, im_info, gt_boxes, num_boxes, support_ims):
+        """step() with the device work replayed from two CUDA graphs (_CapturedStep); one capture per input shape."""
+        if self.net.n_way != 2 or support_ims.shape[1] != 2 * self.net.n_shot:
+            raise ValueError("train mode expects n_way = 2 and 2 * n_shot support crops per image")
+        key = (tuple(im_data.shape), tuple(support_ims.shape), tuple(gt_boxes.shape))
+        cap = self._captured.get(key)
+        if cap is None:
+            for a in self.arenas:
+                a.rebind_grads()
+            try:
+                cap = _CapturedStep(self, im_data, im_info, gt_boxes, support_ims)
+            except Exception as e:  # noqa: BLE001  -- capture is an optimisation, never a requirement
+                import warnings
+                warnings.warn("dana_b200: CUDA graph capture of the training step failed (%r); running eagerly" % (e,))
+                cap = False
+            self._captured[key] = cap
+        if cap is False:
+            return self.step(im_data, im_info, gt_boxes, num_boxes, support_ims, _eager=True)
+        self._mark("start")
+        out = cap.run(im_data, im_info, gt_boxes, support_ims)
+        self._mark("graphs")
+        self._finish()
+        self._mark("allreduce+sgd")
+        return cap.loss.detach().clone(), tuple(l.detach().clone() for l in cap.losses)
+
+    def step(self, im_data, im_info, gt_boxes, num_boxes, support_ims, _eager=False):
         """-> (loss, (rpn_loss_cls, rpn_loss_box, RCNN_loss_cls, RCNN_loss_bbox)) as detached 0-dim CUDA tensors."""
+        if self.cuda_graph and not _eager:
+            return self.step_captured(im_data, im_info, gt_boxes, num_boxes, support_ims)
         for a in self.arenas:
             a.rebind_grads()
             a.grad.zero_()
         self._mark("start")
+        # weight gradients of the conv / linear functions are accumulated by the unpack kernel straight into the arena;
+        # completion is signalled to the all-reduce like a post-accumulate hook would
+        autograd_ops.set_direct_grads(lambda p: self._grad_of.get(id(p)),
+                                      self.sync._on_grad if self.sync is not None else None)
         out = self.net(im_data, im_info, gt_boxes, num_boxes, support_ims)
         losses = out[3:7]
         loss = losses[0].mean() + losses[1].mean() + losses[2].mean() + losses[3].mean()      # train.py:136-137
@@ -154,6 +302,7 @@ class SGDTrainer:
         if self.sync is not None:
             self.sync.arm()
         loss.backward()
+        autograd_ops.set_direct_grads(None, None)
         self._mark("backward")
         if self.sync is not None:
             self.sync.finish()

@@ -343,7 +343,40 @@ int dana_im2col_t(const void* x_hi, const void* x_lo, int batch, int height, int
 int dana_pack_conv_weight(const float* weight, const float* scale, int out_channels, int in_channels, int kh, int kw,
                           void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* dgrad_lo, void* stream);
 int dana_unpack_conv_wgrad(const float* wgrad, const float* scale, int out_channels, int in_channels, int taps,
-                           float* weight_grad, void* stream);
+                           float* weight_grad, int accumulate, void* stream);
+
+/* dana_conv_backward: the whole backward of y = relu?(conv(x, W*s) + t (+ res)) in one call (what torch.autograd does with
+ * cudnn_convolution_backward + threshold_backward for resnet.py:66-102 under train.py:138): dana_grad_prepare on grad_out
+ * (mask by relu_out when given), the data-gradient GEMM into dx (NULL: skipped; zero-filled first when stride > 1), the
+ * transposing im2col of the saved input pair + the weight-gradient GEMM + unpack into dw (NULL: skipped; dw_accumulate:
+ * dw += instead of dw =, so that a parameter used twice -- query and support trunk -- or a gradient arena is written
+ * in place), dres = the masked fp32 gradient (the residual branch's share / the bias gradient's summand; NULL: skipped).
+ * x is the saved NHWC input pair [batch][height][width][in_channels] (element strides x_s*); wd_* the data-gradient weight
+ * planes of dana_pack_conv_weight; workspace >= dana_conv_backward_workspace_bytes(), 256-byte aligned, private to the stream;
+ * gemm_workspace / sk_epoch as in dana_conv_gemm_args (two consecutive epochs are used). */
+typedef struct dana_conv_bwd_args {
+  int32_t batch, height, width, in_channels, out_channels, ksize, stride;
+  const float* grad_out;
+  const float* relu_out;
+  const void* x_hi;
+  const void* x_lo;
+  int64_t x_sn, x_sy, x_sx;
+  const void* wd_hi;
+  const void* wd_lo;
+  const float* scale;
+  float* dx;
+  float* dw;
+  float* dres;
+  int32_t dw_accumulate;
+  void* workspace;
+  int64_t workspace_bytes;
+  void* gemm_workspace;
+  int64_t gemm_workspace_bytes;
+  int32_t sk_epoch;
+} dana_conv_bwd_args;
+int64_t dana_conv_backward_workspace_bytes(int batch, int height, int width, int in_channels, int out_channels, int ksize,
+                                           int stride);
+int dana_conv_backward(const dana_conv_bwd_args* args, void* stream);
 int dana_sgd_momentum(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                       float weight_decay, float grad_scale, void* stream);
 int dana_depthwise_xcorr(const void* in_hi, const void* in_lo, int batch, int h, int w, int c, const float* kernel,

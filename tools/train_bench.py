@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--width", type=int, default=1333)
     ap.add_argument("--shots", type=int, default=5)
     ap.add_argument("--bucket-mb", type=int, default=25)
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the two CUDA graphs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -58,7 +59,7 @@ def main():
     net.create_architecture()
     net.load_state_dict(synthetic_state_dict(1996, num_layers=args.layers), strict=False)
     net.cuda().train()
-    trainer = SGDTrainer(net, bucket_bytes=args.bucket_mb << 20)
+    trainer = SGDTrainer(net, bucket_bytes=args.bucket_mb << 20, cuda_graph=not args.eager)
     n_params = sum(g[1].numel() for g in trainer.groups)
 
     b = args.batch
@@ -126,7 +127,8 @@ def main():
             "config": {"workload": "res%d DAnA training step (fwd + bwd + grad all-reduce + SGD), %d image/GPU, %dx%d, 2 sets x %d shots"
                        % (args.layers, b, args.height, args.width, args.shots), "trainable_params": n_params,
                        "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0, "bucket_mb": args.bucket_mb,
-                       "collective": "NCCL all-reduce (sum / world), bucketed, launched from post-accumulate hooks" if world > 1 else "none"},
+                       "launch": "eager (Python launches)" if args.eager else "two CUDA graphs around the host target layers",
+                       "collective": ("NCCL all-reduce (sum / world) of the gradient arenas, " + ("bucketed, launched from post-accumulate hooks during backward" if args.eager else "after the backward graph")) if world > 1 else "none"},
             "split_one_step": split, "gpu_launches": launches, "loss_first_last": [round(losses[0], 4), round(losses[-1], 4)],
             "device_error": err}))
     if world > 1:

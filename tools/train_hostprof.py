@@ -36,4 +36,4 @@ for _ in range(3):
     tr.step(*args)
 torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+pstats.Stats(pr).sort_stats("tottime").print_stats(28)
