@@ -245,7 +245,9 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ g, const floa
     const int co = static_cast<int>(i / (static_cast<long long>(taps) * ci_n));
     float v = g[(static_cast<long long>(co) * taps + tap) * ci_n + ci];
     if (scale != nullptr) v *= scale[co];
-    dw[i] = accumulate ? dw[i] + v : v;
+    // accumulate: a red.add -- the query trunk's and the support trunk's backward run on two streams and may write the
+    // same parameter's gradient at the same time (two commutative contributions onto a zeroed arena: deterministic)
+    if (accumulate) atomicAdd(dw + i, v); else dw[i] = v;
   }
 }
 

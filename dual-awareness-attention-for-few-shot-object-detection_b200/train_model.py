@@ -15,6 +15,7 @@ What runs where:
 
 Activations are fp32 NHWC; every GEMM operand is a split-bf16 pair (fp32-equivalent products)."""
 import math
+import os
 
 import numpy as np
 import torch
@@ -80,6 +81,7 @@ class TrainGraph:
         self.channel_gamma, self.unary_gamma = channel_gamma, unary_gamma
         self._bn = {}
         self._pe = {}
+        self._side = None
 
     # ------------------------------------------------------------------ trunk
     def bn(self, name):
@@ -238,18 +240,42 @@ class TrainGraph:
         b = im_data.shape[0]
         num_a = base_anchors.shape[0]
         A.begin_step()
+        # The support trunk runs on a side stream next to the query trunk: one 800x1333 query or ten 320x320 crops make
+        # 33 pixel tiles per layer -- a launch fills a quarter to half of the 148 SMs -- so the two independent trunks
+        # share the GPU.  autograd runs each node's backward on its forward's stream, so the two backward passes overlap
+        # as well, and under capture they become parallel branches of the CUDA graph.
+        # Shared by both trunks, so made BEFORE the fork (the cache would otherwise hand one stream planes that the other
+        # stream's pack kernel is still writing): operand planes of every layer2 / layer3 weight, the BN folds.
+        for name, w in p.items():
+            if name.startswith(("RCNN_base.5.", "RCNN_base.6.")) and name.endswith(("conv1.weight", "conv2.weight",
+                                                                                       "conv3.weight", "downsample.0.weight")):
+                bn_name = name[:-len("conv1.weight")] + "bn" + name[-len("1.weight")] if "conv" in name else \
+                    name[:-len("0.weight")] + "1"
+                A._packed(w, self.bn(bn_name)[0], need_dgrad=True)
+        cur = torch.cuda.current_stream()
+        use_side = os.environ.get("DANA_TRAIN_SIDE_STREAM", "1") != "0"
+        if use_side and self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side if use_side else cur
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            with torch.no_grad():
+                s1 = stem(support_ims.reshape(-1, *support_ims.shape[2:]))
+            sup = self.trunk_tail(s1)                                         # [B*2K,hs,ws,1024]
+            hs, ws, c = sup.shape[1], sup.shape[2], sup.shape[3]
+            if hs != ws:
+                raise ValueError("support feature maps must be square (AvgPool2d of dana.py:42)")
+            sup = sup.view(b, 2, k, hs, ws, c)                                # positive set, negative set (dana.py:100-108)
+            sup_pooled = F.avg_pool2d(sup.reshape(-1, hs, ws, c).permute(0, 3, 1, 2), hs - 6, 1).permute(0, 2, 3, 1)
+            sup_pooled = sup_pooled.reshape(b, 2, k, 7, 7, c)
         with torch.no_grad():
             q1 = stem(im_data)
-            s1 = stem(support_ims.reshape(-1, *support_ims.shape[2:]))
         base = self.trunk_tail(q1)                                            # [B,h,w,1024]
-        sup = self.trunk_tail(s1)                                             # [B*2K,hs,ws,1024]
-        _, qh, qw, c = base.shape
-        hs, ws = sup.shape[1], sup.shape[2]
-        if hs != ws:
-            raise ValueError("support feature maps must be square (AvgPool2d of dana.py:42)")
-        sup = sup.view(b, 2, k, hs, ws, c)                                    # positive set, negative set (dana.py:100-108)
-        sup_pooled = F.avg_pool2d(sup.reshape(-1, hs, ws, c).permute(0, 3, 1, 2), hs - 6, 1).permute(0, 2, 3, 1)
-        sup_pooled = sup_pooled.reshape(b, 2, k, 7, 7, c)
+        _, qh, qw, _ = base.shape
+        cur.wait_stream(side)
+        if use_side:
+            sup.record_stream(cur)
+            sup_pooled.record_stream(cur)
 
         dense = self.rpn_attention(base, sup[:, 0])
         corr = torch.cat([base, dense], 3)                                    # dana.py:154
