@@ -255,6 +255,13 @@ inline int conv_gemm_dispatch(const dana_conv_gemm_args* a, cudaStream_t stream)
   if (static_cast<long long>(taps) * a->a_c <= 2048) {
     while (block_n > 64 && sp_tiles * ((a->n_out + block_n - 1) / block_n) * 2 <= sms) block_n >>= 1;
   }
+  // long K with few output tiles (the weight-gradient GEMMs of the training step: M = output channels, K = pixels; the
+  // layers of a single 800x1333 episode): stream-K alone leaves every CTA a short K range plus a 128 x 256 fp32 partial to
+  // exchange; narrower tiles give it whole tiles to spread first.  Measured on the res101 training step: 36.8 ms with
+  // this rule off, 33.5 / 32.9 ms with every launch forced to 128 / 64 columns (tools/train_bench.py, DANA_BLOCK_N).
+  if (a->a_lo != nullptr) {
+    while (block_n > 64 && sp_tiles * ((a->n_out + block_n - 1) / block_n) < sms) block_n >>= 1;
+  }
   if (softmax) block_n = a->softmax_ns <= 64 ? 64 : (a->softmax_ns <= 256 ? 256 : 512);   // one N-tile per shot segment
   const bool wide = softmax && block_n == 512;
   const int sm_half = wide ? ((a->softmax_ns + 31) / 32 * 32) / 2 : 0;   // % 16 == 0, <= 256

@@ -26,7 +26,7 @@ net = DAnARCNN(["bg", "fg"], "concat", 256, 256, pretrained=False, semantic_enha
 net.create_architecture()
 net.load_state_dict(synthetic_state_dict(1996, num_layers=layers), strict=False)
 net.cuda().train()
-tr = SGDTrainer(net)
+tr = SGDTrainer(net, cuda_graph=os.environ.get('EAGER', '0') != '1')
 im, info, sup = synthetic_episode(100, 1, h, w, 2 * shots)
 gt = torch.zeros(1, 50, 5)
 gt[0, 0] = torch.tensor([100.0, 120.0, 400.0, 380.0, 1.0])
