@@ -63,10 +63,36 @@ _DONE = None
 _USES = {}
 
 
-def set_direct_grads(sink=None, done=None):
-    global _SINK, _DONE
+_FORK = False
+_AUX = {}
+_FORKED = {}
+_KEEP = []
+
+
+def set_direct_grads(sink=None, done=None, fork_wgrad=False):
+    """fork_wgrad: run the weight-gradient half of every conv backward on an auxiliary stream (only with a sink and
+    without a `done` callback: the gradients are complete after join_forks(), not when the last use returns)."""
+    global _SINK, _DONE, _FORK
     _SINK, _DONE = sink, done
+    _FORK = bool(fork_wgrad) and sink is not None and done is None
     _USES.clear()
+
+
+def _aux_stream(main):
+    key = main.cuda_stream
+    st = _AUX.get(key)
+    if st is None:
+        st = _AUX[key] = torch.cuda.Stream(device=main.device)
+    return st
+
+
+def join_forks():
+    """Make the current stream wait for every auxiliary weight-gradient stream, then release the kept inputs."""
+    cur = torch.cuda.current_stream()
+    for st in _FORKED.values():          # only the streams forked since the last join (a capture must not wait on others)
+        cur.wait_stream(st)
+    _FORKED.clear()
+    _KEEP.clear()
 
 
 class _ConvFn(torch.autograd.Function):
@@ -101,9 +127,26 @@ class _ConvFn(torch.autograd.Function):
         want_dres = (need_r and ctx.relu) or need_b
         leaf = ctx.leaf
         into = _SINK(leaf).view(gy.shape[-1], -1, ctx.ksize, ctx.ksize) if (leaf is not None and need_w) else None
-        dx, dw, gf = ops.conv_backward(gy, y, ctx.xp, _dgrad_weight(ctx.ent, ctx.scale) if need_x else None, ctx.scale,
-                                       ctx.ksize, ctx.stride, need_dx=need_x, need_dw=need_w, want_dres=want_dres,
-                                       dw_into=into)
+        if _FORK and into is not None and need_x:
+            # weight gradient on an auxiliary stream: it is off the critical path (nothing in backward consumes it), the
+            # data gradient is the chain every earlier layer waits for -- and a single-episode launch fills only part of
+            # the GPU.  The two halves share nothing but their inputs (each runs its own grad_prepare into its own
+            # per-stream workspace); the inputs are kept alive until join_forks().
+            main = torch.cuda.current_stream()
+            aux = _aux_stream(main)
+            gy = gy.contiguous()
+            aux.wait_stream(main)
+            _FORKED[aux.cuda_stream] = aux
+            with torch.cuda.stream(aux):
+                ops.conv_backward(gy, y, ctx.xp, None, ctx.scale, ctx.ksize, ctx.stride, need_dx=False, need_dw=True,
+                                  want_dres=False, dw_into=into)
+            _KEEP.append((gy, y, ctx.xp))
+            dx, dw, gf = ops.conv_backward(gy, y, ctx.xp, _dgrad_weight(ctx.ent, ctx.scale), ctx.scale, ctx.ksize,
+                                           ctx.stride, need_dx=True, need_dw=False, want_dres=want_dres)
+        else:
+            dx, dw, gf = ops.conv_backward(gy, y, ctx.xp, _dgrad_weight(ctx.ent, ctx.scale) if need_x else None, ctx.scale,
+                                           ctx.ksize, ctx.stride, need_dx=need_x, need_dw=need_w, want_dres=want_dres,
+                                           dw_into=into)
         if leaf is not None and need_w:
             _USES[id(leaf)] -= 1
             if _USES[id(leaf)] == 0 and _DONE is not None:

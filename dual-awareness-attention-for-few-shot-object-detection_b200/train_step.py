@@ -13,6 +13,8 @@ produces the gradients).  That makes
 
 Parameter groups as train.py:78-89: biases take lr * (DOUBLE_BIAS + 1) and weight decay only if BIAS_DECAY, everything
 else lr and WEIGHT_DECAY; momentum cfg.TRAIN.MOMENTUM."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -144,6 +146,7 @@ class _CapturedStep:
         self.stride = cfg.FEAT_STRIDE[0]
         self.s_im, self.s_info, self.s_sup = im_data.detach().clone(), im_info.detach().float().clone(), support_ims.detach().clone()
         sink = lambda p: trainer._grad_of.get(id(p))  # noqa: E731
+        fork = os.environ.get("DANA_TRAIN_FORK_WGRAD", "0") == "1"   # measured: no gain (33.2 vs 32.8 ms), opt-in
         rng_state = np.random.get_state()          # capture draws targets too: leave the caller's RNG stream untouched
 
         def host_targets(st, gt_host, info_host):
@@ -163,11 +166,12 @@ class _CapturedStep:
         side.wait_stream(cur)
         with torch.cuda.stream(side):              # warm-up outside capture: lazy workspaces, kernel attributes, PE tables
             for _ in range(2):
-                autograd_ops.set_direct_grads(sink, None)
+                autograd_ops.set_direct_grads(sink, None, fork_wgrad=fork)
                 st = self.tg.part1(self.stem, self.s_im, self.s_info, self.s_sup, self.anchors, self.stride)
                 a_t, smp = host_targets(st, gt_host, info_host)
                 out = self.tg.part2(st, [t.to(dev) for t in a_t], [t.to(dev) for t in smp])
                 (out[3] + out[4] + out[5] + out[6]).backward()
+                autograd_ops.join_forks()
                 autograd_ops.set_direct_grads(None, None)
         cur.wait_stream(side)
         torch.cuda.synchronize()
@@ -175,7 +179,7 @@ class _CapturedStep:
         self.s_sample = [t.to(dev) for t in smp]
         pool = torch.cuda.graph_pool_handle()
         self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        autograd_ops.set_direct_grads(sink, None)
+        autograd_ops.set_direct_grads(sink, None, fork_wgrad=fork)
         launches0 = ops.LAUNCHES
         try:
             with torch.cuda.graph(self.g1, pool=pool):
@@ -187,6 +191,7 @@ class _CapturedStep:
                 self.losses = out[3:7]
                 self.loss = out[3] + out[4] + out[5] + out[6]
                 self.loss.backward()
+                autograd_ops.join_forks()
         finally:
             autograd_ops.set_direct_grads(None, None)
         self.launches = ops.LAUNCHES - launches0       # own kernels recorded in the two graphs (replayed every step)
