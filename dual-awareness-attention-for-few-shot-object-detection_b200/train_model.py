@@ -27,6 +27,9 @@ from .config import cfg
 from .engine import BN_EPS, RES_LAYERS, _Block, positional_encoding
 
 
+SIDE_STREAM = True      # module switch: the support trunk may run on a side stream (see TrainGraph.part1)
+
+
 class _RoIAlignNHWC(torch.autograd.Function):
     """ROIAlign(7, 7, 1/16, 0) on an NHWC map (roi_layers/roi_align.py:12-45): forward and backward kernels."""
 
@@ -253,7 +256,7 @@ class TrainGraph:
                     name[:-len("0.weight")] + "1"
                 A._packed(w, self.bn(bn_name)[0], need_dgrad=True)
         cur = torch.cuda.current_stream()
-        use_side = os.environ.get("DANA_TRAIN_SIDE_STREAM", "1") != "0"
+        use_side = SIDE_STREAM and os.environ.get("DANA_TRAIN_SIDE_STREAM", "1") != "0"
         if use_side and self._side is None:
             self._side = torch.cuda.Stream(device=dev)
         side = self._side if use_side else cur

@@ -18,7 +18,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from . import autograd_ops, ops
+from . import autograd_ops, ops, train_model
 from .config import cfg
 
 
@@ -83,6 +83,7 @@ class ArenaGradAllReduce:
         self._pending = [self.arenas[ai].buckets[bi][1] - self.arenas[ai].buckets[bi][0] for ai, bi in self.order]
         self._work = [None] * len(self.order)
         self._next = 0
+        self._seen = set()
         for a in self.arenas:
             for _, p in a.named:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -93,10 +94,14 @@ class ArenaGradAllReduce:
         self._hooks = []
 
     def _on_grad(self, p):
+        # A parameter whose gradient is written by the direct sink (autograd_ops) is signalled by its last use AND,
+        # depending on the torch version, by the post-accumulate hook of its (gradient-less) AccumulateGrad node: the
+        # first signal counts
+        if id(p) in self._seen:
+            return
+        self._seen.add(id(p))
         k = self._bucket_of[id(p)]
         self._pending[k] -= 1
-        if self._pending[k] < 0:
-            raise RuntimeError("ArenaGradAllReduce: a gradient arrived twice after one arm()")
         # collectives must be issued in the same order on every rank: strictly in bucket order (as DDP does)
         while self._next < len(self.order) and self._pending[self._next] == 0:
             self._launch(self._next)
@@ -240,6 +245,9 @@ class SGDTrainer:
         self.groups = [(n, p) for a in self.arenas for n, p in a.named]
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.sync = ArenaGradAllReduce(self.arenas) if self.world > 1 else None
+        # eager + hook-launched collectives: a bucket's all-reduce is ordered after the CURRENT stream only, so the support
+        # trunk must not run its backward on a side stream there (the captured step reduces after the whole graph)
+        self._eager_side_stream = self.world == 1
         self.events = None               # optional: list receiving (name, CUDA event) marks of one step
         self._grad_of = {}               # id(param) -> its slice of the gradient arena (autograd_ops' direct sink)
         for a in self.arenas:
@@ -300,7 +308,11 @@ class SGDTrainer:
         # completion is signalled to the all-reduce like a post-accumulate hook would
         autograd_ops.set_direct_grads(lambda p: self._grad_of.get(id(p)),
                                       self.sync._on_grad if self.sync is not None else None)
-        out = self.net(im_data, im_info, gt_boxes, num_boxes, support_ims)
+        train_model.SIDE_STREAM = self._eager_side_stream
+        try:
+            out = self.net(im_data, im_info, gt_boxes, num_boxes, support_ims)
+        finally:
+            train_model.SIDE_STREAM = True
         losses = out[3:7]
         loss = losses[0].mean() + losses[1].mean() + losses[2].mean() + losses[3].mean()      # train.py:136-137
         self._mark("forward")
