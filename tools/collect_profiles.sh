@@ -19,6 +19,12 @@ cp $S/cisa_sweep.json $D/r02_cisa_sweep.json
 cp $S/episode_bench.txt $D/r02_episode_bench.txt
 cp $S/gpu_state.txt $D/r02_gpu_state.txt
 cp $S/pytest_gpu.txt $D/r02_pytest_gpu.txt
+: > $D/r02_train_bench_lines.jsonl
+for f in train_bench train_bench_eager train_bench_res50_bs4; do
+  [ -f $S/$f.log ] && tail -1 $S/$f.log >> $D/r02_train_bench_lines.jsonl
+done
+grep -A40 "GPU kernels" $S/train_profile.txt > $D/r02_train_profile.txt 2>/dev/null
+cp $S/bwd_bench.txt $D/r02_bwd_bench.txt 2>/dev/null
 cp $S/ncu_summary.md $D/r02_ncu_summary.md
 cp $S/ncu_*.metrics.txt $S/ncu_*.hot.txt $D/r02_ncu/ 2>/dev/null
 python tools/gemm_traffic.py $S/launches_mixed.csv mixed $D/r02_gemm_traffic_mixed.json > /dev/null

@@ -25,6 +25,12 @@ timeout 600 python tools/cisa_sweep.py --out $O/cisa_sweep.json > $O/cisa_sweep.
 timeout 900 ncu --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum --clock-control none -k regex:conv_gemm --csv --log-file $O/cisa_sweep_ncu.csv python tools/cisa_sweep.py --ncu-pass > $O/cisa_ncu.log 2>&1
 python tools/cisa_sweep.py --merge $O/cisa_sweep.json $O/cisa_sweep_ncu.csv > $O/cisa_merge.log 2>&1
 timeout 100 python tools/episode_bench.py > $O/episode_bench.txt 2>&1
+# training step (BASELINE configs[3]): captured and eager lines, kernel profile of one captured step, backward kernels alone
+timeout 300 python tools/train_bench.py --steps 20 > $O/train_bench.log 2>&1
+timeout 300 python tools/train_bench.py --steps 10 --eager > $O/train_bench_eager.log 2>&1
+timeout 300 python tools/train_bench.py --steps 10 --layers 50 --batch 4 --height 600 --width 1000 --shots 3 > $O/train_bench_res50_bs4.log 2>&1
+timeout 300 python tools/train_profile.py > $O/train_profile.txt 2>&1
+timeout 300 python tools/bwd_bench.py > $O/bwd_bench.txt 2>&1
 N="ncu --set full --clock-control none --import-source on"
 timeout 200 $N -k regex:roi_align7_kernel --launch-skip 2 -c 1 -o $O/ncu_roi_head16_mix python tools/roi_bench.py --iters 1 --only head16 > $O/ncu1.log 2>&1
 timeout 200 $N -k regex:roi_align7_bwd --launch-skip 1 -c 1 -o $O/ncu_roi_bwd python tools/roi_bench.py --iters 1 > $O/ncu2.log 2>&1
@@ -34,6 +40,9 @@ done
 timeout 200 $N -k regex:conv_gemm --launch-skip 3 -c 1 -o $O/ncu_gemm_rpn_f16 python tools/gemm_bench.py --only 7 --precision f16 --iters 1 > $O/ncu4.log 2>&1
 timeout 200 $N -k regex:conv_gemm --launch-skip 3 -c 1 -o $O/ncu_gemm_l1c2_dx3 python tools/gemm_bench.py --only 1 --precision bf16x3 --iters 1 > $O/ncu5.log 2>&1
 timeout 200 $N -k regex:conv_gemm --launch-skip 3 -c 1 -o $O/ncu_gemm_l1c3_x3 python tools/gemm_bench.py --only 2 --precision bf16x3 --iters 1 > $O/ncu6.log 2>&1
+timeout 200 $N -k regex:grad_prepare --launch-skip 2 -c 1 -o $O/ncu_bwd_grad_prepare python tools/bwd_bench.py --iters 1 --only 2 > $O/ncu7.log 2>&1
+timeout 200 $N -k regex:im2col_t --launch-skip 2 -c 1 -o $O/ncu_bwd_im2col_t python tools/bwd_bench.py --iters 1 --only 1 > $O/ncu8.log 2>&1
+timeout 200 $N -k regex:conv_gemm --launch-skip 3 -c 1 -o $O/ncu_bwd_wgrad_l3c2 python tools/bwd_bench.py --iters 1 --only 1 > $O/ncu9.log 2>&1
 # the .ncu-rep files (20 MB each with sources) do not fit the 64 MiB return channel: extract what profiles/ keeps
 python tools/ncu_summary.py $O/ncu_summary.md $O/*.ncu-rep > /dev/null 2>&1
 for r in $O/*.ncu-rep; do
