@@ -449,7 +449,16 @@ if __name__ == "__main__":
     ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--workload", default="forward", choices=["forward", "train"],
+                    help="forward: the headline (BASELINE configs[1]); train: the training step of configs[3] "
+                         "(res101, 800x1333, fwd + bwd + NCCL all-reduce + SGD) -- delegates to tools/train_bench.py")
     a = ap.parse_args()
+    if a.workload == "train":
+        import runpy
+        sys.argv = [os.path.join(ROOT, "tools", "train_bench.py"), "--gpus", str(a.gpus), "--steps", str(a.steps),
+                    "--warmup", str(max(a.warmup, 3))] + (["--eager"] if a.no_graph else [])
+        runpy.run_path(sys.argv[0], run_name="__main__")
+        sys.exit(0)
     if a.impl == "reference":
         run_reference(a)
     else:

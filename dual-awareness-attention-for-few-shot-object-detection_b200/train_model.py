@@ -85,6 +85,7 @@ class TrainGraph:
         self._bn = {}
         self._pe = {}
         self._side = None
+        self._side2 = None
 
     # ------------------------------------------------------------------ trunk
     def bn(self, name):
@@ -322,10 +323,36 @@ class TrainGraph:
         per = rois.shape[1]
         r = b * per
         pooled = _RoIAlignNHWC.apply(st["base"], rois.view(-1, 5).contiguous())     # [R,7,7,1024]
-        fc7 = self.head_to_tail(pooled)
-        bbox_pred = self.lin(fc7, "RCNN_bbox_pred")
-        sc_pos = self.rcnn_head(pooled, st["sup_pooled"][:, 0], per)                # dana.py:189-194
-        sc_neg = self.rcnn_head(pooled, st["sup_pooled"][:, 1], per)
+        # Three independent branches on the pooled RoIs -- layer4 + box regressor, the positive-set head pass, the
+        # negative-set head pass (dana.py:186-194) -- each a chain of small launches (128 RoIs x 49 bins): side by side on
+        # three streams, forward and (autograd follows the forward's streams) backward.  The weights the two head passes
+        # share are packed before the fork.
+        cur = torch.cuda.current_stream()
+        use_side = SIDE_STREAM and os.environ.get("DANA_TRAIN_SIDE_STREAM", "1") != "0"
+        if use_side:
+            for name in ("rcnn_adapt_q_layer", "rcnn_adapt_k_layer", "rcnn_transform_layer", "output_score_layer.linear1"):
+                w = self.p[name + ".weight"]
+                A._packed(w.view(w.shape[0], w.shape[1], 1, 1), None, need_dgrad=True)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=pooled.device)
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=pooled.device)
+            heads = []
+            for stream, set_index in ((self._side, 0), (self._side2, 1)):
+                stream.wait_stream(cur)
+                with torch.cuda.stream(stream):
+                    heads.append(self.rcnn_head(pooled, st["sup_pooled"][:, set_index], per))   # dana.py:189-194
+            fc7 = self.head_to_tail(pooled)
+            bbox_pred = self.lin(fc7, "RCNN_bbox_pred")
+            for stream, t in ((self._side, heads[0]), (self._side2, heads[1])):
+                cur.wait_stream(stream)
+                t.record_stream(cur)
+            sc_pos, sc_neg = heads
+        else:
+            fc7 = self.head_to_tail(pooled)
+            bbox_pred = self.lin(fc7, "RCNN_bbox_pred")
+            sc_pos = self.rcnn_head(pooled, st["sup_pooled"][:, 0], per)            # dana.py:189-194
+            sc_neg = self.rcnn_head(pooled, st["sup_pooled"][:, 1], per)
         cls_score = torch.cat([sc_pos, sc_neg], 0)
         cls_prob = F.softmax(cls_score.detach(), 1)
         labels = lab_s.view(-1).long()
