@@ -134,6 +134,16 @@ class _CapturedStep:
        in 84 ms), the captured one is not.  The all-reduce and the two SGD launches follow graph 2."""
 
     def __init__(self, trainer, im_data, im_info, gt_boxes, support_ims):
+        # parallel graph branches (the two trunks, the three head branches) on side streams; eager steps stay
+        # single-stream: their hook-launched collectives are ordered after the current stream only, and they are launch-bound
+        train_model.SIDE_STREAM = True
+        try:
+            self._build(trainer, im_data, im_info, gt_boxes, support_ims)
+        finally:
+            train_model.SIDE_STREAM = False
+            autograd_ops.set_direct_grads(None, None)
+
+    def _build(self, trainer, im_data, im_info, gt_boxes, support_ims):
         import numpy as np
 
         from .anchors import generate_anchors
@@ -245,9 +255,6 @@ class SGDTrainer:
         self.groups = [(n, p) for a in self.arenas for n, p in a.named]
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.sync = ArenaGradAllReduce(self.arenas) if self.world > 1 else None
-        # eager + hook-launched collectives: a bucket's all-reduce is ordered after the CURRENT stream only, so the support
-        # trunk must not run its backward on a side stream there (the captured step reduces after the whole graph)
-        self._eager_side_stream = self.world == 1
         self.events = None               # optional: list receiving (name, CUDA event) marks of one step
         self._grad_of = {}               # id(param) -> its slice of the gradient arena (autograd_ops' direct sink)
         for a in self.arenas:
@@ -308,11 +315,7 @@ class SGDTrainer:
         # completion is signalled to the all-reduce like a post-accumulate hook would
         autograd_ops.set_direct_grads(lambda p: self._grad_of.get(id(p)),
                                       self.sync._on_grad if self.sync is not None else None)
-        train_model.SIDE_STREAM = self._eager_side_stream
-        try:
-            out = self.net(im_data, im_info, gt_boxes, num_boxes, support_ims)
-        finally:
-            train_model.SIDE_STREAM = True
+        out = self.net(im_data, im_info, gt_boxes, num_boxes, support_ims)
         losses = out[3:7]
         loss = losses[0].mean() + losses[1].mean() + losses[2].mean() + losses[3].mean()      # train.py:136-137
         self._mark("forward")
