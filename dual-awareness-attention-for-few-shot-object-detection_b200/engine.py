@@ -389,6 +389,17 @@ class DanaEngine:
         self._mark("start")
         qh, qw = self._trunk_hw(im_data.shape[2], im_data.shape[3])
         nq = qh * qw
+        # the support trunk on the side stream next to the query trunk (DANA_TRUNK_SIDE=0: off), so that one
+        # layer's tail wave overlaps the other trunk's next launch: 739 -> 787 images/s (mixed), 620 -> 649 (bf16x3)
+        sup_early = None
+        trunk_side = (os.environ.get("DANA_TRUNK_SIDE", "1") != "0" and support_feats is None and self.stage_events is None
+                      and ops.GEMM_TRACE is None)
+        if trunk_side:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                sup_early = self.encode_supports(support_ims)
         if self.f16:
             # the RPN input [base | dense] is one fp16 plane; the trunk keeps its own bf16-pair output (the q-projection
             # and RoIAlign read it at full precision)
@@ -401,7 +412,13 @@ class DanaEngine:
             base = self.trunk(im_data.float().contiguous(), out=corr[..., :1024])
             dense_out = Pair(corr.hi.view(b * nq, 2048)[:, 1024:],
                              None if corr.lo is None else corr.lo.view(b * nq, 2048)[:, 1024:])
-        sup = support_feats if support_feats is not None else self.encode_supports(support_ims)
+        if sup_early is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+            sup_early.hi.record_stream(torch.cuda.current_stream())
+            if sup_early.lo is not None:
+                sup_early.lo.record_stream(torch.cuda.current_stream())
+        sup = support_feats if support_feats is not None else (sup_early if sup_early is not None else
+                                                               self.encode_supports(support_ims))
         maps, sh, sw, c = sup.hi.shape
         if sh != sw:
             raise ValueError("support feature maps must be square (got %dx%d): AvgPool2d(%d) of dana.py:42 assumes "
