@@ -199,8 +199,36 @@ class DanaEngine:
         `out` optionally receives the last block's output (e.g. a channel slice of the RPN input).
         DANA_TRUNK_CHUNK=n (experiment): depth-first over chunks of n images, so that a chunk's layer1/2
         activations (38 MB per 600x1000 image at 256 channels) stay L2-resident between consecutive layers."""
-        chunk = int(os.environ.get("DANA_TRUNK_CHUNK", "0"))
         n = im_nchw.shape[0]
+        nstreams = int(os.environ.get("DANA_TRUNK_STREAMS", "1"))
+        if nstreams > 1 and n >= nstreams and self.stage_events is None and ops.GEMM_TRACE is None:
+            # experiment: the batch in `nstreams` chunks on as many streams (tail waves of one chunk's layer overlap the
+            # other chunk's launches)
+            if out is None:
+                qh, qw = self._trunk_hw(im_nchw.shape[2], im_nchw.shape[3])
+                out = Pair.empty((n, qh, qw, 1024), self.device, self.split)
+            cur = torch.cuda.current_stream()
+            if not hasattr(self, "_tstreams"):
+                self._tstreams = {}
+            key = cur.cuda_stream
+            if key not in self._tstreams:
+                self._tstreams[key] = [torch.cuda.Stream(device=self.device) for _ in range(nstreams - 1)]
+            per = (n + nstreams - 1) // nstreams
+            for j in range(nstreams):
+                i0, i1 = j * per, min(n, (j + 1) * per)
+                if i0 >= i1:
+                    break
+                if j == 0:
+                    self._trunk(im_nchw[i0:i1], out=out[i0:i1])
+                else:
+                    st = self._tstreams[key][j - 1]
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        self._trunk(im_nchw[i0:i1], out=out[i0:i1])
+            for st in self._tstreams[key]:
+                cur.wait_stream(st)
+            return out
+        chunk = int(os.environ.get("DANA_TRUNK_CHUNK", "0"))
         if chunk > 0 and n > chunk:
             if out is None:
                 qh, qw = self._trunk_hw(im_nchw.shape[2], im_nchw.shape[3])
