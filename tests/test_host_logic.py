@@ -390,3 +390,48 @@ def test_pretrained_trunk_load(tmp_path):
     bad.model_path = path
     with pytest.raises(RuntimeError):
         bad.create_architecture()
+
+
+# ------------------------------------------------------------------ training losses in their static-shape form (row a15)
+def test_static_shape_losses_match_oracle():
+    """train_model.TrainGraph's loss expressions -- written with 0 / 1 weights and device-side ranks instead of
+    index_select, so that the step can be captured into a CUDA graph -- against the oracle's index-based restatement
+    of rpn.py:96-116 and dana.py:199-215 (values AND gradients), including no-foreground, few-background and
+    more-foreground-than-quota cases."""
+    import train_oracle as T
+    from dana_b200.train_model import TrainGraph
+    rs = np.random.RandomState(11)
+    tg = TrainGraph({}, num_layers=50)
+    # RPN losses: NHWC raw head output [B,H,W,6A] vs the oracle's NCHW layouts
+    b, h, w, a = 2, 7, 9, 12
+    raw = torch.from_numpy(rs.standard_normal((b, h, w, 6 * a)).astype(np.float32)).requires_grad_(True)
+    labels = torch.from_numpy(rs.choice([-1, 0, 1], size=(b, h * w * a), p=[0.7, 0.2, 0.1]).astype(np.int8))
+    tgt = torch.from_numpy(rs.standard_normal((b, h * w * a, 4)).astype(np.float32)) * 0.3
+    in_w = (labels == 1).float()
+    out_w = (labels >= 0).float() / 41.0
+    got = tg.rpn_losses(raw, (labels, tgt, in_w, out_w), a)
+    (got[0] + got[1]).backward()
+    g_got = raw.grad.clone()
+    raw2 = raw.detach().clone().requires_grad_(True)
+    nchw = raw2.permute(0, 3, 1, 2)
+    o_lab = labels.view(b, h, w, a).permute(0, 3, 1, 2).reshape(b, 1, a * h, w).float()
+    to4 = lambda t: t.view(b, h, w, a, 1).expand(b, h, w, a, 4).reshape(b, h, w, 4 * a).permute(0, 3, 1, 2)  # noqa: E731
+    want = T.rpn_losses(nchw[:, :2 * a].contiguous(), nchw[:, 2 * a:].contiguous(),
+                        (o_lab, tgt.view(b, h, w, 4 * a).permute(0, 3, 1, 2), to4(in_w), to4(out_w)), a)
+    (want[0] + want[1]).backward()
+    assert abs(float(got[0].detach()) - float(want[0].detach())) <= 1e-6 * abs(float(want[0].detach()))
+    assert abs(float(got[1].detach()) - float(want[1].detach())) <= 1e-6 * abs(float(want[1].detach()))
+    assert torch.allclose(g_got, raw2.grad, rtol=1e-5, atol=1e-8)
+    # R-CNN classification loss with hard-negative mining
+    for r, n_fg in ((128, 20), (128, 0), (64, 50), (256, 3), (8, 1)):
+        scores = torch.from_numpy(rs.standard_normal((2 * r, 2)).astype(np.float32)).requires_grad_(True)
+        lab = torch.zeros(r)
+        lab[torch.from_numpy(rs.permutation(r)[:n_fg].copy())] = 1
+        lab_all = torch.cat([lab, torch.zeros(r)]).long()
+        got = TrainGraph.rcnn_cls_loss(scores, lab_all)
+        got.backward()
+        s2 = scores.detach().clone().requires_grad_(True)
+        want = T.rcnn_cls_loss(s2, lab_all)
+        want.backward()
+        assert abs(float(got.detach()) - float(want.detach())) <= 1e-6 * abs(float(want.detach())), (r, n_fg)
+        assert torch.allclose(scores.grad, s2.grad, rtol=1e-5, atol=1e-8), (r, n_fg)
