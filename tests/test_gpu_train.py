@@ -152,7 +152,7 @@ def test_train_backward_vs_oracle_and_reference_golden(train_ref, golden_dir):
     losses = out[3:7]
     want = [float(ref[k]) for k in ("rpn_loss_cls", "rpn_loss_box", "RCNN_loss_cls", "RCNN_loss_bbox")]
     for g, w in zip(losses, want):
-        assert abs(float(g) - w) <= 2e-4 * abs(w), ([float(v) for v in losses], want)
+        assert abs(float(g.detach()) - w) <= 2e-4 * abs(w), ([float(v.detach()) for v in losses], want)
     (losses[0].mean() + losses[1].mean() + losses[2].mean() + losses[3].mean()).backward()
 
     named = dict(net.named_parameters())
