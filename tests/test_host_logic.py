@@ -435,3 +435,34 @@ def test_static_shape_losses_match_oracle():
         want.backward()
         assert abs(float(got.detach()) - float(want.detach())) <= 1e-6 * abs(float(want.detach())), (r, n_fg)
         assert torch.allclose(scores.grad, s2.grad, rtol=1e-5, atol=1e-8), (r, n_fg)
+
+
+@pytest.mark.parametrize("bucket_bytes", [1, 200, 4096, 1 << 30])
+def test_param_arena_layout(bucket_bytes):
+    """ParamArena (train_step.py): every parameter and gradient becomes a 16-byte aligned slice of one flat buffer with
+    its values intact; the buckets are contiguous ranges of whole tensors that tile the arena exactly once."""
+    from dana_b200.train_step import ParamArena
+    torch.manual_seed(1)
+    shapes = [(7, 3), (5,), (64, 9), (1,), (33, 2, 3, 3), (4,)]
+    params = [("p%d" % i, torch.nn.Parameter(torch.randn(*s))) for i, s in enumerate(shapes)]
+    before = [p.detach().clone() for _, p in params]
+    arena = ParamArena(params, 0.1, 0.0, bucket_bytes)
+    covered = 0
+    for (i0, i1, begin, end) in arena.buckets:
+        assert i1 > i0 and begin == covered and begin % 4 == 0 and end % 4 == 0
+        assert begin == arena.offsets[i0]
+        last = arena.offsets[i1 - 1] + (params[i1 - 1][1].numel() + 3) // 4 * 4
+        assert end == last
+        covered = end
+    assert covered == arena.total and sum(i1 - i0 for i0, i1, _, _ in arena.buckets) == len(params)
+    for (_, p), b, off in zip(params, before, arena.offsets):
+        assert torch.equal(p.detach(), b) and off % 4 == 0
+        assert p.data_ptr() == arena.param.data_ptr() + 4 * off and p.grad.data_ptr() == arena.grad.data_ptr() + 4 * off
+    # a step's worth of autograd accumulates in place, and rebind_grads repairs a dropped .grad
+    loss = sum((p * p).sum() for _, p in params)
+    loss.backward()
+    for (_, p), off in zip(params, arena.offsets):
+        assert torch.allclose(arena.grad[off:off + p.numel()].view(p.shape), 2 * p.detach())
+    params[2][1].grad = None
+    arena.rebind_grads()
+    assert params[2][1].grad.data_ptr() == arena.grad.data_ptr() + 4 * arena.offsets[2]
